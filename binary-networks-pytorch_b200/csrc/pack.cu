@@ -1,0 +1,202 @@
+// pack.cu -- the two binarizers of the reference as bit-pack kernels.
+//
+//   bnn_pack_act_f32     BasicInputBinarizer / SignActivation.forward
+//                        (reference bnn/ops.py:151-152, 63-66)
+//   bnn_pack_weight_f32  XNORWeightBinarizer.forward (reference bnn/ops.py:116-140)
+//
+// Both are HBM-streaming kernels: the activation pack reads 4 B/element once,
+// coalesced along w, and writes 2 bits/element; the weight pack runs once at
+// prepare time.
+#include "common.cuh"
+
+namespace bnn {
+
+// ---------------------------------------------------------------------------
+// activations: fp32 (element strides) -> abits[n][chunk][h][w] + cnt[n][h][w]
+// one thread = one (n, chunk, h, w) unit = 64 channels of one pixel; adjacent
+// lanes are adjacent w, so every one of the 64 loads of a warp is one 128-B line
+// for NCHW input.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pack_act_kernel(const float* __restrict__ x, long long sn, long long sc, long long sh, long long sw,
+                int N, int C, int H, int W, int nch, uint4* __restrict__ abits,
+                uint32_t* __restrict__ cnt) {
+    const long long total = (long long)N * nch * H * W;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int w = (int)(idx % W);
+    long long r = idx / W;
+    const int h = (int)(r % H);
+    r /= H;
+    const int ch = (int)(r % nch);
+    const int n = (int)(r / nch);
+
+    const float* base = x + n * sn + h * sh + w * sw + (long long)ch * 64 * sc;
+    const int cmax = min(64, C - ch * 64);
+    uint32_t s[2] = {0u, 0u}, m[2] = {0u, 0u};
+    if (cmax == 64) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+            for (int b0 = 0; b0 < 32; b0 += 16) {
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __ldg(base + (long long)(half * 32 + b0 + i) * sc);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const uint32_t pos = v[i] > 0.0f, neg = v[i] < 0.0f;  // NaN, +-0 -> neither
+                    s[half] |= pos << (b0 + i);
+                    m[half] |= (pos | neg) << (b0 + i);
+                }
+            }
+        }
+    } else {
+        for (int b = 0; b < cmax; ++b) {
+            const float v = __ldg(base + (long long)b * sc);
+            const uint32_t pos = v > 0.0f, neg = v < 0.0f;
+            s[b >> 5] |= pos << (b & 31);
+            m[b >> 5] |= (pos | neg) << (b & 31);
+        }
+    }
+    abits[idx] = make_uint4(s[0], s[1], m[0], m[1]);
+    const uint32_t c = __popc(m[0]) + __popc(m[1]);
+    uint32_t* dst = cnt + ((long long)n * H + h) * W + w;
+    if (nch == 1) *dst = c;
+    else atomicAdd(dst, c);  // cnt zeroed by the launcher; integer adds commute
+}
+
+// ---------------------------------------------------------------------------
+// weights: one CTA per output channel.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum(double v, double* scratch) {
+    // deterministic: fixed shuffle tree, then warp partials added in warp order
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    double tot = 0.0;
+    for (int i = 0; i < nw; ++i) tot += scratch[i];
+    return tot;
+}
+
+__global__ void __launch_bounds__(128)
+pack_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, int nch,
+                   int center, int compute_alpha, uint32_t* __restrict__ wbits,
+                   float* __restrict__ alpha, int* __restrict__ n_zero) {
+    extern __shared__ double sm_d[];
+    double* scratch = sm_d;                                 // [4]
+    float* mean = reinterpret_cast<float*>(sm_d + 4);       // [taps]
+    const int co = blockIdx.x;
+    const float* wc = w + (long long)co * Cin * taps;
+    const int nk = nch * taps;
+
+    // mean over c_in per tap (reference ops.py:130-132), summed in fp64, rounded once
+    for (int t = 0; t < taps; ++t) {
+        double part = 0.0;
+        if (center)
+            for (int ci = threadIdx.x; ci < Cin; ci += blockDim.x) part += (double)wc[(long long)ci * taps + t];
+        const double tot = center ? block_sum(part, scratch) : 0.0;
+        if (threadIdx.x == 0) mean[t] = center ? (float)(tot / (double)Cin) : 0.0f;
+    }
+    __syncthreads();
+
+    // alpha = mean |centred w| over (c_in, kh, kw)  (ops.py:116-123)
+    if (compute_alpha) {
+        double part = 0.0;
+        const int per_out = Cin * taps;
+        for (int i = threadIdx.x; i < per_out; i += blockDim.x) {
+            const float v = center ? wc[i] - mean[i % taps] : wc[i];
+            part += fabs((double)v);
+        }
+        const double tot = block_sum(part, scratch);
+        if (threadIdx.x == 0) alpha[co] = (float)(tot / (double)per_out);
+    } else if (threadIdx.x == 0) {
+        alpha[co] = 1.0f;
+    }
+
+    // sign bits: item = (kstep, word) -> 32 channels
+    int zeros = 0;
+    for (int item = threadIdx.x; item < nk * 2; item += blockDim.x) {
+        const int ks = item >> 1, word = item & 1;
+        const int ch = ks / taps, t = ks - ch * taps;
+        uint32_t bits = 0u;
+        for (int b = 0; b < 32; ++b) {
+            const int ci = ch * 64 + word * 32 + b;
+            if (ci >= Cin) break;
+            const float raw = wc[(long long)ci * taps + t];
+            const float v = center ? raw - mean[t] : raw;
+            const bool pos = v > 0.0f, neg = v < 0.0f;
+            bits |= (uint32_t)pos << b;
+            zeros += (!pos && !neg);
+        }
+        wbits[((((long long)(co >> 5) * nk + ks) * 32) + (co & 31)) * 2 + word] = bits;
+    }
+    if (n_zero != nullptr) {
+        for (int o = 16; o > 0; o >>= 1) zeros += __shfl_down_sync(0xffffffffu, zeros, o);
+        if ((threadIdx.x & 31) == 0 && zeros) atomicAdd(n_zero, zeros);
+    }
+}
+
+}  // namespace bnn
+
+using namespace bnn;
+
+extern "C" size_t bnn_act_bits_bytes(int32_t n, int32_t c, int32_t h, int32_t w) {
+    if (n <= 0 || c <= 0 || h <= 0 || w <= 0) return 0;
+    return (size_t)n * ((c + 63) / 64) * h * w * 16;
+}
+extern "C" size_t bnn_act_cnt_bytes(int32_t n, int32_t h, int32_t w) {
+    if (n <= 0 || h <= 0 || w <= 0) return 0;
+    return (size_t)n * h * w * 4;
+}
+extern "C" size_t bnn_weight_bits_bytes(int32_t c_out, int32_t c_in, int32_t kh, int32_t kw) {
+    if (c_out <= 0 || c_in <= 0 || kh <= 0 || kw <= 0) return 0;
+    return (size_t)((c_out + 31) / 32) * ((c_in + 63) / 64) * kh * kw * 32 * 8;
+}
+
+extern "C" int bnn_pack_act_f32(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw,
+                                int32_t n, int32_t c, int32_t h, int32_t w, void* abits,
+                                uint32_t* cnt, void* stream_) {
+    if (!x || !abits || !cnt) return BNN_E_NULL;
+    if (n <= 0 || c <= 0 || h <= 0 || w <= 0) return BNN_E_SHAPE;
+    if (((uintptr_t)abits & 15) != 0) return BNN_E_ALIGN;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int nch = (c + 63) / 64;
+    int launches = 1;
+    if (nch > 1) {
+        cudaError_t e = cudaMemsetAsync(cnt, 0, (size_t)n * h * w * 4, stream);
+        if (e != cudaSuccess) return (int)e;
+    }
+    const long long total = (long long)n * nch * h * w;
+    const int threads = 256;
+    const long long blocks = (total + threads - 1) / threads;
+    if (blocks > 0x7fffffffLL) return BNN_E_UNSUPPORTED;
+    pack_act_kernel<<<(unsigned)blocks, threads, 0, stream>>>(x, sn, sc, sh, sw, n, c, h, w, nch,
+                                                            (uint4*)abits, cnt);
+    count_launch(launches);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int bnn_pack_weight_f32(const float* w, int32_t c_out, int32_t c_in, int32_t kh, int32_t kw,
+                                   int32_t center, int32_t compute_alpha, void* wbits, float* alpha,
+                                   int32_t* n_zero, void* stream_) {
+    if (!w || !wbits || !alpha) return BNN_E_NULL;
+    if (c_out <= 0 || c_in <= 0 || kh <= 0 || kw <= 0) return BNN_E_SHAPE;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    cudaError_t e;
+    // padded output channels / channels beyond c_in keep all-zero bits
+    e = cudaMemsetAsync(wbits, 0, bnn_weight_bits_bytes(c_out, c_in, kh, kw), stream);
+    if (e != cudaSuccess) return (int)e;
+    if (n_zero) {
+        e = cudaMemsetAsync(n_zero, 0, sizeof(int32_t), stream);
+        if (e != cudaSuccess) return (int)e;
+    }
+    const int taps = kh * kw, nch = (c_in + 63) / 64;
+    const size_t smem = 4 * sizeof(double) + (size_t)taps * sizeof(float);
+    if (smem > 48 * 1024) return BNN_E_UNSUPPORTED;
+    pack_weight_kernel<<<c_out, 128, smem, stream>>>(w, c_out, c_in, taps, nch, center, compute_alpha,
+                                                     (uint32_t*)wbits, alpha, n_zero);
+    count_launch(1);
+    return (int)cudaGetLastError();
+}

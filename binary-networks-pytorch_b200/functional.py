@@ -1,0 +1,145 @@
+"""Tensor-level wrappers over the C ABI: allocate outputs with torch, pass raw pointers and the
+current CUDA stream.  torch is plumbing here (device memory + streams); all arithmetic of the
+binarized path happens in the kernels of csrc/.
+"""
+import ctypes
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import native
+from .native import ConvGeom
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _require_cuda_f32(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise native.NativeError(f"{name} must be a CUDA tensor (got {t.device}); the B200 path has no CPU fallback")
+    if t.dtype != torch.float32:
+        raise native.NativeError(f"{name} must be float32 (got {t.dtype})")
+
+
+@dataclass
+class PackedActivations:
+    """Sign/mask planes of one activation tensor (layout: include/bnn_b200.h)."""
+    bits: torch.Tensor   # int32 [n, chunks, h, w, 4]
+    cnt: torch.Tensor    # int32 [n, h, w]
+    n: int
+    c: int
+    h: int
+    w: int
+
+
+@dataclass
+class PackedWeights:
+    """Sign planes + XNOR alpha of one weight tensor."""
+    bits: torch.Tensor       # int32 [c_out/32, ksteps, 32, 2]
+    alpha: torch.Tensor      # float32 [c_out]
+    n_zero: int              # exactly-zero (centred) weights: must be 0 for the packed path
+    c_out: int
+    c_in: int
+    kh: int
+    kw: int
+
+
+def pack_activations(x: torch.Tensor, linear_rows: bool = False) -> PackedActivations:
+    """``BasicInputBinarizer`` (reference bnn/ops.py:151-152) as a bit-pack.
+
+    ``x`` is [n,c,h,w] (any strides) or, with ``linear_rows``, [rows, features] which is packed
+    as n=1, h=1, w=rows so that ``blinear`` can treat rows as pixels."""
+    _require_cuda_f32(x, "input")
+    if linear_rows:
+        rows, feat = x.shape
+        n, c, h, w = 1, feat, 1, rows
+        sn, sc, sh, sw = 0, x.stride(1), 0, x.stride(0)
+    else:
+        n, c, h, w = x.shape
+        sn, sc, sh, sw = x.stride()
+    nch = (c + 63) // 64
+    with torch.cuda.device(x.device):
+        bits = torch.empty((n, nch, h, w, 4), dtype=torch.int32, device=x.device)
+        cnt = torch.empty((n, h, w), dtype=torch.int32, device=x.device)
+        rc = native.lib().bnn_pack_act_f32(x.data_ptr(), sn, sc, sh, sw, n, c, h, w, bits.data_ptr(),
+                                           cnt.data_ptr(), _stream_ptr(x.device))
+    native.check(rc, "bnn_pack_act_f32")
+    return PackedActivations(bits, cnt, n, c, h, w)
+
+
+def pack_weights(weight: torch.Tensor, center_weights: bool, compute_alpha: bool) -> PackedWeights:
+    """``XNORWeightBinarizer`` (reference bnn/ops.py:129-140) as a prepare-time pack."""
+    _require_cuda_f32(weight, "weight")
+    w = weight.detach().contiguous()
+    if w.dim() == 2:
+        c_out, c_in, kh, kw = w.shape[0], w.shape[1], 1, 1
+    elif w.dim() == 3:
+        c_out, c_in, kh, kw = w.shape[0], w.shape[1], 1, w.shape[2]
+    elif w.dim() == 4:
+        c_out, c_in, kh, kw = w.shape
+    else:
+        raise ValueError(f"Expected ndims equal with 2 or 4, but found {w.dim()}")
+    nk = ((c_in + 63) // 64) * kh * kw
+    with torch.cuda.device(w.device):
+        bits = torch.empty(((c_out + 31) // 32, nk, 32, 2), dtype=torch.int32, device=w.device)
+        alpha = torch.empty((c_out,), dtype=torch.float32, device=w.device)
+        nz = torch.zeros((1,), dtype=torch.int32, device=w.device)
+        rc = native.lib().bnn_pack_weight_f32(w.data_ptr(), c_out, c_in, kh, kw, int(center_weights),
+                                              int(compute_alpha), bits.data_ptr(), alpha.data_ptr(),
+                                              nz.data_ptr(), _stream_ptr(w.device))
+    native.check(rc, "bnn_pack_weight_f32")
+    return PackedWeights(bits, alpha, int(nz.item()), c_out, c_in, kh, kw)
+
+
+def _opt_ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def bconv2d(act: PackedActivations, wts: PackedWeights, bias: Optional[torch.Tensor] = None,
+            post: Optional[torch.Tensor] = None, stride: Tuple[int, int] = (1, 1),
+            padding: Tuple[int, int] = (0, 0), dilation: Tuple[int, int] = (1, 1),
+            use_alpha: bool = True, flags: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Packed binary convolution + fused ``(alpha*dot + bias) * post`` epilogue -> fp32 NCHW."""
+    if act.c != wts.c_in:
+        raise native.NativeError(f"channel mismatch: activations {act.c}, weights {wts.c_in}")
+    geom = ConvGeom(act.n, act.c, act.h, act.w, wts.c_out, wts.kh, wts.kw, stride[0], stride[1],
+                    padding[0], padding[1], dilation[0], dilation[1])
+    ho = (act.h + 2 * padding[0] - dilation[0] * (wts.kh - 1) - 1) // stride[0] + 1
+    wo = (act.w + 2 * padding[1] - dilation[1] * (wts.kw - 1) - 1) // stride[1] + 1
+    if ho <= 0 or wo <= 0:
+        raise native.NativeError(f"empty output ({ho}x{wo})")
+    dev = act.bits.device
+    with torch.cuda.device(dev):
+        if out is None:
+            out = torch.empty((act.n, wts.c_out, ho, wo), dtype=torch.float32, device=dev)
+        on, oc, oh, ow = out.stride()
+        rc = native.lib().bnn_bconv2d_fwd(act.bits.data_ptr(), act.cnt.data_ptr(), wts.bits.data_ptr(),
+                                          wts.alpha.data_ptr() if use_alpha else None, _opt_ptr(bias),
+                                          _opt_ptr(post), out.data_ptr(), on, oc, oh, ow, ctypes.byref(geom),
+                                          flags, _stream_ptr(dev))
+    native.check(rc, "bnn_bconv2d_fwd")
+    return out
+
+
+def blinear(act: PackedActivations, wts: PackedWeights, bias: Optional[torch.Tensor] = None,
+            post: Optional[torch.Tensor] = None, use_alpha: bool = True, flags: int = 0) -> torch.Tensor:
+    """Packed binary linear layer: activations packed with ``linear_rows=True`` -> [rows, out]."""
+    rows = act.w
+    dev = act.bits.device
+    with torch.cuda.device(dev):
+        out = torch.empty((rows, wts.c_out), dtype=torch.float32, device=dev)
+        rc = native.lib().bnn_blinear_fwd(act.bits.data_ptr(), act.cnt.data_ptr(), wts.bits.data_ptr(),
+                                          wts.alpha.data_ptr() if use_alpha else None, _opt_ptr(bias),
+                                          _opt_ptr(post), out.data_ptr(), rows, act.c, wts.c_out, flags,
+                                          _stream_ptr(dev))
+    native.check(rc, "bnn_blinear_fwd")
+    return out
+
+
+def ubench(which: int, iters: int = 200) -> float:
+    """Integer-pipe micro-benchmark (giga warp-lane operations / s), see include/bnn_b200.h."""
+    v = ctypes.c_double(0.0)
+    native.check(native.lib().bnn_ubench(which, iters, ctypes.byref(v)), "bnn_ubench")
+    return float(v.value)

@@ -1,0 +1,84 @@
+"""ctypes binding of the C-ABI library ``csrc/libbnn_b200.so`` (see include/bnn_b200.h).
+
+There is no fallback: if the library is missing or a call fails, ``NativeError`` is raised.
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint32, c_void_p, POINTER
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libbnn_b200.so")
+
+F_STAGE_LDG = 1
+F_NO_CSA = 2
+Q_ABI_VERSION, Q_SM_ARCH, Q_DEVICE_SMS, Q_LAUNCH_COUNT = 0, 1, 2, 3
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+class ConvGeom(ctypes.Structure):
+    """``struct bnn_conv_geom`` (include/bnn_b200.h)."""
+    _fields_ = [(k, c_int32) for k in (
+        "n", "c_in", "h", "w", "c_out", "kh", "kw", "stride_h", "stride_w", "pad_h", "pad_w", "dil_h", "dil_w")]
+
+
+_SIGNATURES = {
+    "bnn_query": (c_int, [c_int, POINTER(c_int64)]),
+    "bnn_strerror": (c_char_p, [c_int]),
+    "bnn_act_bits_bytes": (c_size_t, [c_int32] * 4),
+    "bnn_act_cnt_bytes": (c_size_t, [c_int32] * 3),
+    "bnn_weight_bits_bytes": (c_size_t, [c_int32] * 4),
+    "bnn_pack_act_f32": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32,
+                                 c_void_p, c_void_p, c_void_p]),
+    "bnn_pack_weight_f32": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                    c_void_p, c_void_p, c_void_p, c_void_p]),
+    "bnn_bconv2d_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_int64, c_int64, c_int64, c_int64, POINTER(ConvGeom), c_uint32, c_void_p]),
+    "bnn_blinear_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_int32, c_int32, c_int32, c_uint32, c_void_p]),
+    "bnn_ubench": (c_int, [c_int32, c_int32, POINTER(c_double)]),
+}
+
+_lib = None
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def lib() -> ctypes.CDLL:
+    """Load (once) and return the library; raises NativeError if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C binary-networks-pytorch_b200/csrc`). There is no non-CUDA fallback.")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def available() -> bool:
+    return os.path.exists(LIB_PATH)
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        msg = lib().bnn_strerror(code)
+        raise NativeError(f"{what} failed with code {code}: {msg.decode() if msg else '?'}")
+
+
+def query(what: int) -> int:
+    v = c_int64(0)
+    check(lib().bnn_query(what, ctypes.byref(v)), "bnn_query")
+    return int(v.value)
+
+
+def launch_count() -> int:
+    return query(Q_LAUNCH_COUNT)

@@ -1,0 +1,137 @@
+/*
+ * bnn_b200.h -- C ABI of the B200-native binary-convolution forward path.
+ *
+ * This is the drop-in boundary for the hot path of 1adrianb/binary-networks-pytorch
+ * (`bnn` 0.1.2): everything a binarized `bnn.layers.Conv2d` / `Linear` does in
+ * `forward` (reference bnn/layers/conv.py:90-97, bnn/layers/linear.py:22-27) is
+ * reachable through the five compute entry points below.  The reference has no
+ * FFI of its own (it is pure Python over torch); the binding a maintainer adds
+ * is the ctypes stub shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is DEVICE memory owned by the
+ *     caller unless stated otherwise; no allocation, no hidden global state
+ *     besides a lazily resolved driver entry point, no device synchronisation;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - return value: 0 = ok, >0 = cudaError_t, <0 = BNN_E_* argument error;
+ *     `bnn_strerror` renders either;
+ *   - re-entrant across streams and devices (one call = current device, one stream).
+ *
+ * Packed layouts (shared with oracle/bnn_oracle.c)
+ *   activation planes  abits[n][chunk][h][w]  = {s_lo, s_hi, m_lo, m_hi}  4 x u32 (16 B)
+ *       chunk = 64 input channels; s bit <=> x > 0; m bit <=> x != 0 (false for +-0, NaN):
+ *       the reference's sign() is ternary (bnn/ops.py:66), and zero padding is applied
+ *       after binarisation (bnn/layers/conv.py:91-92) -- padded taps simply have m = 0.
+ *   non-zero count     cnt[n][h][w]           u32, number of m bits of that pixel
+ *   weight planes      wbits[c_out/32][kstep][c_out%32][2]  u32,
+ *       kstep = (chunk*kh + i)*kw + j, word 0/1 = channels chunk*64 + 0..31 / 32..63,
+ *       bit <=> centred weight > 0 (bnn/ops.py:130-136)
+ *   dot[n,co,ho,wo] = sum_taps cnt - 2 * sum_k popc(m & (s ^ t))
+ *   y = (scale[co]*dot + bias[co]) * post[co]          (conv.py:92-97, ops.py:136,202)
+ */
+#ifndef BNN_B200_H
+#define BNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BNN_B200_ABI_VERSION 1
+
+/* argument errors (negative); positive codes are cudaError_t */
+#define BNN_E_NULL        (-1)  /* required pointer is NULL                         */
+#define BNN_E_SHAPE       (-2)  /* non-positive / inconsistent dimension            */
+#define BNN_E_UNSUPPORTED (-3)  /* geometry does not fit this build (smem, box)      */
+#define BNN_E_DRIVER      (-4)  /* cuTensorMapEncodeTiled unavailable or failed      */
+#define BNN_E_ALIGN       (-5)  /* pointer not 16-byte aligned                       */
+
+/* Geometry of one binarized convolution; mirrors torch.nn.Conv2d's attributes
+ * read by bnn.layers.Conv2d.from_module (bnn/layers/conv.py:107-110); groups == 1. */
+typedef struct bnn_conv_geom {
+    int32_t n, c_in, h, w;        /* input  [n, c_in, h, w]                 */
+    int32_t c_out, kh, kw;        /* weight [c_out, c_in, kh, kw]           */
+    int32_t stride_h, stride_w;
+    int32_t pad_h, pad_w;         /* zero padding, applied AFTER sign()     */
+    int32_t dil_h, dil_w;
+} bnn_conv_geom;
+
+/* bnn_query selectors */
+#define BNN_Q_ABI_VERSION   0
+#define BNN_Q_SM_ARCH       1   /* 100 => compiled for sm_100a                */
+#define BNN_Q_DEVICE_SMS    2   /* multiprocessor count of the current device */
+#define BNN_Q_LAUNCH_COUNT  3   /* kernels launched by this library so far (process-wide) */
+
+/* flags for bnn_bconv2d_fwd / bnn_blinear_fwd */
+#define BNN_F_STAGE_LDG   1u    /* stage tiles with plain loads instead of TMA (debug / A-B) */
+#define BNN_F_NO_CSA      2u    /* force the one-POPC-per-word inner loop                     */
+
+int         bnn_query(int what, int64_t *value);
+const char *bnn_strerror(int code);
+
+/* sizes (bytes) of the packed buffers the caller must allocate */
+size_t bnn_act_bits_bytes(int32_t n, int32_t c, int32_t h, int32_t w);
+size_t bnn_act_cnt_bytes(int32_t n, int32_t h, int32_t w);
+size_t bnn_weight_bits_bytes(int32_t c_out, int32_t c_in, int32_t kh, int32_t kw);
+
+/*
+ * BasicInputBinarizer / SignActivation.forward (bnn/ops.py:151-152, 63-66) as a
+ * bit-pack: fp32 activations, addressed with ELEMENT strides (so NCHW,
+ * channels_last and Linear's [rows,in] viewed as n=1,h=1,w=rows all fit),
+ * -> abits + cnt.  abits must be 16-byte aligned.
+ */
+int bnn_pack_act_f32(const float *x, int64_t stride_n, int64_t stride_c, int64_t stride_h,
+                     int64_t stride_w, int32_t n, int32_t c, int32_t h, int32_t w,
+                     void *abits, uint32_t *cnt, void *stream);
+
+/*
+ * XNORWeightBinarizer.forward (bnn/ops.py:129-140) as a prepare-time pack:
+ * optional centring over c_in (ops.py:130-132), alpha[co] = mean |w| after
+ * centring (ops.py:116-127; 1.0 if !compute_alpha), sign bits -> wbits.
+ * w is contiguous [c_out, c_in, kh, kw] (Linear: kh = kw = 1).
+ * n_zero (device int32, may be NULL) receives the number of centred weights
+ * that are exactly 0 -- their sign is 0 in the reference, which one bit cannot
+ * hold; callers must not use the packed path when it is non-zero.
+ */
+int bnn_pack_weight_f32(const float *w, int32_t c_out, int32_t c_in, int32_t kh, int32_t kw,
+                        int32_t center_weights, int32_t compute_alpha,
+                        void *wbits, float *alpha, int32_t *n_zero, void *stream);
+
+/*
+ * bnn.layers.Conv2d.forward (bnn/layers/conv.py:90-97) on packed operands:
+ * XNOR/AND + popcount contraction with the fused epilogue
+ *     y = (scale[co] * dot + bias[co]) * post[co]
+ * scale / bias / post may each be NULL (1, 0, 1).  out is fp32, written with
+ * element strides (NCHW contiguous: c_out*ho*wo, ho*wo, wo, 1).
+ */
+int bnn_bconv2d_fwd(const void *abits, const uint32_t *cnt, const void *wbits,
+                    const float *scale, const float *bias, const float *post,
+                    float *out, int64_t ostride_n, int64_t ostride_c, int64_t ostride_h,
+                    int64_t ostride_w, const bnn_conv_geom *geom, uint32_t flags, void *stream);
+
+/*
+ * bnn.layers.Linear.forward (bnn/layers/linear.py:22-27): rows x in_features
+ * packed as n=1,h=1,w=rows (bnn_pack_act_f32 with stride_w = in_features,
+ * stride_c = 1), weight packed with kh = kw = 1; out is [rows, out_features].
+ */
+int bnn_blinear_fwd(const void *abits, const uint32_t *cnt, const void *wbits,
+                    const float *scale, const float *bias, const float *post,
+                    float *out, int32_t rows, int32_t in_features, int32_t out_features,
+                    uint32_t flags, void *stream);
+
+/*
+ * Integer-pipe micro-benchmarks used for the popcount roofline denominator
+ * (bench.py): runs `which` on every SM and returns achieved giga-operations/s
+ * (warp-lane operations) in *gops.  Synchronises the device.  which:
+ *   0 POPC only   1 LOP3 only   2 LOP3+POPC+IADD (one word per POPC)
+ *   3 3:2 carry-save (5 LOP3 + 2 POPC per 3 words)   4 7:3 carry-save
+ * For 2..4 the figure is 32-bit XNOR-popcount WORDS per second.
+ */
+int bnn_ubench(int32_t which, int32_t iters, double *gops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BNN_B200_H */
