@@ -1,0 +1,65 @@
+"""The C-ABI library loads and exports exactly what include/bnn_b200.h declares (no GPU needed)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+import bnn_b200
+from bnn_b200 import native
+
+HEADER = os.path.join(ROOT, "include", "bnn_b200.h")
+
+
+def _declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(bnn_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    assert _declared_functions() == native.exported_symbols()
+
+
+def test_library_exports_every_declared_symbol():
+    assert native.available(), "build the library first: python -c 'import __graft_entry__ as g; g.build()'"
+    lib = native.lib()
+    for name in _declared_functions():
+        assert hasattr(lib, name), name
+
+
+def test_size_helpers_and_errors_without_gpu():
+    lib = native.lib()
+    assert lib.bnn_act_bits_bytes(2, 64, 3, 5) == 2 * 1 * 3 * 5 * 16
+    assert lib.bnn_act_bits_bytes(1, 65, 1, 1) == 2 * 16
+    assert lib.bnn_act_cnt_bytes(2, 3, 5) == 2 * 3 * 5 * 4
+    assert lib.bnn_weight_bits_bytes(33, 64, 3, 3) == 2 * 9 * 32 * 8
+    assert lib.bnn_act_bits_bytes(0, 1, 1, 1) == 0
+    assert native.query(native.Q_ABI_VERSION) == 1
+    assert native.query(native.Q_SM_ARCH) == 100
+    assert b"NULL" in lib.bnn_strerror(-1)
+    # argument errors are reported before any CUDA call
+    assert lib.bnn_pack_act_f32(None, 0, 0, 0, 0, 1, 1, 1, 1, None, None, None) == -1
+    assert lib.bnn_pack_weight_f32(None, 1, 1, 1, 1, 0, 1, None, None, None, None) == -1
+    assert lib.bnn_bconv2d_fwd(None, None, None, None, None, None, None, 0, 0, 0, 0, None, 0, None) == -1
+    g = native.ConvGeom(1, 64, 4, 4, 64, 3, 3, 0, 1, 1, 1, 1, 1)   # stride 0
+    one = ctypes.c_void_p(16)
+    assert lib.bnn_bconv2d_fwd(one, one, one, None, None, None, one, 0, 0, 0, 0, ctypes.byref(g), 0, None) == -2
+    with pytest.raises(native.NativeError):
+        native.check(-3, "x")
+
+
+def test_sass_contains_tma_and_popc():
+    """Evidence the shipped kernels are the sm_100a TMA + POPC design (SASS mnemonics per
+    B200_PROFILING.md); skipped when cuobjdump is unavailable."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("no cuobjdump")
+    sass = subprocess.run([cuobjdump, "-sass", native.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTMALDG", "UBLKCP", "POPC", "LOP3"):
+        assert mnemonic in sass, mnemonic

@@ -1,0 +1,152 @@
+"""Pins the oracle (oracle/) against the reference: its own known-answer vectors and outputs of the
+real reference generated in the build container (tests/golden/*.npz).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+from conftest import rel_err
+from oracle import c_oracle as co
+from oracle import floatsim as fs
+
+
+def _t(a):
+    return None if a is None else torch.from_numpy(a)
+
+
+def test_unit_vectors_reference_known_answers(golden_units):
+    g = golden_units
+    data, w = g["data"], g["weights"]
+    ones3 = np.ones(3, np.float32)
+    # Linear(3,3): reference test/test_layers.py:30-38
+    y = fs.linear(_t(data[:, :, 0, 0].reshape(1, 3)), _t(w.reshape(3, 3)), None, _t(ones3)).numpy()
+    assert np.allclose(y, g["linear_expected"], atol=1e-4)
+    assert np.array_equal(y, g["linear_ref"])
+    yc = co.floatsim_linear(data[:, :, 0, 0].reshape(1, 3), w.reshape(3, 3), None, ones3, False, True)
+    assert np.allclose(yc, g["linear_expected"], atol=1e-4)
+    # Conv1d(3,3,1): test/test_layers.py:40-50
+    y = fs.conv1d(_t(np.ascontiguousarray(data[:, :, :, 0].reshape(1, 3, 2))), _t(w.reshape(3, 3, 1)), None, _t(ones3)).numpy()
+    assert np.allclose(y, g["conv1d_expected"], atol=1e-4)
+    assert np.array_equal(y, g["conv1d_ref"])
+    # Conv2d(3,3,1): test/test_layers.py:52-67
+    y = fs.conv2d(_t(data), _t(w.reshape(3, 3, 1, 1)), None, _t(ones3)).numpy()
+    assert np.allclose(y, g["conv2d_expected"], atol=1e-4)
+    assert np.array_equal(y, g["conv2d_ref"])
+    geo = co.geom(1, 3, 2, 2, 3, 1, 1)
+    yc = co.floatsim_conv2d(data, w.reshape(3, 3, 1, 1), None, ones3, geo, False, True)
+    assert np.allclose(yc, g["conv2d_expected"], atol=1e-4)
+    ab, cnt = co.pack_act(data)
+    wb, alpha, nz = co.pack_weight(w.reshape(3, 3, 1, 1), False, True)
+    assert nz == 0
+    yi = co.bconv2d(ab, cnt, wb, alpha, None, ones3, geo)
+    assert np.allclose(yi, g["conv2d_expected"], atol=1e-4)
+
+
+def test_sign_edge_cases(golden_units):
+    # test/test_binarize.py:118-120 plus +-0, denormal-ish and NaN
+    x, ref = golden_units["sign_in"], golden_units["sign_ref"]
+    assert np.array_equal(torch.sign(_t(x)).numpy(), ref, equal_nan=True)
+    ab, cnt = co.pack_act(x.reshape(1, -1, 1, 1))
+    s, m = int(ab[0, 0, 0, 0, 0]), int(ab[0, 0, 0, 0, 2])
+    got = np.array([((s >> i) & 1) * 2 - 1 if (m >> i) & 1 else 0 for i in range(x.size)], np.float32)
+    want = np.nan_to_num(ref, nan=0.0)   # the mask plane encodes sign(nan) as 0, like sign(+-0)
+    assert np.array_equal(got, want)
+    assert int(cnt[0, 0, 0]) == int((want != 0).sum())
+
+
+def _run_floatsim_torch(case):
+    x, w, bias, post = cases.make_inputs(case)
+    hp = cases.hyper(case)
+    if case["kind"] == "conv2d":
+        return fs.conv2d(_t(x), _t(w), _t(bias), _t(post), hp["stride"], hp["pad"], hp["dil"], hp["alpha"], hp["center"]).numpy()
+    if case["kind"] == "conv1d":
+        return fs.conv1d(_t(x), _t(w), _t(bias), _t(post), hp["stride"], hp["pad"], hp["dil"], hp["alpha"], hp["center"]).numpy()
+    return fs.linear(_t(x), _t(w), _t(bias), _t(post), hp["alpha"], hp["center"]).numpy()
+
+
+def _as_conv2d(case):
+    """(x4d, w4d, geom, unflatten) so that conv1d / linear go through the conv2d C entry points."""
+    x, w, bias, post = cases.make_inputs(case)
+    hp = cases.hyper(case)
+    if case["kind"] == "conv2d":
+        n, c, h, wd = x.shape
+        g = co.geom(n, c, h, wd, w.shape[0], w.shape[2], w.shape[3], hp["stride"], hp["pad"], hp["dil"])
+        return x, w, bias, post, g, hp, lambda y: y
+    if case["kind"] == "conv1d":
+        n, c, l = x.shape
+        g = co.geom(n, c, 1, l, w.shape[0], 1, w.shape[2], (1, hp["stride"][0]), (0, hp["pad"][0]), (1, hp["dil"][0]))
+        return x[:, :, None, :], w[:, :, None, :], bias, post, g, hp, lambda y: y[:, :, 0, :]
+    rows = x.reshape(-1, x.shape[-1])
+    x4 = np.ascontiguousarray(rows.T)[None, :, None, :]            # [1, in, 1, rows]
+    g = co.geom(1, rows.shape[1], 1, rows.shape[0], w.shape[0], 1, 1)
+    lead = x.shape[:-1]
+    return x4, w[:, :, None, None], bias, post, g, hp, lambda y: np.ascontiguousarray(y[0, :, 0, :].T).reshape(*lead, -1)
+
+
+@pytest.mark.parametrize("case", cases.CASES, ids=[c["name"] for c in cases.CASES])
+def test_layer_cases_against_reference_outputs(case, golden_layers):
+    ref = golden_layers[case["name"]]
+    # (1) torch restatement: same torch calls as the reference => tight
+    y = _run_floatsim_torch(case)
+    assert y.shape == ref.shape
+    assert rel_err(y, ref) <= 1e-6, rel_err(y, ref)
+    # (2) plain-C float restatement and (3) packed integer formulation
+    x4, w4, bias, post, g, hp, unflat = _as_conv2d(case)
+    yc = unflat(co.floatsim_conv2d(x4, w4, bias, post, g, hp["center"], hp["alpha"]))
+    assert rel_err(yc, ref) <= 1e-5, rel_err(yc, ref)
+    ab, cnt = co.pack_act(x4)
+    wb, alpha, nz = co.pack_weight(w4, hp["center"], hp["alpha"])
+    assert nz == 0
+    yi = unflat(co.bconv2d(ab, cnt, wb, alpha if hp["alpha"] else None, bias, post, g))
+    assert rel_err(yi, ref) <= 1e-5, rel_err(yi, ref)
+
+
+def test_integer_dot_properties():
+    case = cases.by_name("ragged_c70_s21")
+    x4, w4, _, _, g, hp, _ = _as_conv2d(case)
+    ab, cnt = co.pack_act(x4)
+    wb, _, _ = co.pack_weight(w4, hp["center"], hp["alpha"])
+    dot = co.bconv2d_dot(ab, cnt, wb, g)
+    abn, cntn = co.pack_act(-x4)
+    assert np.array_equal(cnt, cntn)
+    assert np.array_equal(co.bconv2d_dot(abn, cntn, wb, g), -dot)       # antisymmetry in x
+    k = 70 * 9
+    assert np.abs(dot).max() <= k
+    # brute force on the float side: dot == conv(sign x, sign wc) exactly
+    t = torch.nn.functional.conv2d(torch.sign(torch.from_numpy(x4)).double(),
+                                   torch.sign(torch.from_numpy(w4 - w4.mean(1, keepdims=True))).double(),
+                                   None, hp["stride"], hp["pad"], hp["dil"]).numpy()
+    assert np.array_equal(dot, t.astype(np.int32))
+
+
+def test_zero_weights_are_reported():
+    w = np.random.default_rng(0).standard_normal((4, 8, 1, 1)).astype(np.float32)
+    w[1, 3] = 0.0
+    w[2, 5] = -0.0
+    _, _, nz = co.pack_weight(w, False, True)
+    assert nz == 2
+
+
+def test_whole_model_twin_matches_reference_logits(golden_models):
+    """bnn_b200-prepared workload -> float-simulated twin (oracle) reproduces the REAL reference's logits
+    on the seeded model, and the seeded parameters are the reference's (checksum)."""
+    import torch.nn as nn
+    import bnn_b200 as bnn
+    from bnn_b200 import workloads
+    from bnn_b200.ops import BasicInputBinarizer, XNORWeightBinarizer
+    torch.set_grad_enabled(False)
+    for variant in ("basic_relu", "pre_prelu"):
+        torch.manual_seed(0)
+        m = workloads.resnet18() if variant == "basic_relu" else workloads.resnet18(workloads.PreBasicBlock, nn.PReLU)
+        cfg = bnn.BConfig(BasicInputBinarizer, bnn.Identity,
+                          XNORWeightBinarizer.with_args(compute_alpha=True, center_weights=True))
+        m = bnn.prepare_binary_model(m, cfg, ignore_layers_name=["_first_", "_last_"])
+        assert sum(isinstance(x, bnn.layers.Conv2d) for x in m.modules()) == 19
+        workloads.randomize_batchnorm(m, seed=1)
+        chk = np.array([float(p.double().abs().sum()) for p in m.state_dict().values() if p.dtype.is_floating_point])
+        assert np.allclose(chk, golden_models[variant + "_checksum"], rtol=1e-12)
+        twin = fs.mirror_model(m)
+        x = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(0))
+        y = twin(x).numpy()
+        assert rel_err(y, golden_models[variant + "_logits"]) <= 1e-6
+    torch.set_grad_enabled(True)
