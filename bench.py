@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of the ResNet-18 XNOR-Net forward (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA engine
+    python bench.py --impl reference ...                            # reference CPU float-sim arm
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one forward pass of the prepared model over one synthetic batch of 256 images per
+GPU (BASELINE configs[1]; 224x224, random-init weights, randomised BatchNorm statistics --
+SURVEY.md section 8(d)).  One JSON line is printed by rank 0.
+
+  value      whole-job images/s, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e        same metric through the public module API with PINNED HOST input every step
+             (H2D of the batch and D2H of the logits inside the timed region)
+  roofline   binarized-layer path (bit-pack + XNOR-popcount kernels): algorithmic bytes at the
+             drop-in contract (fp32 NCHW in + fp32 NCHW out per layer) divided by
+             the CUDA-event time of those launches, against MEASURED_PEAKS.json hbm_gbs
+  popc       same launches as binary MAC/s against the POPC-pipe peak measured by bnn_ubench
+  cpu_baseline  the oracle's float simulation (oracle/floatsim.py, a torch-CPU restatement of
+             the reference's forward) timed on this box's host cores on a bounded sample
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "images/sec ResNet-18 XNOR fwd @bs256"
+BATCH_PER_GPU = 256
+RES = 224
+
+
+def build_model(variant: str):
+    import bnn_b200 as bnn
+    from bnn_b200 import workloads
+    from bnn_b200.ops import BasicInputBinarizer, XNORWeightBinarizer
+    torch.manual_seed(0)
+    if variant == "pre_prelu":
+        model = workloads.resnet18(workloads.PreBasicBlock, nn.PReLU)
+    else:
+        model = workloads.resnet18()
+    cfg = bnn.BConfig(BasicInputBinarizer, bnn.Identity,
+                      XNORWeightBinarizer.with_args(compute_alpha=True, center_weights=True))
+    model = bnn.prepare_binary_model(model, cfg, ignore_layers_name=["_first_", "_last_"])
+    workloads.randomize_batchnorm(model, seed=1)
+    return model.eval()
+
+
+def layer_algorithmics(model, batch, res):
+    """Algorithmic bytes / binary MACs per binarized layer at the drop-in contract."""
+    import bnn_b200 as bnn
+    shapes = {}
+    hooks = []
+    for name, m in model.named_modules():
+        if isinstance(m, bnn.layers.Conv2d):
+            hooks.append(m.register_forward_hook(
+                lambda mod, inp, out, name=name: shapes.__setitem__(name, (tuple(inp[0].shape), tuple(out.shape)))))
+    with torch.no_grad(), bnn.runtime.floatsim_enabled():
+        twin_in = torch.zeros(1, 3, res, res)
+        import copy
+        copy.deepcopy(model).cpu()(twin_in)
+    for h in hooks:
+        h.remove()
+    table = {}
+    for name, m in model.named_modules():
+        if name in shapes:
+            (_, ci, h, w), (_, co, ho, wo) = shapes[name]
+            k = ci * m.kernel_size[0] * m.kernel_size[1]
+            table[name] = dict(bytes=batch * 4 * (ci * h * w + co * ho * wo) + co * k // 8 + 8 * co,
+                               bmac=batch * co * ho * wo * k)
+    return table
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def cpu_floatsim_rate(model, sample_batch, iters, threads):
+    """images/s of the oracle float simulation on host cores (bounded sample)."""
+    from oracle import floatsim
+    torch.set_num_threads(threads)
+    twin = floatsim.mirror_model(model)
+    x = torch.randn(sample_batch, 3, RES, RES, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        twin(x)                                           # warm-up
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            twin(x)
+        dt = time.perf_counter() - t0
+    return sample_batch * iters / dt, twin, x
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's CPU float-sim forward (oracle port: the reference is pure Python
+    over torch and is not installed on the GPU box) on all host cores, bounded sample per step."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    model = build_model(args.variant)
+    from oracle import floatsim
+    torch.set_num_threads(threads)
+    twin = floatsim.mirror_model(model)
+    sample = args.ref_batch
+    x = torch.randn(sample, 3, RES, RES, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        for _ in range(max(1, min(args.warmup, 2))):
+            twin(x)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            twin(x)
+        dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"resnet18 XNOR-Net ({args.variant}, first/last fp32) {RES}x{RES}",
+                   "sample": f"{sample} images per step on CPU"},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} forwards of {sample} images, oracle/floatsim.py (torch CPU fp32)"},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--variant", default="basic_relu", choices=["basic_relu", "pre_prelu"])
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="images per GPU per step")
+    ap.add_argument("--ref-batch", type=int, default=64, help="images per CPU step of the reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA graph")
+    ap.add_argument("--layers-out", default=None, help="write the per-layer table to this JSON file")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 engine has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    # fp32 glue (stem conv, fc) in true fp32: the reference's CPU float-sim is the parity target
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+    import bnn_b200 as bnn
+    from bnn_b200 import functional as BF
+    from bnn_b200 import native, sharded
+
+    model_cpu = build_model(args.variant)
+    algo = layer_algorithmics(model_cpu, args.batch, RES)
+    model = model_cpu.to(dev)
+    B = args.batch
+    x_dev = torch.randn(B, 3, RES, RES, device=dev)       # 154 MB at bs256 > 126 MB L2
+    x_host = torch.randn(B, 3, RES, RES).pin_memory()
+    logits_host = torch.empty(B * world, 1000).pin_memory()
+    stream = torch.cuda.current_stream()
+
+    def step_resident():
+        y = model(x_dev)
+        if world > 1:
+            y = sharded.gather_logits(y)
+        return y
+
+    def step_e2e():
+        xd = x_host.to(dev, non_blocking=True)
+        y = model(xd)
+        if world > 1:
+            y = sharded.gather_logits(y)
+        logits_host.copy_(y, non_blocking=True)
+        return y
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            step_resident()
+        sync_all()
+
+        graph = None
+        if not args.no_graph and world == 1:
+            # the whole forward as one CUDA graph: ~60 launches per step stop costing host time
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                step_resident()
+                side.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=side):
+                    graph_out = step_resident()
+            torch.cuda.current_stream().wait_stream(side)
+            for _ in range(2):
+                graph.replay()
+            sync_all()
+
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        launches0 = native.launch_count()
+        launches_per_step = None
+        if graph is not None:
+            ms = timed(graph.replay, args.steps)
+            # a replay re-issues every captured launch; count them from one eager step
+            l0 = native.launch_count(); step_resident(); launches_per_step = native.launch_count() - l0
+        else:
+            ms = timed(step_resident, args.steps)
+            launches_per_step = (native.launch_count() - launches0) // args.steps
+        clocks = sampler.stop() if rank == 0 else None
+
+        # end to end through the public module API, host buffers
+        for _ in range(2):
+            step_e2e()
+        ms_e2e = timed(step_e2e, args.steps)
+
+        # per-launch CUDA-event timing of the binarized path (same data, same stream, warm)
+        per_layer = {}
+        if rank == 0:
+            records = []
+            orig_pack, orig_conv = BF.pack_activations, BF.bconv2d
+
+            def ev():
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                return e
+
+            def pack_t(x, *a, **k):
+                e0 = ev(); r = orig_pack(x, *a, **k); records.append(("pack", e0, ev())); return r
+
+            def conv_t(*a, **k):
+                e0 = ev(); r = orig_conv(*a, **k); records.append(("conv", e0, ev())); return r
+
+            BF.pack_activations, BF.bconv2d = pack_t, conv_t
+            names = [n for n, m in model.named_modules() if isinstance(m, bnn.layers.Conv2d)]
+            order = []
+            hooks = [m.register_forward_hook(lambda mod, i, o, n=n: order.append(n))
+                     for n, m in model.named_modules() if isinstance(m, bnn.layers.Conv2d)]
+            reps = max(3, min(args.steps, 10))
+            for _ in range(reps):
+                step_resident()
+            torch.cuda.synchronize()
+            BF.pack_activations, BF.bconv2d = orig_pack, orig_conv
+            for h in hooks:
+                h.remove()
+            packs = [r for r in records if r[0] == "pack"]
+            convs = [r for r in records if r[0] == "conv"]
+            for i, name in enumerate(order):
+                d = per_layer.setdefault(name, {"pack_ms": 0.0, "conv_ms": 0.0})
+                d["pack_ms"] += packs[i][1].elapsed_time(packs[i][2]) / reps
+                d["conv_ms"] += convs[i][1].elapsed_time(convs[i][2]) / reps
+            for name, d in per_layer.items():
+                d.update(algo[name])
+                d["conv_tbmac_s"] = d["bmac"] / (d["conv_ms"] * 1e-3) * 1e-12
+                d["path_gb_s"] = d["bytes"] / ((d["pack_ms"] + d["conv_ms"]) * 1e-3) * 1e-9
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_kind = measured_peaks()
+    total_bytes = sum(d["bytes"] for d in per_layer.values())
+    total_bmac = sum(d["bmac"] for d in per_layer.values())
+    path_ms = sum(d["pack_ms"] + d["conv_ms"] for d in per_layer.values())
+    conv_ms = sum(d["conv_ms"] for d in per_layer.values())
+    achieved = total_bytes / (path_ms * 1e-3) * 1e-9
+    try:
+        popc_gops = BF.ubench(0, 200)                 # POPC warp-lane ops / s on this GPU, now
+        mix_gwords = BF.ubench(2, 200)
+    except native.NativeError:
+        popc_gops = mix_gwords = None
+    popc_peak_tbmac = popc_gops * 32 * 1e-3 if popc_gops else None     # one POPC = 32 binary MACs
+    images = B * world
+    value = images / (ms / args.steps * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": f"resnet18 XNOR-Net ({args.variant}, 19 binarized convs, first/last fp32) {RES}x{RES} bs{B}/GPU",
+                   "global_batch": images, "parallelism": f"dp{world}",
+                   "l2": f"input batch {B * 3 * RES * RES * 4 / 1e6:.0f} MB + activations exceed the 126 MB L2",
+                   "launch": "cuda_graph" if graph is not None else "eager",
+                   "glue": "torch eager fp32 (TF32 off) for stem/BN/act/pool/fc"},
+        "clocks": clocks,
+        "e2e": {"value": images / (ms_e2e / args.steps * 1e-3), "unit": "images/s",
+                "h2d_bytes_per_step": B * 3 * RES * RES * 4 * world, "d2h_bytes_per_step": images * 1000 * 4 * world,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches_per_step * args.steps) if launches_per_step else 0,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind,
+                     "what": "bit-pack + XNOR-popcount launches of the 19 binarized layers, algorithmic bytes "
+                             f"{total_bytes / 1e9:.3f} GB/step over {path_ms:.3f} ms/step; these layers are "
+                             "POPC-bound, see 'popc'"},
+        "popc": {"achieved_tbmac_s": total_bmac / (conv_ms * 1e-3) * 1e-12, "peak_tbmac_s": popc_peak_tbmac,
+                 "frac": (total_bmac / (conv_ms * 1e-3) * 1e-12 / popc_peak_tbmac) if popc_peak_tbmac else None,
+                 "peak_kind": "bnn_ubench(POPC) x 32 on this GPU", "lop3_popc_iadd_gwords_s": mix_gwords,
+                 "conv_ms_per_step": conv_ms, "binarized_path_ms_per_step": path_ms},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sample, iters = 64, 2
+        rate, _, _ = cpu_floatsim_rate(model_cpu, sample, iters, threads)
+        line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
+                                "sample": f"{iters} forwards of {sample} images (oracle/floatsim.py, torch CPU fp32, "
+                                          f"{threads} threads)"}
+    if args.layers_out:
+        os.makedirs(os.path.dirname(os.path.abspath(args.layers_out)), exist_ok=True)
+        with open(args.layers_out, "w") as f:
+            json.dump({"per_layer": per_layer, "line": line}, f, indent=1)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -37,7 +37,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return done != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) { }
+    // try_wait suspends in hardware for a bounded time; a transfer that never lands (bad tensor map)
+    // must not hang the GPU, so give up loudly after ~seconds instead of spinning forever
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
+        if (spins > (1u << 24)) __trap();
 }
 
 // TMA: 5-D tiled tensor load global -> shared, completion on an mbarrier (SASS: UTMALDG)

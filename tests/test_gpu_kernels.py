@@ -1,0 +1,175 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the oracle and the committed
+reference outputs.  Integer work is compared bit-exactly; fp32 outputs within 1e-5 of max|ref|
+(north_star tolerance is 1e-3).  Run on the B200 box:  pytest tests -m gpu."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+from conftest import rel_err
+from oracle import c_oracle as co
+from test_oracle import _as_conv2d
+
+import bnn_b200 as bnn
+from bnn_b200 import functional as BF
+from bnn_b200 import native, runtime
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = 1e-5
+
+
+def _bits(t):
+    return t.cpu().numpy().view(np.uint32)
+
+
+def test_library_reports_device():
+    assert native.query(native.Q_DEVICE_SMS) > 0
+    assert torch.cuda.get_device_capability(0)[0] == 10
+
+
+@pytest.mark.parametrize("shape,layout", [((2, 64, 5, 7), "nchw"), ((1, 3, 4, 4), "nchw"), ((2, 70, 6, 7), "nchw"),
+                                          ((2, 128, 9, 11), "nhwc"), ((3, 200, 3, 5), "sliced"), ((1, 512, 7, 7), "nchw"),
+                                          ((4, 64, 56, 56), "nchw")])
+def test_pack_activations_bit_exact(shape, layout):
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal(shape).astype(np.float32)
+    x[rng.random(shape) < 0.4] = 0.0
+    flat = x.reshape(-1)
+    flat[::13] = -0.0
+    flat[5::97] = np.nan
+    flat[7::101] = 1e-42        # denormal, still > 0
+    xt = torch.from_numpy(x).to(DEV)
+    if layout == "nhwc":
+        xt = xt.contiguous(memory_format=torch.channels_last)
+    elif layout == "sliced":
+        big = torch.zeros((shape[0], shape[1] + 3, shape[2], shape[3] + 2), device=DEV)
+        big[:, 1:-2, :, 1:-1] = xt
+        xt = big[:, 1:-2, :, 1:-1]
+        assert not xt.is_contiguous()
+    packed = BF.pack_activations(xt)
+    ab, cnt = co.pack_act(x)
+    assert np.array_equal(_bits(packed.bits), ab)
+    assert np.array_equal(_bits(packed.cnt), cnt)
+
+
+@pytest.mark.parametrize("wshape,center,alpha", [((64, 64, 3, 3), True, True), ((40, 70, 3, 3), True, True),
+                                                 ((3, 3, 1, 1), False, True), ((128, 64, 1, 1), False, False),
+                                                 ((1000, 512), True, True), ((8, 16, 5), False, True),
+                                                 ((512, 512, 3, 3), True, True)])
+def test_pack_weights_bits_exact_alpha_close(wshape, center, alpha):
+    rng = np.random.default_rng(11)
+    w = (rng.standard_normal(wshape) * 0.05).astype(np.float32)
+    packed = BF.pack_weights(torch.from_numpy(w).to(DEV), center, alpha)
+    wb, al, nz = co.pack_weight(w, center, alpha)
+    assert packed.n_zero == nz == 0
+    assert np.array_equal(_bits(packed.bits), wb)
+    assert rel_err(packed.alpha.cpu().numpy(), al) <= 1e-6
+
+
+def test_pack_weights_counts_exact_zeros():
+    w = torch.randn(4, 8, 1, 1, device=DEV)
+    w[1, 3] = 0.0
+    w[2, 5] = -0.0
+    assert BF.pack_weights(w, False, True).n_zero == 2
+
+
+FLAG_SETS = [native.F_STAGE_LDG, 0, native.F_NO_CSA]
+
+
+@pytest.mark.parametrize("flags", FLAG_SETS, ids=["ldg", "tma", "nocsa"])
+@pytest.mark.parametrize("case", cases.CASES, ids=[c["name"] for c in cases.CASES])
+def test_conv_kernel_against_oracle_and_reference(case, flags, golden_layers):
+    """C ABI level: packed conv == oracle integer path bit-exactly (dot), == reference within TOL."""
+    x4, w4, bias, post, g, hp, unflat = _as_conv2d(case)
+    xt = torch.from_numpy(np.ascontiguousarray(x4)).to(DEV)
+    act = BF.pack_activations(xt)
+    wts = BF.pack_weights(torch.from_numpy(np.ascontiguousarray(w4)).to(DEV), hp["center"], hp["alpha"])
+    stride, pad, dil = (g.stride_h, g.stride_w), (g.pad_h, g.pad_w), (g.dil_h, g.dil_w)
+    # integer dot: scale = None, no bias / post -> exact small integers in fp32
+    dot = BF.bconv2d(act, wts, None, None, stride, pad, dil, use_alpha=False, flags=flags).cpu().numpy()
+    ab, cnt = co.pack_act(x4)
+    wb, _, _ = co.pack_weight(w4, hp["center"], hp["alpha"])
+    want = co.bconv2d_dot(ab, cnt, wb, g)
+    assert np.array_equal(dot.astype(np.int32), want) and np.array_equal(dot, want.astype(np.float32))
+    # fused epilogue vs the real reference's output
+    bt = None if bias is None else torch.from_numpy(bias).to(DEV)
+    pt = None if post is None else torch.from_numpy(post).to(DEV)
+    y = BF.bconv2d(act, wts, bt, pt, stride, pad, dil, use_alpha=hp["alpha"], flags=flags).cpu().numpy()
+    assert rel_err(unflat(y), golden_layers[case["name"]]) <= TOL
+
+
+@pytest.mark.parametrize("case", cases.CASES, ids=[c["name"] for c in cases.CASES])
+def test_module_api_against_reference(case, golden_layers):
+    """Plugin level: nn module -> prepare_binary_model -> forward on the GPU, as a user would."""
+    import torch.nn as nn
+    from bnn_b200.ops import BasicInputBinarizer, BasicScaleBinarizer, XNORWeightBinarizer
+    x, w, bias, post = cases.make_inputs(case)
+    hp = cases.hyper(case)
+    cfg = bnn.BConfig(BasicInputBinarizer, BasicScaleBinarizer if post is not None else bnn.Identity,
+                      XNORWeightBinarizer.with_args(compute_alpha=hp["alpha"], center_weights=hp["center"]))
+    if case["kind"] == "conv2d":
+        m = nn.Conv2d(w.shape[1], w.shape[0], w.shape[2:], stride=hp["stride"], padding=hp["pad"], dilation=hp["dil"],
+                      bias=bias is not None)
+    elif case["kind"] == "conv1d":
+        m = nn.Conv1d(w.shape[1], w.shape[0], w.shape[2], stride=hp["stride"], padding=hp["pad"], dilation=hp["dil"],
+                      bias=bias is not None)
+    else:
+        m = nn.Linear(w.shape[1], w.shape[0], bias=bias is not None)
+    m.weight.data.copy_(torch.from_numpy(w))
+    if bias is not None:
+        m.bias.data.copy_(torch.from_numpy(bias))
+    m = bnn.prepare_binary_model(m.to(DEV), cfg).eval()
+    if post is not None:
+        m.activation_post_process.alpha.data.copy_(torch.from_numpy(post).reshape(m.activation_post_process.alpha.shape))
+    before = native.launch_count()
+    with torch.no_grad():
+        y = m(torch.from_numpy(x).to(DEV))
+    assert native.launch_count() >= before + 2          # pack + conv really ran in the native library
+    assert rel_err(y.cpu().numpy(), golden_layers[case["name"]]) <= TOL
+
+
+def test_reference_known_answer_vectors_on_gpu(golden_units):
+    import torch.nn as nn
+    from bnn_b200.ops import BasicInputBinarizer, BasicScaleBinarizer, XNORWeightBinarizer
+    cfg = bnn.BConfig(BasicInputBinarizer, BasicScaleBinarizer, XNORWeightBinarizer)
+    g = golden_units
+    w = torch.from_numpy(g["weights"])
+    data = torch.from_numpy(g["data"]).to(DEV)
+    with torch.no_grad():
+        lin = nn.Linear(3, 3, bias=False); lin.weight.data.copy_(w.view(3, 3))
+        out = bnn.prepare_binary_model(lin.to(DEV), cfg)(data[:, :, 0, 0].reshape(1, 3))
+        assert np.allclose(out.cpu().numpy(), g["linear_expected"], atol=1e-4)
+        c1 = nn.Conv1d(3, 3, 1, bias=False); c1.weight.data.copy_(w.view(3, 3, 1))
+        out = bnn.prepare_binary_model(c1.to(DEV), cfg)(data[:, :, :, 0].reshape(1, 3, 2))
+        assert np.allclose(out.cpu().numpy(), g["conv1d_expected"], atol=1e-4)
+        c2 = nn.Conv2d(3, 3, 1, bias=False); c2.weight.data.copy_(w.view(3, 3, 1, 1))
+        out = bnn.prepare_binary_model(c2.to(DEV), cfg)(data)
+        assert np.allclose(out.cpu().numpy(), g["conv2d_expected"], atol=1e-4)
+
+
+def test_weight_cache_follows_load_state_dict_and_inplace_updates():
+    import torch.nn as nn
+    from bnn_b200.ops import BasicInputBinarizer, XNORWeightBinarizer
+    cfg = bnn.BConfig(BasicInputBinarizer, bnn.Identity, XNORWeightBinarizer)
+    torch.manual_seed(0)
+    a = bnn.prepare_binary_model(nn.Conv2d(64, 64, 3, padding=1).to(DEV), cfg).eval()
+    b = bnn.prepare_binary_model(nn.Conv2d(64, 64, 3, padding=1).to(DEV), cfg).eval()
+    x = torch.randn(2, 64, 9, 9, device=DEV)
+    with torch.no_grad():
+        ya, yb = a(x), b(x)
+        assert not torch.equal(ya, yb)
+        b.load_state_dict(a.state_dict())
+        assert torch.equal(a(x), b(x))
+        a.weight.neg_()                                   # in-place update bumps the version counter
+        assert torch.equal(a(x) - a.bias.view(1, -1, 1, 1), -(ya - a.bias.view(1, -1, 1, 1)))
+
+
+def test_exact_zero_weights_are_refused_not_approximated():
+    import torch.nn as nn
+    from bnn_b200.ops import BasicInputBinarizer, XNORWeightBinarizer
+    cfg = bnn.BConfig(BasicInputBinarizer, bnn.Identity, XNORWeightBinarizer)
+    m = bnn.prepare_binary_model(nn.Conv2d(64, 64, 1).to(DEV), cfg).eval()
+    m.weight.data[3, 7] = 0.0
+    with torch.no_grad(), pytest.raises(native.NativeError, match="exactly zero"):
+        m(torch.randn(1, 64, 4, 4, device=DEV))

@@ -1,0 +1,124 @@
+"""Whole-model parity and full-size properties on the GPU."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from conftest import rel_err
+from oracle import floatsim as fs
+
+import bnn_b200 as bnn
+from bnn_b200 import functional as BF
+from bnn_b200 import native, workloads
+from bnn_b200.ops import BasicInputBinarizer, BasicScaleBinarizer, XNORWeightBinarizer
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def xnor_cfg(post=bnn.Identity):
+    return bnn.BConfig(BasicInputBinarizer, post, XNORWeightBinarizer.with_args(compute_alpha=True, center_weights=True))
+
+
+def build(variant, cfg=None):
+    torch.manual_seed(0)
+    m = workloads.resnet18() if variant == "basic_relu" else workloads.resnet18(workloads.PreBasicBlock, nn.PReLU)
+    m = bnn.prepare_binary_model(m, cfg or xnor_cfg(), ignore_layers_name=["_first_", "_last_"])
+    workloads.randomize_batchnorm(m, seed=1)
+    return m.eval()
+
+
+@pytest.fixture(autouse=True)
+def _fp32_glue():
+    # the non-binarized glue (stem conv, fc) must not run in TF32, or parity is lost there
+    prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+@pytest.mark.parametrize("variant", ["basic_relu", "pre_prelu"])
+def test_resnet18_logits_match_the_reference(variant, golden_models):
+    m = build(variant).to(DEV)
+    x = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(0))
+    before = native.launch_count()
+    with torch.no_grad():
+        y = m(x.to(DEV)).cpu().numpy()
+    assert native.launch_count() - before >= 2 * 19
+    ref = golden_models[variant + "_logits"]
+    # north_star: within 1e-3 relative of the reference's float-sim forward
+    assert rel_err(y, ref) <= 1e-3, rel_err(y, ref)
+    assert (np.argmax(y, 1) == np.argmax(ref, 1)).all()
+
+
+def test_resnet18_full_resolution_vs_oracle_twin():
+    """224x224, batch 4: CUDA engine vs the oracle's CPU float simulation of the same prepared model,
+    with a learned XNOR-Net++ post scale so the fused epilogue scale is exercised end to end."""
+    m = build("basic_relu", xnor_cfg(BasicScaleBinarizer))
+    twin = fs.mirror_model(m)
+    x = torch.randn(4, 3, 224, 224, generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        want = twin(x).numpy()
+        got = m.to(DEV)(x.to(DEV)).cpu().numpy()
+    assert rel_err(got, want) <= 1e-3, rel_err(got, want)
+
+
+def test_full_size_layer_properties():
+    """BASELINE-size layer (bs 256, 64ch, 56x56) through size-independent identities:
+    batch-split invariance, antisymmetry in x, zero input, integer parity of the dot."""
+    torch.manual_seed(0)
+    n = 256
+    x = torch.relu(torch.randn(n, 64, 56, 56, device=DEV))          # ~50 % exact zeros, like a ReLU-fed layer
+    w = torch.randn(64, 64, 3, 3, device=DEV) * 0.05
+    wts = BF.pack_weights(w, True, True)
+    act = BF.pack_activations(x)
+    dot = BF.bconv2d(act, wts, None, None, (1, 1), (1, 1), (1, 1), use_alpha=False)
+    # (a) any sub-batch gives bit-identical rows
+    sub = BF.bconv2d(BF.pack_activations(x[100:132]), wts, None, None, (1, 1), (1, 1), (1, 1), use_alpha=False)
+    assert torch.equal(dot[100:132], sub)
+    # (b) dot(-x) == -dot(x) exactly (mask plane unchanged, sign plane flipped)
+    neg = BF.bconv2d(BF.pack_activations(-x[:16]), wts, None, None, (1, 1), (1, 1), (1, 1), use_alpha=False)
+    assert torch.equal(neg, -dot[:16])
+    # (c) dot and the number of non-zero inputs under the window have the same parity
+    ones = torch.ones(1, 1, 3, 3, device=DEV)
+    nz = torch.nn.functional.conv2d((x[:16] != 0).float().sum(1, keepdim=True), ones, padding=1)
+    assert torch.equal(torch.remainder(dot[:16], 2), torch.remainder(nz, 2).expand(-1, 64, -1, -1))
+    assert dot.abs().max().item() <= 576
+    # (d) all-zero input -> bias * post exactly
+    bias = torch.randn(64, device=DEV)
+    post = torch.rand(64, device=DEV) + 0.5
+    z = BF.bconv2d(BF.pack_activations(torch.zeros(2, 64, 56, 56, device=DEV)), wts, bias, post, (1, 1), (1, 1), (1, 1))
+    assert torch.equal(z, (bias * post).view(1, -1, 1, 1).expand_as(z))
+    # (e) epilogue is exactly (alpha*dot + bias)*post in fp32
+    y = BF.bconv2d(BF.pack_activations(x[:8]), wts, bias, post, (1, 1), (1, 1), (1, 1))
+    want = (wts.alpha.view(1, -1, 1, 1) * dot[:8] + bias.view(1, -1, 1, 1)) * post.view(1, -1, 1, 1)
+    assert torch.equal(y, want)
+
+
+def test_full_batch_model_rows_are_independent():
+    m = build("basic_relu").to(DEV)
+    x = torch.randn(64, 3, 224, 224, device=DEV)
+    with torch.no_grad():
+        full = m(x)
+        part = m(x[16:24])
+    assert torch.isfinite(full).all()
+    assert rel_err(full[16:24].cpu().numpy(), part.cpu().numpy()) <= 1e-5
+
+
+def test_forward_is_cuda_graph_capturable():
+    m = build("basic_relu").to(DEV)
+    x = torch.randn(8, 3, 96, 96, device=DEV)
+    with torch.no_grad():
+        eager = m(x)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            m(x)
+            torch.cuda.current_stream().synchronize()
+            with torch.cuda.graph(g, stream=s):
+                out = m(x)
+        g.replay()
+        torch.cuda.synchronize()
+    assert torch.equal(out, eager)
