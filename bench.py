@@ -95,7 +95,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except OSError:
@@ -103,7 +103,11 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def window(self, t0, t1):
+        """keep only the samples taken while the timed region ran (50 ms slack either side)"""
+        self.t0, self.t1 = t0 - 0.05, t1 + 0.05
 
     def stop(self):
         if self.proc is None:
@@ -115,7 +119,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        t0, t1 = getattr(self, "t0", -1e30), getattr(self, "t1", 1e30)
+        for stamp, line in self.lines:
+            if not (t0 <= stamp <= t1):
+                continue
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 7:
                 continue
@@ -190,7 +197,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--variant", default="basic_relu", choices=["basic_relu", "pre_prelu"])
@@ -267,6 +274,9 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()            # started before warm-up: nvidia-smi needs a moment to deliver samples
     with torch.no_grad():
         for _ in range(args.warmup):
             step_resident()
@@ -288,10 +298,8 @@ def main():
                 graph.replay()
             sync_all()
 
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
         launches0 = native.launch_count()
+        t_region0 = time.perf_counter()
         launches_per_step = None
         if graph is not None:
             ms = timed(graph.replay, args.steps)
@@ -300,6 +308,8 @@ def main():
         else:
             ms = timed(step_resident, args.steps)
             launches_per_step = (native.launch_count() - launches0) // args.steps
+        if rank == 0:
+            sampler.window(t_region0, time.perf_counter())
         clocks = sampler.stop() if rank == 0 else None
 
         # end to end through the public module API, host buffers

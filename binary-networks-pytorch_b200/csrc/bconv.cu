@@ -57,6 +57,9 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
     uint4* act = reinterpret_cast<uint4*>(smem + 128);
     uint2* wsm = reinterpret_cast<uint2*>(smem + 128 + ((a.act_bytes + 127u) & ~127u));
+    // per-warp transpose buffer for the epilogue: 32 channels x PITCH pixels (odd pitch: no conflicts)
+    constexpr int PITCH = P | 1;
+    float* stage_all = reinterpret_cast<float*>(smem + 128 + ((a.act_bytes + 127u) & ~127u) + (size_t)C * a.w_bytes);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     int unit = blockIdx.x;
@@ -224,20 +227,51 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
 
         // fused epilogue: y = (alpha_w * dot + bias) * alpha_post, same order as the reference
         float* obase = a.out + (long long)n * a.on + (long long)ho * a.oh;
+        int ms[P];
 #pragma unroll
-        for (int p = 0; p < P; ++p) {
-            const int ms = __shfl_sync(0xffffffffu, msum, p);
-            const int wo = wo_first + p;
-            if (wo >= a.Wo) break;
+        for (int p = 0; p < P; ++p) ms[p] = __shfl_sync(0xffffffffu, msum, p);
+        if (a.ow != 1) {
+            // channel-contiguous output (Linear's [rows, out]): lanes <-> channels is already coalesced
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                const int wo = wo_first + p;
+                if (wo >= a.Wo) break;
+#pragma unroll
+                for (int j = 0; j < C; ++j) {
+                    if (!c_ok[j]) continue;
+                    const int c = (blk0 + j) * 32 + lane;
+                    float y = __fmul_rn(e_scale[j], (float)(ms[p] - 2 * acc[p][j]));
+                    if (a.bias) y = __fadd_rn(y, e_bias[j]);
+                    if (a.post) y = __fmul_rn(y, e_post[j]);
+                    obase[(long long)c * a.oc + (long long)wo * a.ow] = y;
+                }
+            }
+        } else {
+            // pixel-contiguous output (NCHW): transpose each 32-channel block through shared memory so a
+            // store instruction covers whole 32-byte runs of P pixels instead of 32 scattered words
+            float* stg = stage_all + warp * (32 * PITCH);
+            constexpr int PW = (P > 4) ? 8 : 4;          // lanes per channel row when reading back
+            constexpr int ROWS = 32 / PW;                // channel rows per store instruction
+            const int pr = lane % PW, rr = lane / PW;
 #pragma unroll
             for (int j = 0; j < C; ++j) {
-                if (!c_ok[j]) continue;
-                const int c = (blk0 + j) * 32 + lane;
-                const int dot = ms - 2 * acc[p][j];
-                float y = __fmul_rn(e_scale[j], (float)dot);
-                if (a.bias) y = __fadd_rn(y, e_bias[j]);
-                if (a.post) y = __fmul_rn(y, e_post[j]);
-                obase[(long long)c * a.oc + (long long)wo * a.ow] = y;
+                __syncwarp();
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    float y = __fmul_rn(e_scale[j], (float)(ms[p] - 2 * acc[p][j]));
+                    if (a.bias) y = __fadd_rn(y, e_bias[j]);
+                    if (a.post) y = __fmul_rn(y, e_post[j]);
+                    stg[lane * PITCH + p] = y;
+                }
+                __syncwarp();
+                const int cblk = (blk0 + j) * 32;
+#pragma unroll
+                for (int r0 = 0; r0 < 32; r0 += ROWS) {
+                    const int cl = r0 + rr;
+                    const int c = cblk + cl, wo = wo_first + pr;
+                    if (pr < P && wo < a.Wo && c < a.Cout)
+                        obase[(long long)c * a.oc + wo] = stg[cl * PITCH + pr];
+                }
             }
         }
     }
@@ -313,7 +347,7 @@ static int make_plan(const bnn_conv_geom& g, int Ho, int Wo, uint32_t flags, int
     while (C > 1 && (size_t)C * nk * 256 > 96 * 1024) C >>= 1;
     const size_t wbytes = (size_t)C * nk * 256;
     if (wbytes + 8192 > smem_cap) return BNN_E_UNSUPPORTED;
-    const size_t act_budget = (wbytes <= 64 * 1024 ? 110 * 1024 : smem_cap) - wbytes - 256;
+    const size_t act_budget = (wbytes <= 64 * 1024 ? 110 * 1024 : smem_cap) - wbytes - 256 - 8 * 32 * 9 * 4;
 
     // pixels per group: least padding waste, then prefer a register window, then larger
     const int cand[3] = {8, 7, 4};
@@ -366,7 +400,7 @@ static int make_plan(const bnn_conv_geom& g, int Ho, int Wo, uint32_t flags, int
     pl.G = bTH * pl.gpr;
     pl.tiles_h = ceil_div(Ho, bTH);
     const size_t act_bytes = (size_t)nch * pl.BH * pl.BW * 16;
-    pl.smem = 128 + ((act_bytes + 127) & ~(size_t)127) + wbytes;
+    pl.smem = 128 + ((act_bytes + 127) & ~(size_t)127) + wbytes + (size_t)pl.NW * 32 * (pl.P | 1) * 4;
     *out = pl;
     return 0;
 }

@@ -1,0 +1,60 @@
+"""Run single binarized layers of the ResNet-18 workload in isolation (for ncu / event timing).
+
+    python scripts/profile_layer.py [--layers l1,l2,l3,l4,...] [--reps 5] [--batch 256] [--flags 0]
+Prints one JSON object per layer with CUDA-event times of the pack and conv launches."""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bnn_b200  # noqa: E402
+from bnn_b200 import functional as BF  # noqa: E402
+
+LAYERS = {  # name: (c_in, c_out, h, w, k, stride, pad)
+    "l1": (64, 64, 56, 56, 3, 1, 1), "l2s": (64, 128, 56, 56, 3, 2, 1), "l2": (128, 128, 28, 28, 3, 1, 1),
+    "l2d": (64, 128, 28, 28, 1, 1, 0), "l3s": (128, 256, 28, 28, 3, 2, 1), "l3": (256, 256, 14, 14, 3, 1, 1),
+    "l3d": (128, 256, 14, 14, 1, 1, 0), "l4s": (256, 512, 14, 14, 3, 2, 1), "l4": (512, 512, 7, 7, 3, 1, 1),
+    "l4d": (256, 512, 7, 7, 1, 1, 0),
+}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--layers", default="l1,l2,l3,l4")
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--flags", type=int, default=0)
+    args = ap.parse_args()
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    for name in args.layers.split(","):
+        ci, co, h, w, k, s, p = LAYERS[name]
+        x = torch.relu(torch.randn(args.batch, ci, h, w, device=dev))
+        wt = torch.randn(co, ci, k, k, device=dev) * 0.05
+        wts = BF.pack_weights(wt, True, True)
+        act = BF.pack_activations(x)
+        out = BF.bconv2d(act, wts, None, None, (s, s), (p, p), (1, 1), flags=args.flags)
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        tp = tc = 0.0
+        for _ in range(args.reps):
+            ev[0].record()
+            act = BF.pack_activations(x)
+            ev[1].record()
+            BF.bconv2d(act, wts, None, None, (s, s), (p, p), (1, 1), flags=args.flags, out=out)
+            ev[2].record()
+            torch.cuda.synchronize()
+            tp += ev[0].elapsed_time(ev[1]) / args.reps
+            tc += ev[1].elapsed_time(ev[2]) / args.reps
+        ho, wo = out.shape[2], out.shape[3]
+        bmac = args.batch * co * ho * wo * ci * k * k
+        print(json.dumps({"layer": name, "pack_ms": round(tp, 4), "conv_ms": round(tc, 4),
+                          "tbmac_s": round(bmac / tc * 1e-9, 1),
+                          "out_gb_s": round(out.numel() * 4 / tc * 1e-6, 1)}), flush=True)
+
+
+if __name__ == "__main__":
+    main()

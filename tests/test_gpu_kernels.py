@@ -153,8 +153,8 @@ def test_weight_cache_follows_load_state_dict_and_inplace_updates():
     from bnn_b200.ops import BasicInputBinarizer, XNORWeightBinarizer
     cfg = bnn.BConfig(BasicInputBinarizer, bnn.Identity, XNORWeightBinarizer)
     torch.manual_seed(0)
-    a = bnn.prepare_binary_model(nn.Conv2d(64, 64, 3, padding=1).to(DEV), cfg).eval()
-    b = bnn.prepare_binary_model(nn.Conv2d(64, 64, 3, padding=1).to(DEV), cfg).eval()
+    a = bnn.prepare_binary_model(nn.Conv2d(64, 64, 3, padding=1, bias=False).to(DEV), cfg).eval()
+    b = bnn.prepare_binary_model(nn.Conv2d(64, 64, 3, padding=1, bias=False).to(DEV), cfg).eval()
     x = torch.randn(2, 64, 9, 9, device=DEV)
     with torch.no_grad():
         ya, yb = a(x), b(x)
@@ -162,7 +162,7 @@ def test_weight_cache_follows_load_state_dict_and_inplace_updates():
         b.load_state_dict(a.state_dict())
         assert torch.equal(a(x), b(x))
         a.weight.neg_()                                   # in-place update bumps the version counter
-        assert torch.equal(a(x) - a.bias.view(1, -1, 1, 1), -(ya - a.bias.view(1, -1, 1, 1)))
+        assert torch.equal(a(x), -ya)                     # repacked: alpha unchanged, every dot negated
 
 
 def test_exact_zero_weights_are_refused_not_approximated():
