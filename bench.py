@@ -81,6 +81,17 @@ def layer_algorithmics(model, batch, res):
     return table
 
 
+def fused_layer_order(model):
+    """Names of the binarized convs in the order the fused engine launches them (shortcut first)."""
+    names = []
+    for lname in ("layer1", "layer2", "layer3", "layer4"):
+        for bi, blk in enumerate(getattr(model, lname)):
+            if getattr(blk, "downsample", None) is not None:
+                names.append(f"{lname}.{bi}.downsample.1")
+            names += [f"{lname}.{bi}.conv1", f"{lname}.{bi}.conv2"]
+    return names
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
 
@@ -205,6 +216,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=64, help="images per CPU step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA graph")
+    ap.add_argument("--no-fuse", action="store_true", help="per-layer kernels + torch glue (no cross-module fusion)")
     ap.add_argument("--layers-out", default=None, help="write the per-layer table to this JSON file")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -235,6 +247,8 @@ def main():
     model_cpu = build_model(args.variant)
     algo = layer_algorithmics(model_cpu, args.batch, RES)
     model = model_cpu.to(dev)
+    from bnn_b200 import fuse
+    engine = model if args.no_fuse else fuse.optimize(model)       # public API: bnn_b200.fuse.optimize(model)
     B = args.batch
     x_dev = torch.randn(B, 3, RES, RES, device=dev)       # 154 MB at bs256 > 126 MB L2
     x_host = torch.randn(B, 3, RES, RES).pin_memory()
@@ -242,14 +256,14 @@ def main():
     stream = torch.cuda.current_stream()
 
     def step_resident():
-        y = model(x_dev)
+        y = engine(x_dev)
         if world > 1:
             y = sharded.gather_logits(y)
         return y
 
     def step_e2e():
         xd = x_host.to(dev, non_blocking=True)
-        y = model(xd)
+        y = engine(xd)
         if world > 1:
             y = sharded.gather_logits(y)
         logits_host.copy_(y, non_blocking=True)
@@ -321,7 +335,7 @@ def main():
         per_layer = {}
         if rank == 0:
             records = []
-            orig_pack, orig_conv = BF.pack_activations, BF.bconv2d
+            orig_pack, orig_conv, orig_fused = BF.pack_activations, BF.bconv2d, BF.bconv2d_fused
 
             def ev():
                 e = torch.cuda.Event(enable_timing=True)
@@ -334,8 +348,12 @@ def main():
             def conv_t(*a, **k):
                 e0 = ev(); r = orig_conv(*a, **k); records.append(("conv", e0, ev())); return r
 
-            BF.pack_activations, BF.bconv2d = pack_t, conv_t
-            names = [n for n, m in model.named_modules() if isinstance(m, bnn.layers.Conv2d)]
+            def fused_t(act, wts, *a, **k):
+                e0 = ev(); r = orig_fused(act, wts, *a, **k)
+                records.append(("conv", e0, ev(), (wts.c_in, wts.c_out, wts.kh, act.h, act.w)))
+                return r
+
+            BF.pack_activations, BF.bconv2d, BF.bconv2d_fused = pack_t, conv_t, fused_t
             order = []
             hooks = [m.register_forward_hook(lambda mod, i, o, n=n: order.append(n))
                      for n, m in model.named_modules() if isinstance(m, bnn.layers.Conv2d)]
@@ -343,19 +361,32 @@ def main():
             for _ in range(reps):
                 step_resident()
             torch.cuda.synchronize()
-            BF.pack_activations, BF.bconv2d = orig_pack, orig_conv
+            BF.pack_activations, BF.bconv2d, BF.bconv2d_fused = orig_pack, orig_conv, orig_fused
             for h in hooks:
                 h.remove()
             packs = [r for r in records if r[0] == "pack"]
             convs = [r for r in records if r[0] == "conv"]
-            for i, name in enumerate(order):
-                d = per_layer.setdefault(name, {"pack_ms": 0.0, "conv_ms": 0.0})
-                d["pack_ms"] += packs[i][1].elapsed_time(packs[i][2]) / reps
-                d["conv_ms"] += convs[i][1].elapsed_time(convs[i][2]) / reps
+            if order:                                   # unfused: module hooks give the layer names
+                for i, name in enumerate(order):
+                    d = per_layer.setdefault(name, {"pack_ms": 0.0, "conv_ms": 0.0})
+                    d["pack_ms"] += packs[i][1].elapsed_time(packs[i][2]) / reps
+                    d["conv_ms"] += convs[i][1].elapsed_time(convs[i][2]) / reps
+            else:                                       # fused engine: conv launches in execution order
+                names = fused_layer_order(model)
+                per_step = len(convs) // reps
+                for i, rec in enumerate(convs):
+                    name = names[i % per_step] if per_step == len(names) else f"conv{i % per_step}"
+                    d = per_layer.setdefault(name, {"pack_ms": 0.0, "conv_ms": 0.0})
+                    d["conv_ms"] += rec[1].elapsed_time(rec[2]) / reps
+                pack_total = sum(r[1].elapsed_time(r[2]) for r in packs) / reps
+                per_layer["_pack_launches_total"] = {"pack_ms": pack_total, "conv_ms": 0.0, "bytes": 0, "bmac": 0,
+                                                     "n_per_step": len(packs) // reps}
             for name, d in per_layer.items():
-                d.update(algo[name])
-                d["conv_tbmac_s"] = d["bmac"] / (d["conv_ms"] * 1e-3) * 1e-12
-                d["path_gb_s"] = d["bytes"] / ((d["pack_ms"] + d["conv_ms"]) * 1e-3) * 1e-9
+                d.setdefault("bytes", 0); d.setdefault("bmac", 0)
+                if name in algo:
+                    d.update(algo[name])
+                    d["conv_tbmac_s"] = d["bmac"] / (d["conv_ms"] * 1e-3) * 1e-12
+                    d["path_gb_s"] = d["bytes"] / ((d["pack_ms"] + d["conv_ms"]) * 1e-3) * 1e-9
 
     if rank != 0:
         if world > 1:
@@ -384,7 +415,9 @@ def main():
                    "global_batch": images, "parallelism": f"dp{world}",
                    "l2": f"input batch {B * 3 * RES * RES * 4 / 1e6:.0f} MB + activations exceed the 126 MB L2",
                    "launch": "cuda_graph" if graph is not None else "eager",
-                   "glue": "torch eager fp32 (TF32 off) for stem/BN/act/pool/fc"},
+                   "fusion": "per-layer" if args.no_fuse else "bnn_b200.fuse.optimize (BN/act/residual/sign in conv epilogues)",
+                   "glue": "torch fp32 (TF32 off): stem conv7x7+BN+ReLU+maxpool, avgpool, fc"
+                           + (", BN/act/add per layer" if args.no_fuse else "")},
         "clocks": clocks,
         "e2e": {"value": images / (ms_e2e / args.steps * 1e-3), "unit": "images/s",
                 "h2d_bytes_per_step": B * 3 * RES * RES * 4 * world, "d2h_bytes_per_step": images * 1000 * 4 * world,

@@ -29,15 +29,20 @@
 
 namespace bnn {
 
-struct ConvArgs {
-    const uint4* abits;
-    const uint32_t* cnt;
-    const uint2* wbits;
-    const float* scale;
-    const float* bias;
-    const float* post;
+struct Epi {                       // device view of bnn_epilogue
+    const float *scale, *bias, *post, *bn_scale, *bn_shift, *slope, *nx_scale, *nx_shift;
+    const float* res;
+    long long rn, rc, rh, rw;
     float* out;
     long long on, oc, oh, ow;
+    uint4* obits;
+    int act, res_after_act, ochunks;
+};
+
+struct ConvArgs {
+    const uint4* abits;
+    const uint2* wbits;
+    Epi e;
     int N, Cin, H, W, Cout, KH, KW, SH, SW, PH, PW, DH, DW, Ho, Wo;
     int nch, nk, nblk32;          // 64-ch chunks, k-steps, 32-channel output blocks
     int TH, TW, BH, BW;           // output tile, input box
@@ -47,6 +52,9 @@ struct ConvArgs {
     int stage_ldg;
 };
 
+// per-CTA table of per-channel epilogue constants in shared memory: [EP_N][32*C]
+enum { EP_SCALE = 0, EP_BIAS, EP_POST, EP_BNS, EP_BNH, EP_SLOPE, EP_NXS, EP_NXH, EP_N };
+
 __device__ __forceinline__ int word_dis(uint32_t m, uint32_t s, uint32_t t) { return __popc(m & (s ^ t)); }
 __device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (c & (a ^ b)); }
 
@@ -54,12 +62,13 @@ template <int P, int C, int KWT, int SWT, int MODE>
 __global__ void __launch_bounds__(256, 2)
 bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ConvArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
+    constexpr int PITCH = P | 1;      // odd pitch: conflict-free transposes
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
     uint4* act = reinterpret_cast<uint4*>(smem + 128);
-    uint2* wsm = reinterpret_cast<uint2*>(smem + 128 + ((a.act_bytes + 127u) & ~127u));
-    // per-warp transpose buffer for the epilogue: 32 channels x PITCH pixels (odd pitch: no conflicts)
-    constexpr int PITCH = P | 1;
-    float* stage_all = reinterpret_cast<float*>(smem + 128 + ((a.act_bytes + 127u) & ~127u) + (size_t)C * a.w_bytes);
+    unsigned char* after_act = smem + 128 + ((a.act_bytes + 127u) & ~127u);
+    uint2* wsm = reinterpret_cast<uint2*>(after_act);
+    float* stage_all = reinterpret_cast<float*>(after_act + (size_t)C * a.w_bytes);
+    float* epc = stage_all + (blockDim.x >> 5) * (32 * PITCH);      // [EP_N][32*C]
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     int unit = blockIdx.x;
@@ -87,7 +96,6 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
             for (int j = 0; j < nvalid; ++j)
                 bulk_load_1d(wsm + (size_t)j * nk32, a.wbits + (size_t)(blk0 + j) * nk32, a.w_bytes, bar);
         }
-        mbar_wait(bar, 0);
     } else {
         const int units = a.nch * a.BH * a.BW;
         for (int i = threadIdx.x; i < units; i += blockDim.x) {
@@ -105,23 +113,30 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
             const uint2* src = a.wbits + (size_t)(blk0 + j) * nk32;
             for (int i = threadIdx.x; i < nk32; i += blockDim.x) wsm[(size_t)j * nk32 + i] = src[i];
         }
-        __syncthreads();
     }
+    // per-channel epilogue constants -> shared memory (overlaps the TMA flight time)
+    for (int i = threadIdx.x; i < 32 * C; i += blockDim.x) {
+        const int c = blk0 * 32 + i;
+        const bool ok = c < a.Cout;
+        epc[EP_SCALE * 32 * C + i] = (ok && a.e.scale) ? __ldg(a.e.scale + c) : 1.0f;
+        epc[EP_BIAS * 32 * C + i] = (ok && a.e.bias) ? __ldg(a.e.bias + c) : 0.0f;
+        epc[EP_POST * 32 * C + i] = (ok && a.e.post) ? __ldg(a.e.post + c) : 1.0f;
+        epc[EP_BNS * 32 * C + i] = (ok && a.e.bn_scale) ? __ldg(a.e.bn_scale + c) : 1.0f;
+        epc[EP_BNH * 32 * C + i] = (ok && a.e.bn_shift) ? __ldg(a.e.bn_shift + c) : 0.0f;
+        epc[EP_SLOPE * 32 * C + i] = (ok && a.e.slope) ? __ldg(a.e.slope + c) : 0.0f;
+        epc[EP_NXS * 32 * C + i] = (ok && a.e.nx_scale) ? __ldg(a.e.nx_scale + c) : 1.0f;
+        epc[EP_NXH * 32 * C + i] = (ok && a.e.nx_shift) ? __ldg(a.e.nx_shift + c) : 0.0f;
+    }
+    __syncthreads();
+    if (!a.stage_ldg) mbar_wait(bar, 0);
 
-    // ---------------- per-lane epilogue constants ----------------
-    float e_scale[C], e_bias[C], e_post[C];
-    bool c_ok[C];
-#pragma unroll
-    for (int j = 0; j < C; ++j) {
-        const int c = (blk0 + j) * 32 + lane;
-        c_ok[j] = c < a.Cout;
-        e_scale[j] = (c_ok[j] && a.scale) ? __ldg(a.scale + c) : 1.0f;
-        e_bias[j] = (c_ok[j] && a.bias) ? __ldg(a.bias + c) : 0.0f;
-        e_post[j] = (c_ok[j] && a.post) ? __ldg(a.post + c) : 1.0f;
-    }
     const int SW = (KWT > 0) ? SWT : a.SW;
     const int KW = (KWT > 0) ? KWT : a.KW;
     const int DW = (KWT > 0) ? 1 : a.DW;
+    float* stg = stage_all + warp * (32 * PITCH);
+    constexpr int PW = (P > 4) ? 8 : 4;          // lanes per channel row in the transposed phases
+    constexpr int ROWS = 32 / PW;                // channel rows per load/store instruction
+    const int pr = lane % PW, rr = lane / PW;
 
     // ---------------- pixel groups ----------------
     for (int g = warp; g < a.G; g += nwarps) {
@@ -130,6 +145,27 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
         const int ho = ho0 + r;
         const int wo_first = wo0 + wq;
         if (ho >= a.Ho || wo_first >= a.Wo) continue;   // warp-uniform
+
+        // ---- number of non-zero inputs under each pixel's window: popc of the m planes already in
+        //      shared memory, spread over the lanes (lane = pixel + 8*part), summed by two shuffles
+        int msum = 0;
+        {
+            const int pix = lane & 7, part = lane >> 3;
+            int it = 0;
+            if (pix < P) {
+                for (int ch = 0; ch < a.nch; ++ch)
+                    for (int kh = 0; kh < a.KH; ++kh) {
+                        const uint4* arow = act + (size_t)(ch * a.BH + r * a.SH + kh * a.DH) * a.BW + (wq + pix) * SW;
+                        for (int kw = 0; kw < KW; ++kw, ++it)
+                            if ((it & 3) == part) {
+                                const uint4 v = arow[kw * DW];
+                                msum += __popc(v.z) + __popc(v.w);
+                            }
+                    }
+            }
+            msum += __shfl_xor_sync(0xffffffffu, msum, 8);
+            msum += __shfl_xor_sync(0xffffffffu, msum, 16);
+        }
 
         int acc[P][C];
 #pragma unroll
@@ -209,68 +245,114 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
             }
         }
 
-        // number of non-zero inputs under each pixel's receptive field (lane p <-> pixel p)
-        int msum = 0;
-        if (lane < P) {
-            const int wo = wo_first + lane;
-            if (wo < a.Wo) {
-                for (int kh = 0; kh < a.KH; ++kh) {
-                    const int hi = ho * a.SH - a.PH + kh * a.DH;
-                    if ((unsigned)hi >= (unsigned)a.H) continue;
-                    for (int kw = 0; kw < KW; ++kw) {
-                        const int wi = wo * SW - a.PW + kw * DW;
-                        if ((unsigned)wi < (unsigned)a.W) msum += (int)__ldg(a.cnt + ((size_t)n * a.H + hi) * a.W + wi);
+        // ---------------- fused epilogue (order fixed by include/bnn_b200.h) ----------------
+        int ms[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) ms[p] = __shfl_sync(0xffffffffu, msum, p);
+        const bool transposed = (a.e.ow == 1) || (a.e.out == nullptr);
+        uint32_t sbits[C], mbits[C];     // lane p keeps the packed words of pixel p
+#pragma unroll
+        for (int j = 0; j < C; ++j) { sbits[j] = 0u; mbits[j] = 0u; }
+
+#pragma unroll
+        for (int j = 0; j < C; ++j) {
+            const int cl = j * 32 + lane;                // channel inside the CTA tile
+            const int cblk = (blk0 + j) * 32;
+            const bool c_ok = cblk + lane < a.Cout;
+            const float k_scale = epc[EP_SCALE * 32 * C + cl], k_bias = epc[EP_BIAS * 32 * C + cl],
+                        k_post = epc[EP_POST * 32 * C + cl];
+            float res[P];
+            if (a.e.res != nullptr) {
+                // residual tile [32 ch][P px] -> per-lane channel rows, coalesced along pixels when rw == 1
+                const float* rbase = a.e.res + (long long)n * a.e.rn + (long long)ho * a.e.rh;
+                if (a.e.rw == 1) {
+                    __syncwarp();
+#pragma unroll
+                    for (int r0 = 0; r0 < 32; r0 += ROWS) {
+                        const int rl = r0 + rr, c = cblk + rl, wo = wo_first + pr;
+                        float v = 0.0f;
+                        if (pr < P && wo < a.Wo && c < a.Cout) v = __ldg(rbase + (long long)c * a.e.rc + wo);
+                        if (pr < P) stg[rl * PITCH + pr] = v;
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int p = 0; p < P; ++p) res[p] = stg[lane * PITCH + p];
+                } else {
+#pragma unroll
+                    for (int p = 0; p < P; ++p) {
+                        const int wo = wo_first + p;
+                        res[p] = (c_ok && wo < a.Wo)
+                                     ? __ldg(rbase + (long long)(cblk + lane) * a.e.rc + (long long)wo * a.e.rw) : 0.0f;
+                    }
+                }
+            }
+            float v[P];
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                float y = __fmul_rn(k_scale, (float)(ms[p] - 2 * acc[p][j]));
+                if (a.e.bias) y = __fadd_rn(y, k_bias);
+                if (a.e.post) y = __fmul_rn(y, k_post);
+                if (a.e.bn_scale) y = __fadd_rn(__fmul_rn(y, epc[EP_BNS * 32 * C + cl]), epc[EP_BNH * 32 * C + cl]);
+                if (a.e.res != nullptr && !a.e.res_after_act) y = __fadd_rn(y, res[p]);
+                if (a.e.act == BNN_ACT_RELU) y = (y > 0.0f) ? y : ((y != y) ? y : 0.0f);    // NaN propagates like torch.relu
+                else if (a.e.act == BNN_ACT_PRELU) y = (y > 0.0f) ? y : __fmul_rn(epc[EP_SLOPE * 32 * C + cl], y);
+                if (a.e.res != nullptr && a.e.res_after_act) y = __fadd_rn(y, res[p]);
+                v[p] = y;
+            }
+            if (a.e.obits != nullptr) {
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    float b = v[p];
+                    if (a.e.nx_scale) b = __fadd_rn(__fmul_rn(b, epc[EP_NXS * 32 * C + cl]), epc[EP_NXH * 32 * C + cl]);
+                    const uint32_t sw = __ballot_sync(0xffffffffu, c_ok && b > 0.0f);
+                    const uint32_t mw = __ballot_sync(0xffffffffu, c_ok && (b > 0.0f || b < 0.0f));
+                    if (lane == p) { sbits[j] = sw; mbits[j] = mw; }
+                }
+            }
+            if (a.e.out != nullptr) {
+                float* obase = a.e.out + (long long)n * a.e.on + (long long)ho * a.e.oh;
+                if (!transposed) {
+                    // channel-contiguous output (Linear's [rows, out]): lanes <-> channels is already coalesced
+#pragma unroll
+                    for (int p = 0; p < P; ++p) {
+                        const int wo = wo_first + p;
+                        if (c_ok && wo < a.Wo) obase[(long long)(cblk + lane) * a.e.oc + (long long)wo * a.e.ow] = v[p];
+                    }
+                } else {
+                    // pixel-contiguous output (NCHW): transpose through shared memory so one store instruction
+                    // writes whole 32-byte pixel runs instead of 32 scattered words
+                    __syncwarp();
+#pragma unroll
+                    for (int p = 0; p < P; ++p) stg[lane * PITCH + p] = v[p];
+                    __syncwarp();
+#pragma unroll
+                    for (int r0 = 0; r0 < 32; r0 += ROWS) {
+                        const int rl = r0 + rr, c = cblk + rl, wo = wo_first + pr;
+                        if (pr < P && wo < a.Wo && c < a.Cout) obase[(long long)c * a.e.oc + wo] = stg[rl * PITCH + pr];
                     }
                 }
             }
         }
-
-        // fused epilogue: y = (alpha_w * dot + bias) * alpha_post, same order as the reference
-        float* obase = a.out + (long long)n * a.on + (long long)ho * a.oh;
-        int ms[P];
-#pragma unroll
-        for (int p = 0; p < P; ++p) ms[p] = __shfl_sync(0xffffffffu, msum, p);
-        if (a.ow != 1) {
-            // channel-contiguous output (Linear's [rows, out]): lanes <-> channels is already coalesced
-#pragma unroll
-            for (int p = 0; p < P; ++p) {
-                const int wo = wo_first + p;
-                if (wo >= a.Wo) break;
-#pragma unroll
-                for (int j = 0; j < C; ++j) {
-                    if (!c_ok[j]) continue;
-                    const int c = (blk0 + j) * 32 + lane;
-                    float y = __fmul_rn(e_scale[j], (float)(ms[p] - 2 * acc[p][j]));
-                    if (a.bias) y = __fadd_rn(y, e_bias[j]);
-                    if (a.post) y = __fmul_rn(y, e_post[j]);
-                    obase[(long long)c * a.oc + (long long)wo * a.ow] = y;
-                }
-            }
-        } else {
-            // pixel-contiguous output (NCHW): transpose each 32-channel block through shared memory so a
-            // store instruction covers whole 32-byte runs of P pixels instead of 32 scattered words
-            float* stg = stage_all + warp * (32 * PITCH);
-            constexpr int PW = (P > 4) ? 8 : 4;          // lanes per channel row when reading back
-            constexpr int ROWS = 32 / PW;                // channel rows per store instruction
-            const int pr = lane % PW, rr = lane / PW;
+        if (a.e.obits != nullptr && lane < P && wo_first + lane < a.Wo) {
+            // lane p writes the 16-byte units of pixel p: consecutive lanes -> consecutive units (coalesced)
+            uint32_t* ob = reinterpret_cast<uint32_t*>(a.e.obits);
 #pragma unroll
             for (int j = 0; j < C; ++j) {
-                __syncwarp();
-#pragma unroll
-                for (int p = 0; p < P; ++p) {
-                    float y = __fmul_rn(e_scale[j], (float)(ms[p] - 2 * acc[p][j]));
-                    if (a.bias) y = __fadd_rn(y, e_bias[j]);
-                    if (a.post) y = __fmul_rn(y, e_post[j]);
-                    stg[lane * PITCH + p] = y;
-                }
-                __syncwarp();
-                const int cblk = (blk0 + j) * 32;
-#pragma unroll
-                for (int r0 = 0; r0 < 32; r0 += ROWS) {
-                    const int cl = r0 + rr;
-                    const int c = cblk + cl, wo = wo_first + pr;
-                    if (pr < P && wo < a.Wo && c < a.Cout)
-                        obase[(long long)c * a.oc + wo] = stg[cl * PITCH + pr];
+                const int blk = blk0 + j;
+                if (blk >= a.nblk32) break;
+                const size_t unit_idx = (((size_t)n * a.e.ochunks + (blk >> 1)) * a.Ho + ho) * a.Wo + wo_first + lane;
+                if (C >= 2) {
+                    if ((j & 1) == 0) {       // blk0 is even when C >= 2: (j, j+1) form one 64-channel unit
+                        constexpr int JH = (C >= 2) ? 1 : 0;
+                        reinterpret_cast<uint4*>(ob)[unit_idx] = make_uint4(sbits[j], sbits[j + JH], mbits[j], mbits[j + JH]);
+                    }
+                } else {
+                    ob[unit_idx * 4 + (blk & 1)] = sbits[j];
+                    ob[unit_idx * 4 + 2 + (blk & 1)] = mbits[j];
+                    if ((blk & 1) == 0 && blk + 1 >= a.nblk32) {   // no odd partner: its half of the unit is zero
+                        ob[unit_idx * 4 + 1] = 0u;
+                        ob[unit_idx * 4 + 3] = 0u;
+                    }
                 }
             }
         }
@@ -327,92 +409,90 @@ static KernelFn pick_kernel(const Plan& p) {
 
 static int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
-// Choose tile shape for one layer.  Small search, host only, microseconds.
+static size_t plan_smem(int nch, int BH, int BW, int C, int nk, int NW, int P) {
+    const size_t act_bytes = (size_t)nch * BH * BW * 16;
+    return 128 + ((act_bytes + 127) & ~(size_t)127) + (size_t)C * nk * 256 + (size_t)NW * 32 * (P | 1) * 4 +
+           (size_t)EP_N * 32 * C * 4;
+}
+
+// Choose the tile shape for one layer by minimising a small cost model (host only, microseconds):
+//   time ~ waves x (rounds x work_per_round + staging), waves = ceil(CTAs / (SMs x CTAs_per_SM)).
+// It captures the three measured loss terms: idle lanes of partial pixel groups / idle warps in the last
+// round, the tail of the last wave, and the staging latency of very small CTAs.
 static int make_plan(const bnn_conv_geom& g, int Ho, int Wo, uint32_t flags, int sms, Plan* out) {
-    Plan pl{};
     const int nch = ceil_div(g.c_in, 64), nk = nch * g.kh * g.kw;
     if (nch > 256) return BNN_E_UNSUPPORTED;
-    // specialisation on kernel width / horizontal stride (dilation_w must be 1)
-    pl.kwt = 0; pl.swt = 0;
+    int kwt = 0, swt = 0;            // unrolled instances: kernel width x horizontal stride, dilation_w == 1
     if (g.dil_w == 1) {
-        if (g.kw == 3 && (g.stride_w == 1 || g.stride_w == 2)) { pl.kwt = 3; pl.swt = g.stride_w; }
-        else if (g.kw == 1 && g.stride_w == 1) { pl.kwt = 1; pl.swt = 1; }
+        if (g.kw == 3 && (g.stride_w == 1 || g.stride_w == 2)) { kwt = 3; swt = g.stride_w; }
+        else if (g.kw == 1 && g.stride_w == 1) { kwt = 1; swt = 1; }
     }
-    pl.mode = (pl.kwt == 3 && !(flags & BNN_F_NO_CSA)) ? 1 : 0;
-
-    // output channels per lane
+    const int mode = (kwt == 3 && !(flags & BNN_F_NO_CSA)) ? 1 : 0;
     const int nblk32 = ceil_div(g.c_out, 32);
-    int C = nblk32 >= 4 ? 4 : (nblk32 >= 2 ? 2 : 1);
-    const size_t smem_cap = 200 * 1024;
-    while (C > 1 && (size_t)C * nk * 256 > 96 * 1024) C >>= 1;
-    const size_t wbytes = (size_t)C * nk * 256;
-    if (wbytes + 8192 > smem_cap) return BNN_E_UNSUPPORTED;
-    const size_t act_budget = (wbytes <= 64 * 1024 ? 110 * 1024 : smem_cap) - wbytes - 256 - 8 * 32 * 9 * 4;
+    const size_t smem_cap = 220 * 1024;
 
-    // pixels per group: least padding waste, then prefer a register window, then larger
-    const int cand[3] = {8, 7, 4};
-    int bestP = 0; double bestW = 1e9;
-    for (int i = 0; i < 3; ++i) {
-        const int P = cand[i];
-        const int sw = pl.kwt ? pl.swt : 1, kw = pl.kwt ? pl.kwt : 1;
-        const bool window = ((P - 1) * sw + kw) <= 12;
-        double waste = (double)ceil_div(Wo, P) * P / Wo;
-        waste += window ? 0.0 : 0.02;
-        waste -= 0.001 * P;
-        if (waste < bestW) { bestW = waste; bestP = P; }
-    }
-    pl.P = bestP; pl.C = C;
-
-    // tile width: whole row if the input box fits the 256-element TMA box limit
-    const int wo_pad = ceil_div(Wo, pl.P) * pl.P;
-    int TW = wo_pad;
-    while ((TW - 1) * g.stride_w + (g.kw - 1) * g.dil_w + 1 > 256 && TW > pl.P) TW -= pl.P;
-    if ((TW - 1) * g.stride_w + (g.kw - 1) * g.dil_w + 1 > 256) return BNN_E_UNSUPPORTED;
-    pl.TW = TW;
-    pl.BW = (TW - 1) * g.stride_w + (g.kw - 1) * g.dil_w + 1;
-    pl.gpr = TW / pl.P;
-    pl.tiles_w = ceil_div(Wo, TW);
-
-    // tile height / warps per CTA: minimise (row padding) x (idle warps in the last round)
-    double best = 1e18; int bTH = 0, bNW = 0;
-    const long long cout_tiles = ceil_div(nblk32, C);
-    for (int NW = 8; NW >= 7; --NW) {
-        for (int TH = 1; TH <= Ho; ++TH) {
-            const int BH = (TH - 1) * g.stride_h + (g.kh - 1) * g.dil_h + 1;
-            if (BH > 256) break;
-            if ((size_t)nch * BH * pl.BW * 16 > act_budget) break;
-            const int G = TH * pl.gpr;
-            const int rounds = ceil_div(G, NW);
-            if (rounds > 8 && TH > 1) break;
-            const double row_waste = (double)ceil_div(Ho, TH) * TH / Ho;
-            const double warp_waste = (double)rounds * NW / G;
-            const double halo = (double)BH / ((TH - 1) * g.stride_h + 1);     // staging re-reads
-            const long long ctas = (long long)g.n * ceil_div(Ho, TH) * pl.tiles_w * cout_tiles;
-            const double fill = ctas < 2LL * sms ? (double)(2LL * sms) / (double)ctas : 1.0;
-            const double score = row_waste * warp_waste * (1.0 + 0.01 * halo) * (1.0 + 0.25 * (fill - 1.0)) *
-                                 (1.0 + 0.02 / rounds) * (NW == 8 ? 1.0 : 1.01);
-            if (score < best) { best = score; bTH = TH; bNW = NW; }
+    double best = 1e300;
+    Plan bp{};
+    const int candP[3] = {8, 7, 4}, candC[3] = {4, 2, 1};
+    for (int ci = 0; ci < 3; ++ci) {
+        const int C = candC[ci];
+        if (C > 1 && C / 2 >= nblk32) continue;                  // would only add idle channel blocks
+        const size_t wbytes = (size_t)C * nk * 256;
+        if (wbytes + 16 * 1024 > smem_cap) continue;
+        const int cout_tiles = ceil_div(nblk32, C);
+        for (int pi = 0; pi < 3; ++pi) {
+            const int P = candP[pi];
+            const int usw = kwt ? swt : 1, ukw = kwt ? kwt : 1;
+            const bool window = ((P - 1) * usw + ukw) <= 12;
+            int TW = ceil_div(Wo, P) * P;
+            while ((TW - 1) * g.stride_w + (g.kw - 1) * g.dil_w + 1 > 256 && TW > P) TW -= P;
+            const int BW = (TW - 1) * g.stride_w + (g.kw - 1) * g.dil_w + 1;
+            if (BW > 256) continue;
+            const int gpr = TW / P, tiles_w = ceil_div(Wo, TW);
+            // cycles per 32-bit word per warp: fewer channels per lane -> more shared-memory loads per word
+            double cpw = (C == 4 ? 1.0 : C == 2 ? 1.08 : 1.25) * (window ? 1.0 : 1.12) * (P == 4 ? 1.06 : 1.0);
+            const double round_work = (double)P * C * nk * 2.0 * cpw + 60.0 * P * C;   // main loop + epilogue
+            for (int NW = 8; NW >= 7; --NW) {
+                for (int TH = 1; TH <= Ho; ++TH) {
+                    const int BH = (TH - 1) * g.stride_h + (g.kh - 1) * g.dil_h + 1;
+                    if (BH > 256) break;
+                    const size_t smem = plan_smem(nch, BH, BW, C, nk, NW, P);
+                    if (smem > smem_cap) break;
+                    const int G = TH * gpr, rounds = ceil_div(G, NW);
+                    if (rounds > 12 && TH > 1) break;
+                    const int occ = smem * 2 <= 226 * 1024 ? 2 : 1;
+                    const long long ctas = (long long)g.n * ceil_div(Ho, TH) * tiles_w * cout_tiles;
+                    const long long slots = (long long)sms * occ;
+                    const double waves = (double)((ctas + slots - 1) / slots);
+                    // warps of co-resident CTAs share the SM's issue slots: 8*occ warps over 4 schedulers
+                    const double share = (double)(NW * occ) / 4.0;
+                    const double stage = 1500.0 + 0.02 * (double)(smem);
+                    const double t = waves * (rounds * round_work * share + stage);
+                    if (t < best) {
+                        best = t;
+                        bp.P = P; bp.C = C; bp.kwt = kwt; bp.swt = swt; bp.mode = mode;
+                        bp.TH = TH; bp.TW = TW; bp.BH = BH; bp.BW = BW; bp.NW = NW; bp.gpr = gpr; bp.G = G;
+                        bp.tiles_h = ceil_div(Ho, TH); bp.tiles_w = tiles_w; bp.smem = smem;
+                    }
+                }
+            }
         }
     }
-    if (bTH == 0) return BNN_E_UNSUPPORTED;
-    pl.TH = bTH; pl.NW = bNW;
-    pl.BH = (bTH - 1) * g.stride_h + (g.kh - 1) * g.dil_h + 1;
-    pl.G = bTH * pl.gpr;
-    pl.tiles_h = ceil_div(Ho, bTH);
-    const size_t act_bytes = (size_t)nch * pl.BH * pl.BW * 16;
-    pl.smem = 128 + ((act_bytes + 127) & ~(size_t)127) + wbytes + (size_t)pl.NW * 32 * (pl.P | 1) * 4;
-    *out = pl;
+    if (best >= 1e300) return BNN_E_UNSUPPORTED;
+    *out = bp;
     return 0;
 }
 
-static int launch_bconv(const void* abits, const uint32_t* cnt, const void* wbits, const float* scale,
-                        const float* bias, const float* post, float* out, int64_t on, int64_t oc, int64_t oh,
-                        int64_t ow, const bnn_conv_geom& g, uint32_t flags, cudaStream_t stream) {
-    if (!abits || !cnt || !wbits || !out) return BNN_E_NULL;
+static int launch_bconv(const void* abits, const void* wbits, const bnn_conv_geom& g, const bnn_epilogue& ep,
+                        uint32_t flags, cudaStream_t stream) {
+    if (!abits || !wbits || (!ep.out && !ep.out_bits)) return BNN_E_NULL;
     if (g.n <= 0 || g.c_in <= 0 || g.h <= 0 || g.w <= 0 || g.c_out <= 0 || g.kh <= 0 || g.kw <= 0 ||
         g.stride_h <= 0 || g.stride_w <= 0 || g.pad_h < 0 || g.pad_w < 0 || g.dil_h <= 0 || g.dil_w <= 0)
         return BNN_E_SHAPE;
-    if (((uintptr_t)abits & 15) || ((uintptr_t)wbits & 15)) return BNN_E_ALIGN;
+    if (ep.act < BNN_ACT_NONE || ep.act > BNN_ACT_PRELU || (ep.act == BNN_ACT_PRELU && !ep.act_slope)) return BNN_E_SHAPE;
+    if ((ep.bn_scale == nullptr) != (ep.bn_shift == nullptr) || (ep.nx_scale == nullptr) != (ep.nx_shift == nullptr))
+        return BNN_E_NULL;
+    if (((uintptr_t)abits & 15) || ((uintptr_t)wbits & 15) || ((uintptr_t)ep.out_bits & 15)) return BNN_E_ALIGN;
     const int Ho = out_dim(g.h, g.kh, g.stride_h, g.pad_h, g.dil_h);
     const int Wo = out_dim(g.w, g.kw, g.stride_w, g.pad_w, g.dil_w);
     if (Ho <= 0 || Wo <= 0) return BNN_E_SHAPE;
@@ -434,9 +514,14 @@ static int launch_bconv(const void* abits, const uint32_t* cnt, const void* wbit
     if (!fn) return BNN_E_UNSUPPORTED;
 
     ConvArgs a{};
-    a.abits = (const uint4*)abits; a.cnt = cnt; a.wbits = (const uint2*)wbits;
-    a.scale = scale; a.bias = bias; a.post = post; a.out = out;
-    a.on = on; a.oc = oc; a.oh = oh; a.ow = ow;
+    a.abits = (const uint4*)abits; a.wbits = (const uint2*)wbits;
+    a.e.scale = ep.scale; a.e.bias = ep.bias; a.e.post = ep.post;
+    a.e.bn_scale = ep.bn_scale; a.e.bn_shift = ep.bn_shift; a.e.slope = ep.act_slope;
+    a.e.nx_scale = ep.nx_scale; a.e.nx_shift = ep.nx_shift;
+    a.e.res = ep.residual; a.e.rn = ep.rstride_n; a.e.rc = ep.rstride_c; a.e.rh = ep.rstride_h; a.e.rw = ep.rstride_w;
+    a.e.out = ep.out; a.e.on = ep.ostride_n; a.e.oc = ep.ostride_c; a.e.oh = ep.ostride_h; a.e.ow = ep.ostride_w;
+    a.e.obits = (uint4*)ep.out_bits; a.e.act = ep.act; a.e.res_after_act = ep.residual_after_act;
+    a.e.ochunks = ceil_div(g.c_out, 64);
     a.N = g.n; a.Cin = g.c_in; a.H = g.h; a.W = g.w; a.Cout = g.c_out; a.KH = g.kh; a.KW = g.kw;
     a.SH = g.stride_h; a.SW = g.stride_w; a.PH = g.pad_h; a.PW = g.pad_w; a.DH = g.dil_h; a.DW = g.dil_w;
     a.Ho = Ho; a.Wo = Wo;
@@ -481,19 +566,31 @@ static int launch_bconv(const void* abits, const uint32_t* cnt, const void* wbit
 
 using namespace bnn;
 
-extern "C" int bnn_bconv2d_fwd(const void* abits, const uint32_t* cnt, const void* wbits, const float* scale,
-                               const float* bias, const float* post, float* out, int64_t on, int64_t oc,
-                               int64_t oh, int64_t ow, const bnn_conv_geom* geom, uint32_t flags, void* stream) {
-    if (!geom) return BNN_E_NULL;
-    return launch_bconv(abits, cnt, wbits, scale, bias, post, out, on, oc, oh, ow, *geom, flags,
-                        (cudaStream_t)stream);
+extern "C" int bnn_bconv2d_fused_fwd(const void* abits, const void* wbits, const bnn_conv_geom* geom,
+                                     const bnn_epilogue* epilogue, uint32_t flags, void* stream) {
+    if (!geom || !epilogue) return BNN_E_NULL;
+    return launch_bconv(abits, wbits, *geom, *epilogue, flags, (cudaStream_t)stream);
 }
 
-extern "C" int bnn_blinear_fwd(const void* abits, const uint32_t* cnt, const void* wbits, const float* scale,
-                               const float* bias, const float* post, float* out, int32_t rows,
-                               int32_t in_features, int32_t out_features, uint32_t flags, void* stream) {
+extern "C" int bnn_bconv2d_fwd(const void* abits, const void* wbits, const float* scale, const float* bias,
+                               const float* post, float* out, int64_t on, int64_t oc, int64_t oh, int64_t ow,
+                               const bnn_conv_geom* geom, uint32_t flags, void* stream) {
+    if (!geom) return BNN_E_NULL;
+    if (!out) return BNN_E_NULL;
+    bnn_epilogue ep{};
+    ep.scale = scale; ep.bias = bias; ep.post = post;
+    ep.out = out; ep.ostride_n = on; ep.ostride_c = oc; ep.ostride_h = oh; ep.ostride_w = ow;
+    return launch_bconv(abits, wbits, *geom, ep, flags, (cudaStream_t)stream);
+}
+
+extern "C" int bnn_blinear_fwd(const void* abits, const void* wbits, const float* scale, const float* bias,
+                               const float* post, float* out, int32_t rows, int32_t in_features,
+                               int32_t out_features, uint32_t flags, void* stream) {
+    if (!out) return BNN_E_NULL;
     // rows play the role of the image width: x is [1, in, 1, rows], out is stored [rows, out]
     bnn_conv_geom g{1, in_features, 1, rows, out_features, 1, 1, 1, 1, 0, 0, 1, 1};
-    return launch_bconv(abits, cnt, wbits, scale, bias, post, out, 0, 1, 0, (int64_t)out_features, g, flags,
-                        (cudaStream_t)stream);
+    bnn_epilogue ep{};
+    ep.scale = scale; ep.bias = bias; ep.post = post;
+    ep.out = out; ep.ostride_n = 0; ep.ostride_c = 1; ep.ostride_h = 0; ep.ostride_w = (int64_t)out_features;
+    return launch_bconv(abits, wbits, g, ep, flags, (cudaStream_t)stream);
 }

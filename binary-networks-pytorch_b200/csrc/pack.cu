@@ -12,16 +12,28 @@
 namespace bnn {
 
 // ---------------------------------------------------------------------------
-// activations: fp32 (element strides) -> abits[n][chunk][h][w] + cnt[n][h][w]
+// activations: fp32 (element strides) -> abits[n][chunk][h][w]
 // one thread = one (n, chunk, h, w) unit = 64 channels of one pixel; adjacent
 // lanes are adjacent w, so every one of the 64 loads of a warp is one 128-B line
-// for NCHW input.
+// for NCHW input.  POOL > 0 averages a POOL x POOL window first (AvgPool2d with
+// kernel = stride, count_include_pad = False): sum in row-major order, divide by
+// the number of in-bounds elements, exactly like torch's CPU kernel.
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ float load_pooled(const float* p, long long sh, long long sw, int k, int hmax, int wmax) {
+    if (k <= 1) return __ldg(p);
+    float sum = 0.0f;
+    int cnt = 0;
+    for (int i = 0; i < k && i < hmax; ++i)
+        for (int j = 0; j < k && j < wmax; ++j) { sum = __fadd_rn(sum, __ldg(p + i * sh + j * sw)); ++cnt; }
+    return __fdiv_rn(sum, (float)cnt);
+}
+
 __global__ void __launch_bounds__(256)
 pack_act_kernel(const float* __restrict__ x, long long sn, long long sc, long long sh, long long sw,
-                int N, int C, int H, int W, int nch, uint4* __restrict__ abits,
-                uint32_t* __restrict__ cnt) {
-    const long long total = (long long)N * nch * H * W;
+                int N, int C, int H, int W, int nch, int pool, int Hin, int Win,
+                const float* __restrict__ pre_scale, const float* __restrict__ pre_shift,
+                uint4* __restrict__ abits) {
+    const long long total = (long long)N * nch * H * W;       // H, W: OUTPUT (pooled) plane size
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int w = (int)(idx % W);
@@ -31,10 +43,12 @@ pack_act_kernel(const float* __restrict__ x, long long sn, long long sc, long lo
     const int ch = (int)(r % nch);
     const int n = (int)(r / nch);
 
-    const float* base = x + n * sn + h * sh + w * sw + (long long)ch * 64 * sc;
+    const int k = pool > 1 ? pool : 1;
+    const float* base = x + n * sn + (long long)h * k * sh + (long long)w * k * sw + (long long)ch * 64 * sc;
+    const int hmax = Hin - h * k, wmax = Win - w * k;
     const int cmax = min(64, C - ch * 64);
     uint32_t s[2] = {0u, 0u}, m[2] = {0u, 0u};
-    if (cmax == 64) {
+    if (cmax == 64 && pool <= 1 && pre_scale == nullptr) {
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
 #pragma unroll
@@ -51,18 +65,19 @@ pack_act_kernel(const float* __restrict__ x, long long sn, long long sc, long lo
             }
         }
     } else {
+#pragma unroll 4
         for (int b = 0; b < cmax; ++b) {
-            const float v = __ldg(base + (long long)b * sc);
+            float v = load_pooled(base + (long long)b * sc, sh, sw, k, hmax, wmax);
+            if (pre_scale != nullptr) {
+                const int c = ch * 64 + b;
+                v = __fadd_rn(__fmul_rn(v, __ldg(pre_scale + c)), __ldg(pre_shift + c));
+            }
             const uint32_t pos = v > 0.0f, neg = v < 0.0f;
             s[b >> 5] |= pos << (b & 31);
             m[b >> 5] |= (pos | neg) << (b & 31);
         }
     }
     abits[idx] = make_uint4(s[0], s[1], m[0], m[1]);
-    const uint32_t c = __popc(m[0]) + __popc(m[1]);
-    uint32_t* dst = cnt + ((long long)n * H + h) * W + w;
-    if (nch == 1) *dst = c;
-    else atomicAdd(dst, c);  // cnt zeroed by the launcher; integer adds commute
 }
 
 // ---------------------------------------------------------------------------
@@ -146,36 +161,47 @@ extern "C" size_t bnn_act_bits_bytes(int32_t n, int32_t c, int32_t h, int32_t w)
     if (n <= 0 || c <= 0 || h <= 0 || w <= 0) return 0;
     return (size_t)n * ((c + 63) / 64) * h * w * 16;
 }
-extern "C" size_t bnn_act_cnt_bytes(int32_t n, int32_t h, int32_t w) {
-    if (n <= 0 || h <= 0 || w <= 0) return 0;
-    return (size_t)n * h * w * 4;
-}
 extern "C" size_t bnn_weight_bits_bytes(int32_t c_out, int32_t c_in, int32_t kh, int32_t kw) {
     if (c_out <= 0 || c_in <= 0 || kh <= 0 || kw <= 0) return 0;
     return (size_t)((c_out + 31) / 32) * ((c_in + 63) / 64) * kh * kw * 32 * 8;
 }
 
-extern "C" int bnn_pack_act_f32(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw,
-                                int32_t n, int32_t c, int32_t h, int32_t w, void* abits,
-                                uint32_t* cnt, void* stream_) {
-    if (!x || !abits || !cnt) return BNN_E_NULL;
-    if (n <= 0 || c <= 0 || h <= 0 || w <= 0) return BNN_E_SHAPE;
+static int launch_pack(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, int32_t n, int32_t c,
+                       int32_t h, int32_t w, int32_t pool, int32_t ceil_mode, const float* pre_scale,
+                       const float* pre_shift, void* abits, void* stream_) {
+    if (!x || !abits) return BNN_E_NULL;
+    if ((pre_scale == nullptr) != (pre_shift == nullptr)) return BNN_E_NULL;
+    if (n <= 0 || c <= 0 || h <= 0 || w <= 0 || pool < 0) return BNN_E_SHAPE;
     if (((uintptr_t)abits & 15) != 0) return BNN_E_ALIGN;
     cudaStream_t stream = (cudaStream_t)stream_;
     const int nch = (c + 63) / 64;
-    int launches = 1;
-    if (nch > 1) {
-        cudaError_t e = cudaMemsetAsync(cnt, 0, (size_t)n * h * w * 4, stream);
-        if (e != cudaSuccess) return (int)e;
+    int ho = h, wo = w;
+    if (pool > 1) {
+        ho = ceil_mode ? (h + pool - 1) / pool : h / pool;
+        wo = ceil_mode ? (w + pool - 1) / pool : w / pool;
+        if (ho <= 0 || wo <= 0) return BNN_E_SHAPE;
     }
-    const long long total = (long long)n * nch * h * w;
+    const long long total = (long long)n * nch * ho * wo;
     const int threads = 256;
     const long long blocks = (total + threads - 1) / threads;
     if (blocks > 0x7fffffffLL) return BNN_E_UNSUPPORTED;
-    pack_act_kernel<<<(unsigned)blocks, threads, 0, stream>>>(x, sn, sc, sh, sw, n, c, h, w, nch,
-                                                            (uint4*)abits, cnt);
-    count_launch(launches);
+    pack_act_kernel<<<(unsigned)blocks, threads, 0, stream>>>(x, sn, sc, sh, sw, n, c, ho, wo, nch, pool, h, w,
+                                                            pre_scale, pre_shift, (uint4*)abits);
+    count_launch(1);
     return (int)cudaGetLastError();
+}
+
+extern "C" int bnn_pack_act_f32(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw,
+                                int32_t n, int32_t c, int32_t h, int32_t w, const float* pre_scale,
+                                const float* pre_shift, void* abits, void* stream) {
+    return launch_pack(x, sn, sc, sh, sw, n, c, h, w, 0, 0, pre_scale, pre_shift, abits, stream);
+}
+
+extern "C" int bnn_avgpool_pack_f32(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw,
+                                    int32_t n, int32_t c, int32_t h, int32_t w, int32_t k, int32_t ceil_mode,
+                                    const float* pre_scale, const float* pre_shift, void* abits, void* stream) {
+    if (k < 1) return BNN_E_SHAPE;
+    return launch_pack(x, sn, sc, sh, sw, n, c, h, w, k, ceil_mode, pre_scale, pre_shift, abits, stream);
 }
 
 extern "C" int bnn_pack_weight_f32(const float* w, int32_t c_out, int32_t c_in, int32_t kh, int32_t kw,

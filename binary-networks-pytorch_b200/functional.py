@@ -27,7 +27,6 @@ def _require_cuda_f32(t: torch.Tensor, name: str) -> None:
 class PackedActivations:
     """Sign/mask planes of one activation tensor (layout: include/bnn_b200.h)."""
     bits: torch.Tensor   # int32 [n, chunks, h, w, 4]
-    cnt: torch.Tensor    # int32 [n, h, w]
     n: int
     c: int
     h: int
@@ -46,11 +45,14 @@ class PackedWeights:
     kw: int
 
 
-def pack_activations(x: torch.Tensor, linear_rows: bool = False) -> PackedActivations:
+def pack_activations(x: torch.Tensor, linear_rows: bool = False, pre: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+                     pool: int = 0, ceil_mode: bool = True) -> PackedActivations:
     """``BasicInputBinarizer`` (reference bnn/ops.py:151-152) as a bit-pack.
 
     ``x`` is [n,c,h,w] (any strides) or, with ``linear_rows``, [rows, features] which is packed
-    as n=1, h=1, w=rows so that ``blinear`` can treat rows as pixels."""
+    as n=1, h=1, w=rows so that ``blinear`` can treat rows as pixels.  ``pre=(scale, shift)`` folds a
+    per-channel affine (eval BatchNorm) in front of the sign; ``pool=k`` first applies
+    AvgPool2d(k, k, ceil_mode, count_include_pad=False)."""
     _require_cuda_f32(x, "input")
     if linear_rows:
         rows, feat = x.shape
@@ -60,13 +62,21 @@ def pack_activations(x: torch.Tensor, linear_rows: bool = False) -> PackedActiva
         n, c, h, w = x.shape
         sn, sc, sh, sw = x.stride()
     nch = (c + 63) // 64
+    ho, wo = h, w
+    if pool > 1:
+        ho = -(-h // pool) if ceil_mode else h // pool
+        wo = -(-w // pool) if ceil_mode else w // pool
+    ps, ph = (None, None) if pre is None else (pre[0].data_ptr(), pre[1].data_ptr())
     with torch.cuda.device(x.device):
-        bits = torch.empty((n, nch, h, w, 4), dtype=torch.int32, device=x.device)
-        cnt = torch.empty((n, h, w), dtype=torch.int32, device=x.device)
-        rc = native.lib().bnn_pack_act_f32(x.data_ptr(), sn, sc, sh, sw, n, c, h, w, bits.data_ptr(),
-                                           cnt.data_ptr(), _stream_ptr(x.device))
+        bits = torch.empty((n, nch, ho, wo, 4), dtype=torch.int32, device=x.device)
+        if pool > 1:
+            rc = native.lib().bnn_avgpool_pack_f32(x.data_ptr(), sn, sc, sh, sw, n, c, h, w, pool, int(ceil_mode),
+                                                   ps, ph, bits.data_ptr(), _stream_ptr(x.device))
+        else:
+            rc = native.lib().bnn_pack_act_f32(x.data_ptr(), sn, sc, sh, sw, n, c, h, w, ps, ph, bits.data_ptr(),
+                                               _stream_ptr(x.device))
     native.check(rc, "bnn_pack_act_f32")
-    return PackedActivations(bits, cnt, n, c, h, w)
+    return PackedActivations(bits, n, c, ho, wo)
 
 
 def pack_weights(weight: torch.Tensor, center_weights: bool, compute_alpha: bool) -> PackedWeights:
@@ -97,6 +107,14 @@ def _opt_ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+def _out_hw(act, wts, stride, padding, dilation):
+    ho = (act.h + 2 * padding[0] - dilation[0] * (wts.kh - 1) - 1) // stride[0] + 1
+    wo = (act.w + 2 * padding[1] - dilation[1] * (wts.kw - 1) - 1) // stride[1] + 1
+    if ho <= 0 or wo <= 0:
+        raise native.NativeError(f"empty output ({ho}x{wo})")
+    return ho, wo
+
+
 def bconv2d(act: PackedActivations, wts: PackedWeights, bias: Optional[torch.Tensor] = None,
             post: Optional[torch.Tensor] = None, stride: Tuple[int, int] = (1, 1),
             padding: Tuple[int, int] = (0, 0), dilation: Tuple[int, int] = (1, 1),
@@ -106,21 +124,61 @@ def bconv2d(act: PackedActivations, wts: PackedWeights, bias: Optional[torch.Ten
         raise native.NativeError(f"channel mismatch: activations {act.c}, weights {wts.c_in}")
     geom = ConvGeom(act.n, act.c, act.h, act.w, wts.c_out, wts.kh, wts.kw, stride[0], stride[1],
                     padding[0], padding[1], dilation[0], dilation[1])
-    ho = (act.h + 2 * padding[0] - dilation[0] * (wts.kh - 1) - 1) // stride[0] + 1
-    wo = (act.w + 2 * padding[1] - dilation[1] * (wts.kw - 1) - 1) // stride[1] + 1
-    if ho <= 0 or wo <= 0:
-        raise native.NativeError(f"empty output ({ho}x{wo})")
+    ho, wo = _out_hw(act, wts, stride, padding, dilation)
     dev = act.bits.device
     with torch.cuda.device(dev):
         if out is None:
             out = torch.empty((act.n, wts.c_out, ho, wo), dtype=torch.float32, device=dev)
         on, oc, oh, ow = out.stride()
-        rc = native.lib().bnn_bconv2d_fwd(act.bits.data_ptr(), act.cnt.data_ptr(), wts.bits.data_ptr(),
+        rc = native.lib().bnn_bconv2d_fwd(act.bits.data_ptr(), wts.bits.data_ptr(),
                                           wts.alpha.data_ptr() if use_alpha else None, _opt_ptr(bias),
                                           _opt_ptr(post), out.data_ptr(), on, oc, oh, ow, ctypes.byref(geom),
                                           flags, _stream_ptr(dev))
     native.check(rc, "bnn_bconv2d_fwd")
     return out
+
+
+def bconv2d_fused(act: PackedActivations, wts: PackedWeights, *, bias=None, post=None, bn=None, residual=None,
+                  residual_after_act: bool = False, activation: int = native.ACT_NONE, act_slope=None,
+                  want_out: bool = True, want_bits: bool = False, nx=None, stride=(1, 1), padding=(0, 0),
+                  dilation=(1, 1), use_alpha: bool = True, flags: int = 0):
+    """Binary convolution with the cross-module epilogue of ``struct bnn_epilogue``:
+    ``y=(alpha*dot+bias)*post; z=y*bn[0]+bn[1]; (+residual); act; (+residual)`` -> fp32 ``out`` and/or the
+    packed planes of ``sign(v*nx[0]+nx[1])`` for the next binarized layer.  Returns (out, PackedActivations)."""
+    if act.c != wts.c_in:
+        raise native.NativeError(f"channel mismatch: activations {act.c}, weights {wts.c_in}")
+    geom = ConvGeom(act.n, act.c, act.h, act.w, wts.c_out, wts.kh, wts.kw, stride[0], stride[1],
+                    padding[0], padding[1], dilation[0], dilation[1])
+    ho, wo = _out_hw(act, wts, stride, padding, dilation)
+    dev = act.bits.device
+    ep = native.Epilogue()
+    ep.scale = wts.alpha.data_ptr() if use_alpha else None
+    ep.bias, ep.post = _opt_ptr(bias), _opt_ptr(post)
+    if bn is not None:
+        ep.bn_scale, ep.bn_shift = bn[0].data_ptr(), bn[1].data_ptr()
+    if residual is not None:
+        if tuple(residual.shape) != (act.n, wts.c_out, ho, wo):
+            raise native.NativeError(f"residual shape {tuple(residual.shape)} != output {(act.n, wts.c_out, ho, wo)}")
+        _require_cuda_f32(residual, "residual")
+        ep.residual = residual.data_ptr()
+        ep.rstride_n, ep.rstride_c, ep.rstride_h, ep.rstride_w = residual.stride()
+    ep.residual_after_act, ep.act, ep.act_slope = int(residual_after_act), int(activation), _opt_ptr(act_slope)
+    if nx is not None:
+        ep.nx_scale, ep.nx_shift = nx[0].data_ptr(), nx[1].data_ptr()
+    out = bits = None
+    with torch.cuda.device(dev):
+        if want_out:
+            out = torch.empty((act.n, wts.c_out, ho, wo), dtype=torch.float32, device=dev)
+            ep.out = out.data_ptr()
+            ep.ostride_n, ep.ostride_c, ep.ostride_h, ep.ostride_w = out.stride()
+        if want_bits:
+            bits = torch.empty((act.n, (wts.c_out + 63) // 64, ho, wo, 4), dtype=torch.int32, device=dev)
+            ep.out_bits = bits.data_ptr()
+        rc = native.lib().bnn_bconv2d_fused_fwd(act.bits.data_ptr(), wts.bits.data_ptr(), ctypes.byref(geom),
+                                                ctypes.byref(ep), flags, _stream_ptr(dev))
+    native.check(rc, "bnn_bconv2d_fused_fwd")
+    packed = None if bits is None else PackedActivations(bits, act.n, wts.c_out, ho, wo)
+    return out, packed
 
 
 def blinear(act: PackedActivations, wts: PackedWeights, bias: Optional[torch.Tensor] = None,
@@ -130,7 +188,7 @@ def blinear(act: PackedActivations, wts: PackedWeights, bias: Optional[torch.Ten
     dev = act.bits.device
     with torch.cuda.device(dev):
         out = torch.empty((rows, wts.c_out), dtype=torch.float32, device=dev)
-        rc = native.lib().bnn_blinear_fwd(act.bits.data_ptr(), act.cnt.data_ptr(), wts.bits.data_ptr(),
+        rc = native.lib().bnn_blinear_fwd(act.bits.data_ptr(), wts.bits.data_ptr(),
                                           wts.alpha.data_ptr() if use_alpha else None, _opt_ptr(bias),
                                           _opt_ptr(post), out.data_ptr(), rows, act.c, wts.c_out, flags,
                                           _stream_ptr(dev))

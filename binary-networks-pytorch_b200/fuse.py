@@ -1,0 +1,210 @@
+"""Cross-module fusion for inference.
+
+``optimize(model)`` wraps a prepared ResNet-style model (``bnn.models.resnet`` layout: ``conv1,
+bn1, relu, maxpool, layer1..4, avgpool, fc``; blocks of the reference's ``BasicBlock`` /
+``PreBasicBlock`` shape, bnn/models/layers/res_block.py:8-56,121-167) in an engine that runs each
+residual block as two (three with a shortcut conv) kernel launches:
+
+* the eval-mode BatchNorm after (or before) a binarized conv, the ReLU / PReLU, the residual add
+  and the *next* layer's sign() are folded into the conv kernel's epilogue (``bnn_bconv2d_fused_fwd``);
+* a conv whose output only feeds another binarized conv never writes fp32 at all -- it emits the
+  next layer's sign/mask planes directly (lanes <-> channels makes that one ``ballot`` per word);
+* the residual stream stays fp32 NCHW and is read once / written once per block;
+* the shortcut's AvgPool2d + sign is one pass (``bnn_avgpool_pack_f32``).
+
+Per-channel BatchNorm constants are folded once (``g = weight / sqrt(var + eps)``, ``h = bias -
+mean * g``) and re-folded when any of the BatchNorm tensors changes (version counters).
+Blocks the engine does not recognise run through their own ``forward`` (per-layer kernels), so
+the engine is always a drop-in for ``model`` in eval mode.  Results agree with the unfused path
+to fp32 rounding of the BatchNorm fold (tests/test_gpu_fused.py); the stem (fp32 conv7x7 + BN +
+ReLU + max-pool) and the classifier stay torch ops.
+"""
+from typing import List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import functional as BF
+from . import native, runtime
+from .layers import Conv2d
+from .layers.binary_modules import NotLowerable, _pair
+
+
+class _FoldedBN:
+    """(scale, shift) of an eval-mode BatchNorm2d, cached against in-place updates."""
+
+    def __init__(self, bn: nn.BatchNorm2d) -> None:
+        self.bn, self.key, self.pair = bn, None, None
+
+    def get(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        bn = self.bn
+        tensors = (bn.running_mean, bn.running_var, bn.weight, bn.bias)
+        key = tuple((t.data_ptr(), t._version) if t is not None else None for t in tensors)
+        if key != self.key:
+            with torch.no_grad():
+                g = torch.rsqrt(bn.running_var + bn.eps)
+                if bn.weight is not None:
+                    g = g * bn.weight
+                h = -bn.running_mean * g
+                if bn.bias is not None:
+                    h = h + bn.bias
+                self.pair = (g.float().contiguous(), h.float().contiguous())
+            self.key = key
+        return self.pair
+
+
+def _activation_spec(mod: nn.Module):
+    if isinstance(mod, nn.ReLU):
+        return native.ACT_RELU, None
+    if isinstance(mod, nn.PReLU):
+        return native.ACT_PRELU, mod
+    if isinstance(mod, nn.Identity):
+        return native.ACT_NONE, None
+    return None
+
+
+def _fusable_conv(conv) -> bool:
+    if not isinstance(conv, Conv2d) or conv._is_float_layer():
+        return False
+    try:
+        low = conv._lowering()
+    except NotLowerable:
+        return False
+    return (not low.has_post) or low.fused_post
+
+
+class _BlockPlan:
+    """One residual block: which modules it is made of and how it is laid out."""
+
+    def __init__(self, block: nn.Module) -> None:
+        self.block = block
+        self.kind = None
+        name = type(block).__name__
+        needed = ("conv1", "bn1", "conv2", "bn2", "act1", "act2")
+        if name in ("BasicBlock", "PreBasicBlock") and all(hasattr(block, k) for k in needed):
+            ok = _fusable_conv(block.conv1) and _fusable_conv(block.conv2)
+            ok = ok and isinstance(block.bn1, nn.BatchNorm2d) and isinstance(block.bn2, nn.BatchNorm2d)
+            ok = ok and block.bn1.track_running_stats and block.bn2.track_running_stats
+            ok = ok and _activation_spec(block.act1) is not None and _activation_spec(block.act2) is not None
+            ds = getattr(block, "downsample", None)
+            self.shortcut = None
+            if ds is not None:
+                # reference resnet.py:129-133: AvgPool2d(k=stride) -> binarized conv1x1 -> BatchNorm
+                good = (isinstance(ds, nn.Sequential) and len(ds) == 3 and isinstance(ds[0], nn.AvgPool2d)
+                        and _fusable_conv(ds[1]) and isinstance(ds[2], nn.BatchNorm2d))
+                if good:
+                    pool = ds[0]
+                    k, s = _pair(pool.kernel_size), _pair(pool.stride)
+                    good = (k[0] == k[1] == s[0] == s[1] and _pair(pool.padding) == (0, 0)
+                            and not pool.count_include_pad and pool.divisor_override is None)
+                ok = ok and good
+                if good:
+                    self.shortcut = (ds[0], ds[1], _FoldedBN(ds[2]))
+            if ok:
+                self.kind = "pre" if name == "PreBasicBlock" else "basic"
+                self.bn1, self.bn2 = _FoldedBN(block.bn1), _FoldedBN(block.bn2)
+
+    @property
+    def fused(self) -> bool:
+        return self.kind is not None
+
+
+def _slope(act: nn.Module, channels: int, dev) -> Optional[torch.Tensor]:
+    if not isinstance(act, nn.PReLU):
+        return None
+    w = act.weight.detach()
+    return w if w.numel() == channels else w.expand(channels).contiguous()
+
+
+def _conv_args(conv: Conv2d):
+    low = conv._lowering()
+    return dict(bias=conv._bias(), post=conv._post_scale(low), stride=_pair(conv.stride),
+                padding=conv._resolved_padding(), dilation=_pair(conv.dilation), use_alpha=low.compute_alpha,
+                flags=runtime.kernel_flags()), conv._packed_weights(low)
+
+
+class FusedResNet(nn.Module):
+    """Inference engine over a prepared ResNet; same call signature as the wrapped model."""
+
+    def __init__(self, model: nn.Module) -> None:
+        super().__init__()
+        self.model = model
+        blocks: List[nn.Module] = []
+        for name in ("layer1", "layer2", "layer3", "layer4"):
+            blocks += list(getattr(model, name))
+        self.plans = [_BlockPlan(b) for b in blocks]
+
+    @property
+    def fused_blocks(self) -> int:
+        return sum(p.fused for p in self.plans)
+
+    # what the NEXT block needs in front of its first sign(): its bn1 if it is pre-activation
+    @staticmethod
+    def _entry_affine(plan: Optional[_BlockPlan]):
+        if plan is None or not plan.fused:
+            return None
+        return plan.bn1.get() if plan.kind == "pre" else None
+
+    def _run_block(self, plan: _BlockPlan, x: torch.Tensor, xbits, nxt: Optional[_BlockPlan]):
+        blk = plan.block
+        want_next_bits = nxt is not None and nxt.fused
+        nx = self._entry_affine(nxt)
+        if not plan.fused:
+            y = blk(x)
+            bits = BF.pack_activations(y, pre=nx) if want_next_bits else None
+            return y, bits
+        if xbits is None:
+            xbits = BF.pack_activations(x, pre=self._entry_affine(plan))
+        # shortcut branch
+        if plan.shortcut is not None:
+            pool, conv_d, bn_d = plan.shortcut
+            kw, wts = _conv_args(conv_d)
+            pooled = BF.pack_activations(x, pool=_pair(pool.kernel_size)[0], ceil_mode=pool.ceil_mode)
+            shortcut, _ = BF.bconv2d_fused(pooled, wts, bn=bn_d.get(), **kw)
+        else:
+            shortcut = x
+        a1, p1 = _activation_spec(blk.act1)
+        a2, p2 = _activation_spec(blk.act2)
+        kw1, w1 = _conv_args(blk.conv1)
+        kw2, w2 = _conv_args(blk.conv2)
+        c1, c2 = blk.conv1.out_channels, blk.conv2.out_channels
+        if plan.kind == "basic":
+            # conv1 -> bn1 -> act1 -> [sign] -> conv2 -> bn2 -> (+shortcut) -> act2
+            _, mid = BF.bconv2d_fused(xbits, w1, bn=plan.bn1.get(), activation=a1, act_slope=_slope(p1, c1, x.device),
+                                      want_out=False, want_bits=True, **kw1)
+            y, bits = BF.bconv2d_fused(mid, w2, bn=plan.bn2.get(), residual=shortcut, activation=a2,
+                                       act_slope=_slope(p2, c2, x.device), want_out=True, want_bits=want_next_bits,
+                                       nx=nx, **kw2)
+        else:
+            # [bn1 -> sign] -> conv1 -> act1 -> [bn2 -> sign] -> conv2 -> act2 -> (+shortcut)
+            _, mid = BF.bconv2d_fused(xbits, w1, activation=a1, act_slope=_slope(p1, c1, x.device), want_out=False,
+                                      want_bits=True, nx=plan.bn2.get(), **kw1)
+            y, bits = BF.bconv2d_fused(mid, w2, residual=shortcut, residual_after_act=True, activation=a2,
+                                       act_slope=_slope(p2, c2, x.device), want_out=True, want_bits=want_next_bits,
+                                       nx=nx, **kw2)
+        return y, bits
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        m = self.model
+        if m.training or (torch.is_grad_enabled() and any(p.requires_grad for p in m.parameters()) and x.requires_grad):
+            raise native.NativeError("FusedResNet is an inference engine: call model.eval() and use torch.no_grad()")
+        with torch.no_grad():
+            x = m.conv1(x)
+            if getattr(m, "stem_type", "basic") == "basic" and hasattr(m, "bn1"):
+                x = m.maxpool(m.relu(m.bn1(x)))
+            bits = None
+            for i, plan in enumerate(self.plans):
+                nxt = self.plans[i + 1] if i + 1 < len(self.plans) else None
+                x, bits = self._run_block(plan, x, bits, nxt)
+            x = torch.flatten(m.avgpool(x), 1)
+            return m.fc(x)
+
+
+def optimize(model: nn.Module) -> nn.Module:
+    """Return the fused inference engine for ``model`` if its layout is recognised, else ``model``."""
+    needed = ("conv1", "layer1", "layer2", "layer3", "layer4", "avgpool", "fc")
+    if all(hasattr(model, k) for k in needed):
+        engine = FusedResNet(model)
+        if engine.fused_blocks:
+            return engine
+    return model

@@ -24,19 +24,33 @@ class ConvGeom(ctypes.Structure):
         "n", "c_in", "h", "w", "c_out", "kh", "kw", "stride_h", "stride_w", "pad_h", "pad_w", "dil_h", "dil_w")]
 
 
+class Epilogue(ctypes.Structure):
+    """``struct bnn_epilogue`` (include/bnn_b200.h)."""
+    _fields_ = [("scale", c_void_p), ("bias", c_void_p), ("post", c_void_p), ("bn_scale", c_void_p),
+                ("bn_shift", c_void_p), ("residual", c_void_p), ("rstride_n", c_int64), ("rstride_c", c_int64),
+                ("rstride_h", c_int64), ("rstride_w", c_int64), ("residual_after_act", c_int32), ("act", c_int32),
+                ("act_slope", c_void_p), ("out", c_void_p), ("ostride_n", c_int64), ("ostride_c", c_int64),
+                ("ostride_h", c_int64), ("ostride_w", c_int64), ("out_bits", c_void_p), ("nx_scale", c_void_p),
+                ("nx_shift", c_void_p)]
+
+
+ACT_NONE, ACT_RELU, ACT_PRELU = 0, 1, 2
+
 _SIGNATURES = {
     "bnn_query": (c_int, [c_int, POINTER(c_int64)]),
     "bnn_strerror": (c_char_p, [c_int]),
     "bnn_act_bits_bytes": (c_size_t, [c_int32] * 4),
-    "bnn_act_cnt_bytes": (c_size_t, [c_int32] * 3),
     "bnn_weight_bits_bytes": (c_size_t, [c_int32] * 4),
     "bnn_pack_act_f32": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32,
-                                 c_void_p, c_void_p, c_void_p]),
+                                 c_void_p, c_void_p, c_void_p, c_void_p]),
+    "bnn_avgpool_pack_f32": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32,
+                                     c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "bnn_pack_weight_f32": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                                     c_void_p, c_void_p, c_void_p, c_void_p]),
-    "bnn_bconv2d_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+    "bnn_bconv2d_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_int64, c_int64, c_int64, c_int64, POINTER(ConvGeom), c_uint32, c_void_p]),
-    "bnn_blinear_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+    "bnn_bconv2d_fused_fwd": (c_int, [c_void_p, c_void_p, POINTER(ConvGeom), POINTER(Epilogue), c_uint32, c_void_p]),
+    "bnn_blinear_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_int32, c_int32, c_int32, c_uint32, c_void_p]),
     "bnn_ubench": (c_int, [c_int32, c_int32, POINTER(c_double)]),
 }

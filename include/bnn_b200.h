@@ -22,11 +22,10 @@
  *       chunk = 64 input channels; s bit <=> x > 0; m bit <=> x != 0 (false for +-0, NaN):
  *       the reference's sign() is ternary (bnn/ops.py:66), and zero padding is applied
  *       after binarisation (bnn/layers/conv.py:91-92) -- padded taps simply have m = 0.
- *   non-zero count     cnt[n][h][w]           u32, number of m bits of that pixel
  *   weight planes      wbits[c_out/32][kstep][c_out%32][2]  u32,
  *       kstep = (chunk*kh + i)*kw + j, word 0/1 = channels chunk*64 + 0..31 / 32..63,
  *       bit <=> centred weight > 0 (bnn/ops.py:130-136)
- *   dot[n,co,ho,wo] = sum_taps cnt - 2 * sum_k popc(m & (s ^ t))
+ *   dot[n,co,ho,wo] = sum_k popc(m) - 2 * sum_k popc(m & (s ^ t))     (k over the receptive field)
  *   y = (scale[co]*dot + bias[co]) * post[co]          (conv.py:92-97, ops.py:136,202)
  */
 #ifndef BNN_B200_H
@@ -39,7 +38,7 @@
 extern "C" {
 #endif
 
-#define BNN_B200_ABI_VERSION 1
+#define BNN_B200_ABI_VERSION 2
 
 /* argument errors (negative); positive codes are cudaError_t */
 #define BNN_E_NULL        (-1)  /* required pointer is NULL                         */
@@ -73,18 +72,29 @@ const char *bnn_strerror(int code);
 
 /* sizes (bytes) of the packed buffers the caller must allocate */
 size_t bnn_act_bits_bytes(int32_t n, int32_t c, int32_t h, int32_t w);
-size_t bnn_act_cnt_bytes(int32_t n, int32_t h, int32_t w);
 size_t bnn_weight_bits_bytes(int32_t c_out, int32_t c_in, int32_t kh, int32_t kw);
 
 /*
  * BasicInputBinarizer / SignActivation.forward (bnn/ops.py:151-152, 63-66) as a
  * bit-pack: fp32 activations, addressed with ELEMENT strides (so NCHW,
  * channels_last and Linear's [rows,in] viewed as n=1,h=1,w=rows all fit),
- * -> abits + cnt.  abits must be 16-byte aligned.
+ * -> abits (16-byte aligned).  pre_scale/pre_shift ([c], both or neither) fold an
+ * eval-mode BatchNorm that sits in front of the layer: sign(x*pre_scale + pre_shift).
  */
 int bnn_pack_act_f32(const float *x, int64_t stride_n, int64_t stride_c, int64_t stride_h,
                      int64_t stride_w, int32_t n, int32_t c, int32_t h, int32_t w,
-                     void *abits, uint32_t *cnt, void *stream);
+                     const float *pre_scale, const float *pre_shift, void *abits, void *stream);
+
+/*
+ * AvgPool2d(kernel = stride = k, ceil_mode, count_include_pad = False) followed by the
+ * bit-pack above, in one pass: the shortcut branch of bnn.models.resnet
+ * (bnn/models/resnet.py:129-133) feeds a binarized 1x1 conv from an average-pooled map.
+ * Output planes have ceil(h/k) x ceil(w/k) pixels (ceil_mode) or floor (otherwise).
+ */
+int bnn_avgpool_pack_f32(const float *x, int64_t stride_n, int64_t stride_c, int64_t stride_h,
+                         int64_t stride_w, int32_t n, int32_t c, int32_t h, int32_t w,
+                         int32_t k, int32_t ceil_mode, const float *pre_scale,
+                         const float *pre_shift, void *abits, void *stream);
 
 /*
  * XNORWeightBinarizer.forward (bnn/ops.py:129-140) as a prepare-time pack:
@@ -106,17 +116,51 @@ int bnn_pack_weight_f32(const float *w, int32_t c_out, int32_t c_in, int32_t kh,
  * scale / bias / post may each be NULL (1, 0, 1).  out is fp32, written with
  * element strides (NCHW contiguous: c_out*ho*wo, ho*wo, wo, 1).
  */
-int bnn_bconv2d_fwd(const void *abits, const uint32_t *cnt, const void *wbits,
+int bnn_bconv2d_fwd(const void *abits, const void *wbits,
                     const float *scale, const float *bias, const float *post,
                     float *out, int64_t ostride_n, int64_t ostride_c, int64_t ostride_h,
                     int64_t ostride_w, const bnn_conv_geom *geom, uint32_t flags, void *stream);
+
+/*
+ * Cross-module fusion: the modules that follow a binarized conv
+ * inside the reference's blocks (bnn/models/layers/res_block.py:40-56,152-167,
+ * hierarchical_block.py:38-60) folded into the same kernel.  With y as above:
+ *     z  = y * bn_scale[co] + bn_shift[co]                (eval BatchNorm; skipped if NULL)
+ *     z += residual                 if residual && !residual_after_act
+ *     v  = act(z)                   0 none, 1 ReLU, 2 PReLU(act_slope[co])
+ *     v += residual                 if residual &&  residual_after_act
+ *     out      <- v                 fp32, element strides; skipped if out == NULL
+ *     out_bits <- planes of sign(v * nx_scale[co] + nx_shift[co])   (next layer's input, in the
+ *                 abits layout for [n, c_out, ho, wo]; nx_* NULL = identity; skipped if NULL)
+ * Every product / sum is a separately rounded fp32 operation in this order.
+ */
+typedef struct bnn_epilogue {
+    const float *scale, *bias, *post;
+    const float *bn_scale, *bn_shift;
+    const float *residual;
+    int64_t rstride_n, rstride_c, rstride_h, rstride_w;
+    int32_t residual_after_act;
+    int32_t act;
+    const float *act_slope;
+    float *out;
+    int64_t ostride_n, ostride_c, ostride_h, ostride_w;
+    void *out_bits;
+    const float *nx_scale, *nx_shift;
+} bnn_epilogue;
+
+#define BNN_ACT_NONE  0
+#define BNN_ACT_RELU  1
+#define BNN_ACT_PRELU 2
+
+int bnn_bconv2d_fused_fwd(const void *abits, const void *wbits, const bnn_conv_geom *geom,
+                          const bnn_epilogue *epilogue, uint32_t flags, void *stream);
 
 /*
  * bnn.layers.Linear.forward (bnn/layers/linear.py:22-27): rows x in_features
  * packed as n=1,h=1,w=rows (bnn_pack_act_f32 with stride_w = in_features,
  * stride_c = 1), weight packed with kh = kw = 1; out is [rows, out_features].
  */
-int bnn_blinear_fwd(const void *abits, const uint32_t *cnt, const void *wbits,
+int bnn_blinear_fwd(const void *abits, const void *wbits,
                     const float *scale, const float *bias, const float *post,
                     float *out, int32_t rows, int32_t in_features, int32_t out_features,
                     uint32_t flags, void *stream);

@@ -19,10 +19,11 @@
  *      The contraction itself is torch's F.conv2d in the reference (third
  *      party, ATen/oneDNN); here it is a plain fp32 accumulation loop.
  *
- *  (B) orc_pack_* + orc_bconv2d -- the integer formulation the CUDA kernels
+ *  (B) orc_pack_* + orc_bconv2d[_fused] -- the integer formulation the CUDA kernels
  *      implement, on exactly the packed layouts of
  *      include/bnn_b200.h:  dot = popc(m) - 2*popc(m & (s ^ t)),
- *      y = (alpha_w*dot + bias) * alpha_post.
+ *      y = (alpha_w*dot + bias) * alpha_post, plus the cross-module fusion epilogue
+ *      (eval BatchNorm, residual, ReLU/PReLU, emission of the next layer's planes).
  *
  * Parity pin: tests/test_oracle.py checks (A) against the reference's own
  * golden vectors (test/test_layers.py:22-66, test/test_binarize.py:118-120)
@@ -166,33 +167,50 @@ int64_t orc_weight_words(int c_out, int c_in, int kh, int kw) {
 
 /*
  * Activation planes: abits[n][chunk][h][w] = {s_lo, s_hi, m_lo, m_hi} (4 x u32),
- * chunk = 64 channels; s bit <=> x>0, m bit <=> x>0 || x<0  (bnn/ops.py:66:
- * sign(0)=sign(-0)=sign(nan)=0 has m=0).  cnt[n][h][w] = number of m bits.
- * x is addressed with element strides so NCHW, channels_last and Linear's
- * [rows,in] (as n=1,h=1,w=rows) all go through the same routine.
+ * chunk = 64 channels; s bit <=> v>0, m bit <=> v>0 || v<0  (bnn/ops.py:66:
+ * sign(0)=sign(-0)=sign(nan)=0 has m=0).  x is addressed with element strides so NCHW,
+ * channels_last and Linear's [rows,in] (as n=1,h=1,w=rows) all go through the same routine.
+ * pool > 1: v is first the AvgPool2d(kernel=stride=pool, ceil_mode, count_include_pad=False)
+ * of x (bnn/models/resnet.py:129-133), summed row-major and divided by the in-bounds count;
+ * pre_scale/pre_shift (may be NULL): v = v*pre_scale[c] + pre_shift[c] (an eval BatchNorm in
+ * front of the binarized layer, e.g. PreBasicBlock.bn1, res_block.py:152-154).
+ * h, w are the INPUT plane size; the output plane is ho x wo.
  */
 void orc_pack_act(const float *x, int64_t sn, int64_t sc, int64_t sh, int64_t sw,
-                  int n, int c, int h, int w, uint32_t *abits, uint32_t *cnt) {
+                  int n, int c, int h, int w, int pool, int ceil_mode,
+                  const float *pre_scale, const float *pre_shift, uint32_t *abits) {
     const int nch = (c + 63) / 64;
+    const int k = pool > 1 ? pool : 1;
+    const int ho = pool > 1 ? (ceil_mode ? (h + k - 1) / k : h / k) : h;
+    const int wo = pool > 1 ? (ceil_mode ? (w + k - 1) / k : w / k) : w;
     for (int in = 0; in < n; ++in)
-        for (int ih = 0; ih < h; ++ih)
-            for (int iw = 0; iw < w; ++iw) {
-                uint32_t total = 0;
+        for (int ih = 0; ih < ho; ++ih)
+            for (int iw = 0; iw < wo; ++iw)
                 for (int ch = 0; ch < nch; ++ch) {
                     uint32_t u[4] = {0, 0, 0, 0};
                     for (int b = 0; b < 64; ++b) {
                         const int ci = ch * 64 + b;
                         if (ci >= c) break;
-                        const float v = x[in * sn + ci * sc + ih * sh + iw * sw];
+                        float v;
+                        if (k == 1) {
+                            v = x[in * sn + ci * sc + ih * sh + iw * sw];
+                        } else {
+                            float sum = 0.0f;
+                            int cnt = 0;
+                            for (int i = 0; i < k && ih * k + i < h; ++i)
+                                for (int j = 0; j < k && iw * k + j < w; ++j) {
+                                    sum += x[in * sn + ci * sc + (ih * k + i) * sh + (iw * k + j) * sw];
+                                    ++cnt;
+                                }
+                            v = sum / (float)cnt;
+                        }
+                        if (pre_scale) v = v * pre_scale[ci] + pre_shift[ci];
                         const uint32_t pos = v > 0.0f, neg = v < 0.0f;
                         u[b >> 5] |= pos << (b & 31);
                         u[2 + (b >> 5)] |= (pos | neg) << (b & 31);
                     }
-                    total += popc32(u[2]) + popc32(u[3]);
-                    memcpy(abits + ((((int64_t)in * nch + ch) * h + ih) * w + iw) * 4, u, 16);
+                    memcpy(abits + ((((int64_t)in * nch + ch) * ho + ih) * wo + iw) * 4, u, 16);
                 }
-                cnt[((int64_t)in * h + ih) * w + iw] = total;
-            }
 }
 
 /*
@@ -227,30 +245,37 @@ int orc_pack_weight(const float *w, int c_out, int c_in, int kh, int kw, int cen
 }
 
 /*
- * Packed binary convolution with the fused epilogue of SURVEY.md section 8(a):
- *   dot = sum_taps cnt - 2 * sum popc(m & (s ^ t));  y = (scale*dot + bias) * post
- * out is written with element strides (on, oc, oh, ow) so Linear can store [rows,out].
- * Out-of-bounds taps contribute nothing (their m would be 0): zero padding is
- * applied after binarization, bnn/layers/conv.py:91-92.
+ * Packed binary convolution with the fused epilogue of include/bnn_b200.h (struct bnn_epilogue):
+ *   dot = sum popc(m) - 2 * sum popc(m & (s ^ t))   over the in-bounds taps
+ *   y = (scale*dot + bias) * post                        reference conv.py:92-97, ops.py:136,202
+ *   z = y*bn_scale + bn_shift ; z += res (pre) ; v = act(z) ; v += res (post)     
+ *   out <- v ;  out_bits <- planes of sign(v*nx_scale + nx_shift)
+ * Out-of-bounds taps contribute nothing (their m would be 0): zero padding is applied after
+ * binarization, bnn/layers/conv.py:91-92.  Every float op is separately rounded (-ffp-contract=off).
  */
-void orc_bconv2d(const uint32_t *abits, const uint32_t *cnt, const uint32_t *wbits,
-                 const float *scale, const float *bias, const float *post, const orc_geom *g,
-                 float *out, int64_t on, int64_t oc, int64_t oh, int64_t ow) {
+typedef struct {
+    const float *scale, *bias, *post;
+    const float *bn_scale, *bn_shift;
+    const float *residual;
+    int64_t rn, rc, rh, rw;
+    int32_t residual_after_act, act;
+    const float *act_slope;
+    float *out;
+    int64_t on, oc, oh, ow;
+    uint32_t *out_bits;
+    const float *nx_scale, *nx_shift;
+} orc_epilogue;
+
+void orc_bconv2d_fused(const uint32_t *abits, const uint32_t *wbits, const orc_geom *g, const orc_epilogue *e) {
     const int ho_n = orc_out_h(g), wo_n = orc_out_w(g);
     const int taps = g->kh * g->kw, nch = (g->c_in + 63) / 64, nk = nch * taps;
+    const int ochunks = (g->c_out + 63) / 64;
+    if (e->out_bits) memset(e->out_bits, 0, sizeof(uint32_t) * 4 * (size_t)g->n * ochunks * ho_n * wo_n);
     for (int n = 0; n < g->n; ++n)
         for (int ho = 0; ho < ho_n; ++ho)
-            for (int wo = 0; wo < wo_n; ++wo) {
-                int msum = 0;
-                for (int kh = 0; kh < g->kh; ++kh)
-                    for (int kw = 0; kw < g->kw; ++kw) {
-                        const int hi = ho * g->stride_h - g->pad_h + kh * g->dil_h;
-                        const int wi = wo * g->stride_w - g->pad_w + kw * g->dil_w;
-                        if (hi < 0 || hi >= g->h || wi < 0 || wi >= g->w) continue;
-                        msum += (int)cnt[((int64_t)n * g->h + hi) * g->w + wi];
-                    }
+            for (int wo = 0; wo < wo_n; ++wo)
                 for (int co = 0; co < g->c_out; ++co) {
-                    int dis = 0;
+                    int msum = 0, dis = 0;
                     for (int ch = 0; ch < nch; ++ch)
                         for (int kh = 0; kh < g->kh; ++kh)
                             for (int kw = 0; kw < g->kw; ++kw) {
@@ -260,24 +285,47 @@ void orc_bconv2d(const uint32_t *abits, const uint32_t *cnt, const uint32_t *wbi
                                 const uint32_t *u = abits + ((((int64_t)n * nch + ch) * g->h + hi) * g->w + wi) * 4;
                                 const int ks = (ch * g->kh + kh) * g->kw + kw;
                                 const uint32_t *t = wbits + ((((int64_t)(co / 32) * nk + ks) * 32) + (co % 32)) * 2;
+                                msum += popc32(u[2]) + popc32(u[3]);
                                 dis += popc32(u[2] & (u[0] ^ t[0])) + popc32(u[3] & (u[1] ^ t[1]));
                             }
-                    float y = (scale ? scale[co] : 1.0f) * (float)(msum - 2 * dis);
-                    if (bias) y = y + bias[co];
-                    if (post) y = y * post[co];
-                    out[n * on + co * oc + ho * oh + wo * ow] = y;
+                    float y = (e->scale ? e->scale[co] : 1.0f) * (float)(msum - 2 * dis);
+                    if (e->bias) y = y + e->bias[co];
+                    if (e->post) y = y * e->post[co];
+                    if (e->bn_scale) y = y * e->bn_scale[co] + e->bn_shift[co];
+                    const float r = e->residual ? e->residual[n * e->rn + co * e->rc + ho * e->rh + wo * e->rw] : 0.0f;
+                    if (e->residual && !e->residual_after_act) y = y + r;
+                    if (e->act == 1) y = (y > 0.0f) ? y : ((y != y) ? y : 0.0f);
+                    else if (e->act == 2) y = (y > 0.0f) ? y : e->act_slope[co] * y;
+                    if (e->residual && e->residual_after_act) y = y + r;
+                    if (e->out) e->out[n * e->on + co * e->oc + ho * e->oh + wo * e->ow] = y;
+                    if (e->out_bits) {
+                        float b = y;
+                        if (e->nx_scale) b = b * e->nx_scale[co] + e->nx_shift[co];
+                        uint32_t *u = e->out_bits + ((((int64_t)n * ochunks + co / 64) * ho_n + ho) * wo_n + wo) * 4;
+                        const int bit = co % 64;
+                        if (b > 0.0f) u[bit >> 5] |= 1u << (bit & 31);
+                        if (b > 0.0f || b < 0.0f) u[2 + (bit >> 5)] |= 1u << (bit & 31);
+                    }
                 }
-            }
+}
+
+void orc_bconv2d(const uint32_t *abits, const uint32_t *wbits,
+                 const float *scale, const float *bias, const float *post, const orc_geom *g,
+                 float *out, int64_t on, int64_t oc, int64_t oh, int64_t ow) {
+    orc_epilogue e;
+    memset(&e, 0, sizeof(e));
+    e.scale = scale; e.bias = bias; e.post = post;
+    e.out = out; e.on = on; e.oc = oc; e.oh = oh; e.ow = ow;
+    orc_bconv2d_fused(abits, wbits, g, &e);
 }
 
 /* raw integer dot products (scale=1, no bias/post) for bit-exact comparison */
-void orc_bconv2d_dot(const uint32_t *abits, const uint32_t *cnt, const uint32_t *wbits,
-                     const orc_geom *g, int32_t *dot) {
+void orc_bconv2d_dot(const uint32_t *abits, const uint32_t *wbits, const orc_geom *g, int32_t *dot) {
     const int ho_n = orc_out_h(g), wo_n = orc_out_w(g);
     const int64_t total = (int64_t)g->n * g->c_out * ho_n * wo_n;
     float *tmp = (float *)malloc(sizeof(float) * total);
     if (!tmp) return;
-    orc_bconv2d(abits, cnt, wbits, NULL, NULL, NULL, g, tmp,
+    orc_bconv2d(abits, wbits, NULL, NULL, NULL, g, tmp,
                 (int64_t)g->c_out * ho_n * wo_n, (int64_t)ho_n * wo_n, wo_n, 1);
     for (int64_t i = 0; i < total; ++i) dot[i] = (int32_t)tmp[i];
     free(tmp);

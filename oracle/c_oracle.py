@@ -60,16 +60,20 @@ def floatsim_linear(x, w, bias, post, center: bool, compute_alpha: bool):
     return out
 
 
-def pack_act(x):
-    """x: float32 [n,c,h,w] (any numpy strides) -> (abits uint32 [n,chunks,h,w,4], cnt uint32 [n,h,w])."""
+def pack_act(x, pool=0, ceil_mode=True, pre_scale=None, pre_shift=None):
+    """x: float32 [n,c,h,w] (any numpy strides) -> abits uint32 [n,chunks,ho,wo,4]."""
     x = np.asarray(x, dtype=np.float32)
     n, c, h, w = x.shape
     sn, sc, sh, sw = (s // 4 for s in x.strides)
     nch = (c + 63) // 64
-    abits = np.zeros((n, nch, h, w, 4), np.uint32)
-    cnt = np.zeros((n, h, w), np.uint32)
-    lib().orc_pack_act(_p(x), c_int64(sn), c_int64(sc), c_int64(sh), c_int64(sw), n, c, h, w, _p(abits), _p(cnt))
-    return abits, cnt
+    k = pool if pool > 1 else 1
+    ho = (-(-h // k) if ceil_mode else h // k) if pool > 1 else h
+    wo = (-(-w // k) if ceil_mode else w // k) if pool > 1 else w
+    abits = np.zeros((n, nch, ho, wo, 4), np.uint32)
+    pre_scale, pre_shift = _f32(pre_scale), _f32(pre_shift)
+    lib().orc_pack_act(_p(x), c_int64(sn), c_int64(sc), c_int64(sh), c_int64(sw), n, c, h, w, int(pool),
+                       int(ceil_mode), _p(pre_scale), _p(pre_shift), _p(abits))
+    return abits
 
 
 def pack_weight(w, center: bool, compute_alpha: bool):
@@ -91,19 +95,54 @@ def pack_weight(w, center: bool, compute_alpha: bool):
     return wbits, alpha, int(nz.value)
 
 
-def bconv2d(abits, cnt, wbits, scale, bias, post, g: Geom, out_strides=None):
+def bconv2d(abits, wbits, scale, bias, post, g: Geom, out_strides=None):
     ho, wo = out_hw(g)
     out = np.zeros((g.n, g.c_out, ho, wo), np.float32)
     if out_strides is None:
         out_strides = tuple(s // 4 for s in out.strides)
     scale, bias, post = _f32(scale), _f32(bias), _f32(post)
-    lib().orc_bconv2d(_p(abits), _p(cnt), _p(wbits), _p(scale), _p(bias), _p(post), ctypes.byref(g), _p(out),
+    lib().orc_bconv2d(_p(abits), _p(wbits), _p(scale), _p(bias), _p(post), ctypes.byref(g), _p(out),
                       *(c_int64(s) for s in out_strides))
     return out
 
 
-def bconv2d_dot(abits, cnt, wbits, g: Geom):
+def bconv2d_dot(abits, wbits, g: Geom):
     ho, wo = out_hw(g)
     dot = np.zeros((g.n, g.c_out, ho, wo), np.int32)
-    lib().orc_bconv2d_dot(_p(abits), _p(cnt), _p(wbits), ctypes.byref(g), _p(dot))
+    lib().orc_bconv2d_dot(_p(abits), _p(wbits), ctypes.byref(g), _p(dot))
     return dot
+
+
+class Epilogue(ctypes.Structure):
+    _fields_ = [("scale", c_void_p), ("bias", c_void_p), ("post", c_void_p), ("bn_scale", c_void_p),
+                ("bn_shift", c_void_p), ("residual", c_void_p), ("rn", c_int64), ("rc", c_int64), ("rh", c_int64),
+                ("rw", c_int64), ("residual_after_act", c_int32), ("act", c_int32), ("act_slope", c_void_p),
+                ("out", c_void_p), ("on", c_int64), ("oc", c_int64), ("oh", c_int64), ("ow", c_int64),
+                ("out_bits", c_void_p), ("nx_scale", c_void_p), ("nx_shift", c_void_p)]
+
+
+def bconv2d_fused(abits, wbits, g: Geom, scale=None, bias=None, post=None, bn=None, residual=None,
+                  residual_after_act=False, act=0, act_slope=None, want_out=True, want_bits=False, nx=None):
+    """Fused epilogue (struct bnn_epilogue). bn / nx: (scale, shift) pairs. Returns (out or None, bits or None)."""
+    ho, wo = out_hw(g)
+    keep = [_f32(a) for a in (scale, bias, post, None if bn is None else bn[0], None if bn is None else bn[1],
+                              residual, act_slope, None if nx is None else nx[0], None if nx is None else nx[1])]
+    scale, bias, post, bns, bnh, residual, act_slope, nxs, nxh = keep
+    out = np.zeros((g.n, g.c_out, ho, wo), np.float32) if want_out else None
+    bits = np.zeros((g.n, (g.c_out + 63) // 64, ho, wo, 4), np.uint32) if want_bits else None
+    e = Epilogue()
+    e.scale, e.bias, e.post, e.bn_scale, e.bn_shift = (_v(a) for a in (scale, bias, post, bns, bnh))
+    if residual is not None:
+        e.residual = _v(residual)
+        e.rn, e.rc, e.rh, e.rw = (s // 4 for s in residual.strides)
+    e.residual_after_act, e.act, e.act_slope = int(residual_after_act), int(act), _v(act_slope)
+    if out is not None:
+        e.out = _v(out)
+        e.on, e.oc, e.oh, e.ow = (s // 4 for s in out.strides)
+    e.out_bits, e.nx_scale, e.nx_shift = _v(bits), _v(nxs), _v(nxh)
+    lib().orc_bconv2d_fused(_p(abits), _p(wbits), ctypes.byref(g), ctypes.byref(e))
+    return out, bits
+
+
+def _v(a):
+    return None if a is None else a.ctypes.data

@@ -1,0 +1,142 @@
+"""Cross-module fusion on the GPU: fused epilogue kernel vs the oracle (bit-exact), fused engine vs
+the unfused per-layer path and vs the reference's logits."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from conftest import rel_err
+from oracle import c_oracle as co
+from oracle import floatsim as fs
+from test_oracle import FUSED_CASES, make_fused_inputs
+from test_gpu_model import build, xnor_cfg
+
+import bnn_b200 as bnn
+from bnn_b200 import functional as BF
+from bnn_b200 import fuse, native, workloads
+from bnn_b200.ops import BasicScaleBinarizer
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _d(a):
+    return None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+@pytest.mark.parametrize("flags", [0, native.F_STAGE_LDG, native.F_NO_CSA], ids=["tma", "ldg", "nocsa"])
+@pytest.mark.parametrize("fc", FUSED_CASES, ids=[c["name"] for c in FUSED_CASES])
+def test_fused_epilogue_bit_exact_vs_oracle(fc, flags):
+    d = make_fused_inputs(fc)
+    g = d["g"]
+    ab = co.pack_act(d["x"])
+    wb, alpha, _ = co.pack_weight(d["w"], True, True)
+    want_out, want_bits = co.bconv2d_fused(ab, wb, g, scale=alpha, bias=d["bias"], post=d["post"], bn=d["bn"],
+                                           residual=d["residual"], residual_after_act=d["res_after"], act=d["act"],
+                                           act_slope=d["slope"], want_out=True, want_bits=True, nx=d["nx"])
+    act = BF.pack_activations(_d(d["x"]))
+    wts = BF.pack_weights(_d(d["w"]), True, True)
+    # alpha differs from the oracle's only in the last bit at most; use the device value on both sides
+    alpha_dev = wts.alpha.cpu().numpy()
+    want_out, want_bits = co.bconv2d_fused(ab, wb, g, scale=alpha_dev, bias=d["bias"], post=d["post"], bn=d["bn"],
+                                           residual=d["residual"], residual_after_act=d["res_after"], act=d["act"],
+                                           act_slope=d["slope"], want_out=True, want_bits=True, nx=d["nx"])
+    pair = lambda p: None if p is None else (_d(p[0]), _d(p[1]))
+    out, bits = BF.bconv2d_fused(act, wts, bias=_d(d["bias"]), post=_d(d["post"]), bn=pair(d["bn"]),
+                                 residual=_d(d["residual"]), residual_after_act=d["res_after"], activation=d["act"],
+                                 act_slope=_d(d["slope"]), want_out=True, want_bits=True, nx=pair(d["nx"]),
+                                 stride=(g.stride_h, g.stride_w), padding=(g.pad_h, g.pad_w), flags=flags)
+    assert np.array_equal(out.cpu().numpy(), want_out)
+    assert np.array_equal(bits.bits.cpu().numpy().view(np.uint32), want_bits)
+    # bits only (no fp32 store) and out only give the same planes / values
+    _, bits2 = BF.bconv2d_fused(act, wts, bias=_d(d["bias"]), post=_d(d["post"]), bn=pair(d["bn"]),
+                                residual=_d(d["residual"]), residual_after_act=d["res_after"], activation=d["act"],
+                                act_slope=_d(d["slope"]), want_out=False, want_bits=True, nx=pair(d["nx"]),
+                                stride=(g.stride_h, g.stride_w), padding=(g.pad_h, g.pad_w), flags=flags)
+    assert torch.equal(bits2.bits, bits.bits)
+
+
+@pytest.mark.parametrize("shape,k,ceil", [((2, 64, 8, 8), 2, True), ((1, 70, 7, 9), 2, True), ((1, 64, 7, 9), 2, False),
+                                          ((4, 128, 28, 28), 2, True)])
+def test_avgpool_pack_bit_exact(shape, k, ceil):
+    rng = np.random.default_rng(3)
+    x = np.maximum(rng.standard_normal(shape), 0).astype(np.float32)
+    got = BF.pack_activations(_d(x), pool=k, ceil_mode=ceil)
+    assert np.array_equal(got.bits.cpu().numpy().view(np.uint32), co.pack_act(x, pool=k, ceil_mode=ceil))
+    s, h = (0.5 + rng.random(shape[1])).astype(np.float32), rng.standard_normal(shape[1]).astype(np.float32)
+    got = BF.pack_activations(_d(x), pre=(_d(s), _d(h)))
+    assert np.array_equal(got.bits.cpu().numpy().view(np.uint32), co.pack_act(x, pre_scale=s, pre_shift=h))
+
+
+@pytest.fixture(autouse=True)
+def _fp32_glue():
+    prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+@pytest.mark.parametrize("variant", ["basic_relu", "pre_prelu"])
+def test_fused_engine_matches_reference_and_unfused(variant, golden_models):
+    m = build(variant).to(DEV)
+    engine = fuse.optimize(m)
+    assert isinstance(engine, fuse.FusedResNet) and engine.fused_blocks == 8
+    x = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(0)).to(DEV)
+    with torch.no_grad():
+        eager = m(x).cpu().numpy()
+        before = native.launch_count()
+        fused = engine(x).cpu().numpy()
+    launches = native.launch_count() - before
+    assert launches <= 1 + 16 + 3 * 2 + 2          # pack + 2 per block + (pool-pack, conv) per shortcut
+    ref = golden_models[variant + "_logits"]
+    print(variant, "fused vs reference", rel_err(fused, ref), "fused vs unfused", rel_err(fused, eager))
+    assert rel_err(fused, ref) <= 1e-3
+    assert rel_err(fused, eager) <= 1e-3
+    assert (np.argmax(fused, 1) == np.argmax(ref, 1)).all()
+
+
+def test_fused_engine_full_resolution_with_post_scale():
+    m = build("basic_relu", xnor_cfg(BasicScaleBinarizer))
+    twin = fs.mirror_model(m)
+    x = torch.randn(4, 3, 224, 224, generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        want = twin(x).numpy()
+        got = fuse.optimize(m.to(DEV))(x.to(DEV)).cpu().numpy()
+    assert rel_err(got, want) <= 1e-3, rel_err(got, want)
+
+
+def test_fused_engine_tracks_batchnorm_updates_and_graph_capture():
+    m = build("basic_relu").to(DEV)
+    engine = fuse.optimize(m)
+    x = torch.randn(4, 3, 96, 96, device=DEV)
+    with torch.no_grad():
+        y0 = engine(x)
+        m.layer1[0].bn1.running_mean.add_(0.5)             # in-place change must be picked up
+        y1 = engine(x)
+        assert not torch.equal(y0, y1)
+        assert rel_err(y1.cpu().numpy(), m(x).cpu().numpy()) <= 1e-3
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            engine(x)
+            torch.cuda.current_stream().synchronize()
+            with torch.cuda.graph(g, stream=s):
+                out = engine(x)
+        g.replay()
+        torch.cuda.synchronize()
+    assert torch.equal(out, y1)
+
+
+def test_unrecognised_blocks_fall_back_to_their_own_forward():
+    torch.manual_seed(0)
+    m = workloads.resnet50()
+    m = bnn.prepare_binary_model(m, xnor_cfg(), ignore_layers_name=["_first_", "_last_"])
+    workloads.randomize_batchnorm(m)
+    m = m.eval().to(DEV)
+    assert fuse.optimize(m) is m                            # Bottleneck blocks: nothing to fuse yet
+    x = torch.randn(2, 3, 64, 64, device=DEV)
+    with torch.no_grad():
+        y = m(x)
+        want = fs.mirror_model(m)(x.cpu()).numpy()
+    assert rel_err(y.cpu().numpy(), want) <= 1e-3

@@ -35,10 +35,10 @@ def test_unit_vectors_reference_known_answers(golden_units):
     geo = co.geom(1, 3, 2, 2, 3, 1, 1)
     yc = co.floatsim_conv2d(data, w.reshape(3, 3, 1, 1), None, ones3, geo, False, True)
     assert np.allclose(yc, g["conv2d_expected"], atol=1e-4)
-    ab, cnt = co.pack_act(data)
+    ab = co.pack_act(data)
     wb, alpha, nz = co.pack_weight(w.reshape(3, 3, 1, 1), False, True)
     assert nz == 0
-    yi = co.bconv2d(ab, cnt, wb, alpha, None, ones3, geo)
+    yi = co.bconv2d(ab, wb, alpha, None, ones3, geo)
     assert np.allclose(yi, g["conv2d_expected"], atol=1e-4)
 
 
@@ -46,12 +46,11 @@ def test_sign_edge_cases(golden_units):
     # test/test_binarize.py:118-120 plus +-0, denormal-ish and NaN
     x, ref = golden_units["sign_in"], golden_units["sign_ref"]
     assert np.array_equal(torch.sign(_t(x)).numpy(), ref, equal_nan=True)
-    ab, cnt = co.pack_act(x.reshape(1, -1, 1, 1))
+    ab = co.pack_act(x.reshape(1, -1, 1, 1))
     s, m = int(ab[0, 0, 0, 0, 0]), int(ab[0, 0, 0, 0, 2])
     got = np.array([((s >> i) & 1) * 2 - 1 if (m >> i) & 1 else 0 for i in range(x.size)], np.float32)
     want = np.nan_to_num(ref, nan=0.0)   # the mask plane encodes sign(nan) as 0, like sign(+-0)
     assert np.array_equal(got, want)
-    assert int(cnt[0, 0, 0]) == int((want != 0).sum())
 
 
 def _run_floatsim_torch(case):
@@ -94,22 +93,22 @@ def test_layer_cases_against_reference_outputs(case, golden_layers):
     x4, w4, bias, post, g, hp, unflat = _as_conv2d(case)
     yc = unflat(co.floatsim_conv2d(x4, w4, bias, post, g, hp["center"], hp["alpha"]))
     assert rel_err(yc, ref) <= 1e-5, rel_err(yc, ref)
-    ab, cnt = co.pack_act(x4)
+    ab = co.pack_act(x4)
     wb, alpha, nz = co.pack_weight(w4, hp["center"], hp["alpha"])
     assert nz == 0
-    yi = unflat(co.bconv2d(ab, cnt, wb, alpha if hp["alpha"] else None, bias, post, g))
+    yi = unflat(co.bconv2d(ab, wb, alpha if hp["alpha"] else None, bias, post, g))
     assert rel_err(yi, ref) <= 1e-5, rel_err(yi, ref)
 
 
 def test_integer_dot_properties():
     case = cases.by_name("ragged_c70_s21")
     x4, w4, _, _, g, hp, _ = _as_conv2d(case)
-    ab, cnt = co.pack_act(x4)
+    ab = co.pack_act(x4)
     wb, _, _ = co.pack_weight(w4, hp["center"], hp["alpha"])
-    dot = co.bconv2d_dot(ab, cnt, wb, g)
-    abn, cntn = co.pack_act(-x4)
-    assert np.array_equal(cnt, cntn)
-    assert np.array_equal(co.bconv2d_dot(abn, cntn, wb, g), -dot)       # antisymmetry in x
+    dot = co.bconv2d_dot(ab, wb, g)
+    abn = co.pack_act(-x4)
+    assert np.array_equal(ab[..., 2:], abn[..., 2:])                     # mask planes unchanged
+    assert np.array_equal(co.bconv2d_dot(abn, wb, g), -dot)       # antisymmetry in x
     k = 70 * 9
     assert np.abs(dot).max() <= k
     # brute force on the float side: dot == conv(sign x, sign wc) exactly
@@ -150,3 +149,82 @@ def test_whole_model_twin_matches_reference_logits(golden_models):
         y = twin(x).numpy()
         assert rel_err(y, golden_models[variant + "_logits"]) <= 1e-6
     torch.set_grad_enabled(True)
+
+
+# ----------------------------------------------------------------------------------------------
+# cross-module fusion epilogue (struct bnn_epilogue) and the pooled / affine bit-pack
+# ----------------------------------------------------------------------------------------------
+FUSED_CASES = [
+    dict(name="basic_mid", cin=64, cout=64, hw=(9, 11), bn=True, act=1, bits=True, out=False),
+    dict(name="basic_out", cin=64, cout=64, hw=(9, 11), bn=True, act=1, res="pre", bits=True, out=True),
+    dict(name="pre_mid", cin=128, cout=128, hw=(7, 7), act=2, bits=True, out=False, nx=True),
+    dict(name="pre_out", cin=128, cout=128, hw=(7, 7), act=2, res="post", bits=True, out=True, nx=True),
+    dict(name="shortcut", cin=64, cout=128, hw=(8, 8), k=1, pad=0, bn=True, out=True, bits=False),
+    dict(name="ragged_c1", cin=70, cout=24, hw=(6, 5), bn=True, act=1, res="pre", bits=True, out=True, bias=True, post=True),
+    dict(name="c96_s2", cin=64, cout=96, hw=(10, 10), stride=2, bn=True, act=2, bits=True, out=True, nx=True),
+]
+
+
+def make_fused_inputs(fc):
+    rng = np.random.default_rng(4242 + [c["name"] for c in FUSED_CASES].index(fc["name"]))
+    k, pad, stride = fc.get("k", 3), fc.get("pad", 1), fc.get("stride", 1)
+    h, w = fc["hw"]
+    n = 2
+    x = np.maximum(rng.standard_normal((n, fc["cin"], h, w)), 0).astype(np.float32)
+    wt = (rng.standard_normal((fc["cout"], fc["cin"], k, k)) * 0.05).astype(np.float32)
+    g = co.geom(n, fc["cin"], h, w, fc["cout"], k, k, (stride, stride), (pad, pad), (1, 1))
+    ho, wo = co.out_hw(g)
+    co_ = fc["cout"]
+    d = dict(x=x, w=wt, g=g,
+             bias=(rng.standard_normal(co_) * 0.3).astype(np.float32) if fc.get("bias") else None,
+             post=(0.5 + rng.random(co_)).astype(np.float32) if fc.get("post") else None,
+             bn=((0.5 + rng.random(co_)).astype(np.float32) * 3, (rng.standard_normal(co_) * 0.3).astype(np.float32)) if fc.get("bn") else None,
+             residual=rng.standard_normal((n, co_, ho, wo)).astype(np.float32) if fc.get("res") else None,
+             res_after=fc.get("res") == "post", act=fc.get("act", 0),
+             slope=(rng.random(co_) * 0.5).astype(np.float32) if fc.get("act", 0) == 2 else None,
+             nx=((0.5 + rng.random(co_)).astype(np.float32), (rng.standard_normal(co_) * 0.2).astype(np.float32)) if fc.get("nx") else None,
+             want_out=fc.get("out", True), want_bits=fc.get("bits", False))
+    return d
+
+
+@pytest.mark.parametrize("fc", FUSED_CASES, ids=[c["name"] for c in FUSED_CASES])
+def test_fused_epilogue_oracle_against_torch_composition(fc):
+    """oracle (integer path + fused epilogue) == the module sequence the reference's blocks execute:
+    conv (float-sim) -> BatchNorm(eval, folded) -> (+res) -> ReLU/PReLU -> (+res); bits == sign of the result."""
+    d = make_fused_inputs(fc)
+    g = d["g"]
+    ab = co.pack_act(d["x"])
+    wb, alpha, nz = co.pack_weight(d["w"], True, True)
+    assert nz == 0
+    out, bits = co.bconv2d_fused(ab, wb, g, scale=alpha, bias=d["bias"], post=d["post"], bn=d["bn"], residual=d["residual"],
+                                 residual_after_act=d["res_after"], act=d["act"], act_slope=d["slope"], want_out=True,
+                                 want_bits=True, nx=d["nx"])
+    y = fs.conv2d(_t(d["x"]), _t(d["w"]), _t(d["bias"]), _t(d["post"]), (g.stride_h, g.stride_w), (g.pad_h, g.pad_w),
+                  (1, 1), True, True)
+    v = lambda a: _t(a).view(1, -1, 1, 1)
+    if d["bn"] is not None:
+        y = y * v(d["bn"][0]) + v(d["bn"][1])
+    if d["residual"] is not None and not d["res_after"]:
+        y = y + _t(d["residual"])
+    if d["act"] == 1:
+        y = torch.relu(y)
+    elif d["act"] == 2:
+        y = torch.nn.functional.prelu(y, _t(d["slope"]))
+    if d["residual"] is not None and d["res_after"]:
+        y = y + _t(d["residual"])
+    assert rel_err(out, y.numpy()) <= 1e-5
+    # emitted planes are exactly the bit-pack of the oracle's own fp32 result (with the next layer's affine)
+    want_bits = co.pack_act(out, pre_scale=None if d["nx"] is None else d["nx"][0],
+                            pre_shift=None if d["nx"] is None else d["nx"][1])
+    assert np.array_equal(bits, want_bits)
+
+
+def test_avgpool_pack_matches_torch():
+    rng = np.random.default_rng(7)
+    for shape, k, ceil in (((2, 64, 8, 8), 2, True), ((1, 70, 7, 9), 2, True), ((1, 64, 7, 9), 2, False), ((1, 3, 9, 9), 3, True)):
+        x = np.maximum(rng.standard_normal(shape), 0).astype(np.float32)
+        pooled = torch.nn.functional.avg_pool2d(_t(x), k, k, 0, ceil_mode=ceil, count_include_pad=False).numpy()
+        assert np.array_equal(co.pack_act(x, pool=k, ceil_mode=ceil), co.pack_act(pooled))
+    x = rng.standard_normal((2, 64, 5, 5)).astype(np.float32)
+    s, h = (0.5 + rng.random(64)).astype(np.float32), rng.standard_normal(64).astype(np.float32)
+    assert np.array_equal(co.pack_act(x, pre_scale=s, pre_shift=h), co.pack_act(x * s[None, :, None, None] + h[None, :, None, None]))
