@@ -53,12 +53,17 @@ struct ConvArgs {
 };
 
 // per-CTA table of per-channel epilogue constants in shared memory: [EP_N][32*C]
-enum { EP_SCALE = 0, EP_BIAS, EP_POST, EP_BNS, EP_BNH, EP_SLOPE, EP_NXS, EP_NXH, EP_N };
+//   EPI == 0 (reference epilogue, exact order):  y = (k0 * dot + k1) * k2         k = scale, bias, post
+//   EPI == 1 (cross-module fusion):              z = fma(k0, dot, k1)            k0/k1 fold scale, bias, post, BN
+//                                                k2 = PReLU slope, k3/k4 = next layer's pre-sign affine
+enum { EP_N = 5 };
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ int word_dis(uint32_t m, uint32_t s, uint32_t t) { return __popc(m & (s ^ t)); }
 __device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (c & (a ^ b)); }
 
-template <int P, int C, int KWT, int SWT, int MODE>
+template <int P, int C, int KWT, int SWT, int MODE, int EPI>
 __global__ void __launch_bounds__(256, 2)
 bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ConvArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -118,14 +123,24 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
     for (int i = threadIdx.x; i < 32 * C; i += blockDim.x) {
         const int c = blk0 * 32 + i;
         const bool ok = c < a.Cout;
-        epc[EP_SCALE * 32 * C + i] = (ok && a.e.scale) ? __ldg(a.e.scale + c) : 1.0f;
-        epc[EP_BIAS * 32 * C + i] = (ok && a.e.bias) ? __ldg(a.e.bias + c) : 0.0f;
-        epc[EP_POST * 32 * C + i] = (ok && a.e.post) ? __ldg(a.e.post + c) : 1.0f;
-        epc[EP_BNS * 32 * C + i] = (ok && a.e.bn_scale) ? __ldg(a.e.bn_scale + c) : 1.0f;
-        epc[EP_BNH * 32 * C + i] = (ok && a.e.bn_shift) ? __ldg(a.e.bn_shift + c) : 0.0f;
-        epc[EP_SLOPE * 32 * C + i] = (ok && a.e.slope) ? __ldg(a.e.slope + c) : 0.0f;
-        epc[EP_NXS * 32 * C + i] = (ok && a.e.nx_scale) ? __ldg(a.e.nx_scale + c) : 1.0f;
-        epc[EP_NXH * 32 * C + i] = (ok && a.e.nx_shift) ? __ldg(a.e.nx_shift + c) : 0.0f;
+        float k0 = (ok && a.e.scale) ? __ldg(a.e.scale + c) : 1.0f;
+        float k1 = (ok && a.e.bias) ? __ldg(a.e.bias + c) : 0.0f;
+        const float post = (ok && a.e.post) ? __ldg(a.e.post + c) : 1.0f;
+        if constexpr (EPI == 0) {
+            epc[0 * 32 * C + i] = k0; epc[1 * 32 * C + i] = k1; epc[2 * 32 * C + i] = post;
+        } else {
+            // fold (scale*dot + bias)*post and the eval BatchNorm into one multiply-add (fixed order, see oracle)
+            k0 = __fmul_rn(k0, post); k1 = __fmul_rn(k1, post);
+            if (a.e.bn_scale) {
+                const float g = ok ? __ldg(a.e.bn_scale + c) : 1.0f, h = ok ? __ldg(a.e.bn_shift + c) : 0.0f;
+                k0 = __fmul_rn(k0, g);
+                k1 = __fadd_rn(__fmul_rn(k1, g), h);
+            }
+            epc[0 * 32 * C + i] = k0; epc[1 * 32 * C + i] = k1;
+            epc[2 * 32 * C + i] = (ok && a.e.slope) ? __ldg(a.e.slope + c) : 0.0f;
+            epc[3 * 32 * C + i] = (ok && a.e.nx_scale) ? __ldg(a.e.nx_scale + c) : 1.0f;
+            epc[4 * 32 * C + i] = (ok && a.e.nx_shift) ? __ldg(a.e.nx_shift + c) : 0.0f;
+        }
     }
     __syncthreads();
     if (!a.stage_ldg) mbar_wait(bar, 0);
@@ -145,6 +160,20 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
         const int ho = ho0 + r;
         const int wo_first = wo0 + wq;
         if (ho >= a.Ho || wo_first >= a.Wo) continue;   // warp-uniform
+
+        if constexpr (EPI == 1) {
+            // the residual tile is needed only after the K loop: pull its lines into L2 now so the epilogue
+            // does not sit on DRAM latency (one 32-byte pixel run per channel row)
+            if (a.e.res != nullptr) {
+#pragma unroll
+                for (int j = 0; j < C; ++j) {
+                    const int c = (blk0 + j) * 32 + lane;
+                    if (c < a.Cout)
+                        prefetch_l2(a.e.res + (long long)n * a.e.rn + (long long)c * a.e.rc + (long long)ho * a.e.rh +
+                                    (long long)wo_first * a.e.rw);
+                }
+            }
+        }
 
         // ---- number of non-zero inputs under each pixel's window: popc of the m planes already in
         //      shared memory, spread over the lanes (lane = pixel + 8*part), summed by two shuffles
@@ -245,11 +274,15 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
             }
         }
 
-        // ---------------- fused epilogue (order fixed by include/bnn_b200.h) ----------------
+        // ---------------- epilogue ----------------
         int ms[P];
 #pragma unroll
         for (int p = 0; p < P; ++p) ms[p] = __shfl_sync(0xffffffffu, msum, p);
         const bool transposed = (a.e.ow == 1) || (a.e.out == nullptr);
+        const bool has_res = (EPI == 1) && a.e.res != nullptr;
+        const bool want_bits = (EPI == 1) && a.e.obits != nullptr;
+        // ReLU output with no affine in front of the next sign(): "non-zero" and "positive" coincide
+        const bool relu_bits = a.e.act == BNN_ACT_RELU && a.e.nx_scale == nullptr && !(has_res && a.e.res_after_act);
         uint32_t sbits[C], mbits[C];     // lane p keeps the packed words of pixel p
 #pragma unroll
         for (int j = 0; j < C; ++j) { sbits[j] = 0u; mbits[j] = 0u; }
@@ -259,54 +292,60 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
             const int cl = j * 32 + lane;                // channel inside the CTA tile
             const int cblk = (blk0 + j) * 32;
             const bool c_ok = cblk + lane < a.Cout;
-            const float k_scale = epc[EP_SCALE * 32 * C + cl], k_bias = epc[EP_BIAS * 32 * C + cl],
-                        k_post = epc[EP_POST * 32 * C + cl];
-            float res[P];
-            if (a.e.res != nullptr) {
-                // residual tile [32 ch][P px] -> per-lane channel rows, coalesced along pixels when rw == 1
-                const float* rbase = a.e.res + (long long)n * a.e.rn + (long long)ho * a.e.rh;
-                if (a.e.rw == 1) {
-                    __syncwarp();
+            const float k0 = epc[0 * 32 * C + cl], k1 = epc[1 * 32 * C + cl], k2 = epc[2 * 32 * C + cl];
+            float v[P];
+            if constexpr (EPI == 0) {
+                // reference order (conv.py:92-97, ops.py:136,202): (alpha*dot + bias) * alpha_post
 #pragma unroll
-                    for (int r0 = 0; r0 < 32; r0 += ROWS) {
-                        const int rl = r0 + rr, c = cblk + rl, wo = wo_first + pr;
-                        float v = 0.0f;
-                        if (pr < P && wo < a.Wo && c < a.Cout) v = __ldg(rbase + (long long)c * a.e.rc + wo);
-                        if (pr < P) stg[rl * PITCH + pr] = v;
+                for (int p = 0; p < P; ++p)
+                    v[p] = __fmul_rn(__fadd_rn(__fmul_rn(k0, (float)(ms[p] - 2 * acc[p][j])), k1), k2);
+            } else {
+                float res[P];
+                if (has_res) {
+                    // residual tile [32 ch][P px] -> per-lane channel rows, coalesced along pixels when rw == 1
+                    const float* rbase = a.e.res + (long long)n * a.e.rn + (long long)ho * a.e.rh;
+                    if (a.e.rw == 1) {
+                        __syncwarp();
+#pragma unroll
+                        for (int r0 = 0; r0 < 32; r0 += ROWS) {
+                            const int rl = r0 + rr, c = cblk + rl, wo = wo_first + pr;
+                            float t = 0.0f;
+                            if (pr < P && wo < a.Wo && c < a.Cout) t = __ldg(rbase + (long long)c * a.e.rc + wo);
+                            if (pr < P) stg[rl * PITCH + pr] = t;
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int p = 0; p < P; ++p) res[p] = stg[lane * PITCH + p];
+                    } else {
+#pragma unroll
+                        for (int p = 0; p < P; ++p) {
+                            const int wo = wo_first + p;
+                            res[p] = (c_ok && wo < a.Wo)
+                                         ? __ldg(rbase + (long long)(cblk + lane) * a.e.rc + (long long)wo * a.e.rw) : 0.0f;
+                        }
                     }
-                    __syncwarp();
-#pragma unroll
-                    for (int p = 0; p < P; ++p) res[p] = stg[lane * PITCH + p];
                 } else {
 #pragma unroll
-                    for (int p = 0; p < P; ++p) {
-                        const int wo = wo_first + p;
-                        res[p] = (c_ok && wo < a.Wo)
-                                     ? __ldg(rbase + (long long)(cblk + lane) * a.e.rc + (long long)wo * a.e.rw) : 0.0f;
-                    }
+                    for (int p = 0; p < P; ++p) res[p] = 0.0f;
                 }
-            }
-            float v[P];
-#pragma unroll
-            for (int p = 0; p < P; ++p) {
-                float y = __fmul_rn(k_scale, (float)(ms[p] - 2 * acc[p][j]));
-                if (a.e.bias) y = __fadd_rn(y, k_bias);
-                if (a.e.post) y = __fmul_rn(y, k_post);
-                if (a.e.bn_scale) y = __fadd_rn(__fmul_rn(y, epc[EP_BNS * 32 * C + cl]), epc[EP_BNH * 32 * C + cl]);
-                if (a.e.res != nullptr && !a.e.res_after_act) y = __fadd_rn(y, res[p]);
-                if (a.e.act == BNN_ACT_RELU) y = (y > 0.0f) ? y : ((y != y) ? y : 0.0f);    // NaN propagates like torch.relu
-                else if (a.e.act == BNN_ACT_PRELU) y = (y > 0.0f) ? y : __fmul_rn(epc[EP_SLOPE * 32 * C + cl], y);
-                if (a.e.res != nullptr && a.e.res_after_act) y = __fadd_rn(y, res[p]);
-                v[p] = y;
-            }
-            if (a.e.obits != nullptr) {
+                const bool after = a.e.res_after_act != 0;
 #pragma unroll
                 for (int p = 0; p < P; ++p) {
-                    float b = v[p];
-                    if (a.e.nx_scale) b = __fadd_rn(__fmul_rn(b, epc[EP_NXS * 32 * C + cl]), epc[EP_NXH * 32 * C + cl]);
-                    const uint32_t sw = __ballot_sync(0xffffffffu, c_ok && b > 0.0f);
-                    const uint32_t mw = __ballot_sync(0xffffffffu, c_ok && (b > 0.0f || b < 0.0f));
-                    if (lane == p) { sbits[j] = sw; mbits[j] = mw; }
+                    float z = __fmaf_rn(k0, (float)(ms[p] - 2 * acc[p][j]), k1);
+                    z = __fadd_rn(z, after ? 0.0f : res[p]);
+                    if (a.e.act == BNN_ACT_RELU) z = fmaxf(z, 0.0f);
+                    else if (a.e.act == BNN_ACT_PRELU) z = (z > 0.0f) ? z : __fmul_rn(k2, z);
+                    v[p] = __fadd_rn(z, after ? res[p] : 0.0f);
+                }
+                if (want_bits) {
+                    const float k3 = epc[3 * 32 * C + cl], k4 = epc[4 * 32 * C + cl];
+#pragma unroll
+                    for (int p = 0; p < P; ++p) {
+                        const float b = a.e.nx_scale ? __fmaf_rn(k3, v[p], k4) : v[p];
+                        const uint32_t sw = __ballot_sync(0xffffffffu, c_ok && b > 0.0f);
+                        const uint32_t mw = relu_bits ? sw : __ballot_sync(0xffffffffu, c_ok && (b > 0.0f || b < 0.0f));
+                        if (lane == p) { sbits[j] = sw; mbits[j] = mw; }
+                    }
                 }
             }
             if (a.e.out != nullptr) {
@@ -333,7 +372,7 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
                 }
             }
         }
-        if (a.e.obits != nullptr && lane < P && wo_first + lane < a.Wo) {
+        if (want_bits && lane < P && wo_first + lane < a.Wo) {
             // lane p writes the 16-byte units of pixel p: consecutive lanes -> consecutive units (coalesced)
             uint32_t* ob = reinterpret_cast<uint32_t*>(a.e.obits);
 #pragma unroll
@@ -387,12 +426,9 @@ struct Plan {
 
 typedef void (*KernelFn)(const CUtensorMap, const ConvArgs);
 
-template <int P, int C, int KWT, int SWT, int MODE>
-static KernelFn kernel_ptr() { return bconv_kernel<P, C, KWT, SWT, MODE>; }
-
-template <int KWT, int SWT, int MODE>
+template <int KWT, int SWT, int MODE, int EPI>
 static KernelFn pick_pc(int P, int C) {
-#define BNN_PC(p, c) if (P == p && C == c) return kernel_ptr<p, c, KWT, SWT, MODE>();
+#define BNN_PC(p, c) if (P == p && C == c) return bconv_kernel<p, c, KWT, SWT, MODE, EPI>;
     BNN_PC(8, 4) BNN_PC(8, 2) BNN_PC(8, 1)
     BNN_PC(7, 4) BNN_PC(7, 2) BNN_PC(7, 1)
     BNN_PC(4, 4) BNN_PC(4, 2) BNN_PC(4, 1)
@@ -400,11 +436,18 @@ static KernelFn pick_pc(int P, int C) {
     return nullptr;
 }
 
-static KernelFn pick_kernel(const Plan& p) {
-    if (p.kwt == 3 && p.swt == 1) return p.mode ? pick_pc<3, 1, 1>(p.P, p.C) : pick_pc<3, 1, 0>(p.P, p.C);
-    if (p.kwt == 3 && p.swt == 2) return p.mode ? pick_pc<3, 2, 1>(p.P, p.C) : pick_pc<3, 2, 0>(p.P, p.C);
-    if (p.kwt == 1 && p.swt == 1) return pick_pc<1, 1, 0>(p.P, p.C);
-    return pick_pc<0, 0, 0>(p.P, p.C);
+// EPI 0 = reference epilogue (both inner-loop modes, for A/B runs); EPI 1 = fused epilogue (carry-save only)
+static KernelFn pick_kernel(const Plan& p, int epi) {
+    if (epi == 0) {
+        if (p.kwt == 3 && p.swt == 1) return p.mode ? pick_pc<3, 1, 1, 0>(p.P, p.C) : pick_pc<3, 1, 0, 0>(p.P, p.C);
+        if (p.kwt == 3 && p.swt == 2) return p.mode ? pick_pc<3, 2, 1, 0>(p.P, p.C) : pick_pc<3, 2, 0, 0>(p.P, p.C);
+        if (p.kwt == 1 && p.swt == 1) return pick_pc<1, 1, 0, 0>(p.P, p.C);
+        return pick_pc<0, 0, 0, 0>(p.P, p.C);
+    }
+    if (p.kwt == 3 && p.swt == 1) return pick_pc<3, 1, 1, 1>(p.P, p.C);
+    if (p.kwt == 3 && p.swt == 2) return pick_pc<3, 2, 1, 1>(p.P, p.C);
+    if (p.kwt == 1 && p.swt == 1) return pick_pc<1, 1, 0, 1>(p.P, p.C);
+    return pick_pc<0, 0, 0, 1>(p.P, p.C);
 }
 
 static int ceil_div(int a, int b) { return (a + b - 1) / b; }
@@ -450,7 +493,7 @@ static int make_plan(const bnn_conv_geom& g, int Ho, int Wo, uint32_t flags, int
             if (BW > 256) continue;
             const int gpr = TW / P, tiles_w = ceil_div(Wo, TW);
             // cycles per 32-bit word per warp: fewer channels per lane -> more shared-memory loads per word
-            double cpw = (C == 4 ? 1.0 : C == 2 ? 1.08 : 1.25) * (window ? 1.0 : 1.12) * (P == 4 ? 1.06 : 1.0);
+            double cpw = (C == 4 ? 1.0 : C == 2 ? 1.25 : 1.5) * (window ? 1.0 : 1.12) * (P == 4 ? 1.06 : 1.0);
             const double round_work = (double)P * C * nk * 2.0 * cpw + 60.0 * P * C;   // main loop + epilogue
             for (int NW = 8; NW >= 7; --NW) {
                 for (int TH = 1; TH <= Ho; ++TH) {
@@ -507,10 +550,12 @@ static int launch_bconv(const void* abits, const void* wbits, const bnn_conv_geo
         if (dev < 64) cached_sms[dev] = sms;
     }
 
+    const int epi = (ep.bn_scale || ep.residual || ep.act != BNN_ACT_NONE || ep.out_bits || ep.nx_scale) ? 1 : 0;
+    if (epi) flags &= ~BNN_F_NO_CSA;
     Plan pl;
     int rc = make_plan(g, Ho, Wo, flags, sms, &pl);
     if (rc) return rc;
-    KernelFn fn = pick_kernel(pl);
+    KernelFn fn = pick_kernel(pl, epi);
     if (!fn) return BNN_E_UNSUPPORTED;
 
     ConvArgs a{};
@@ -565,6 +610,20 @@ static int launch_bconv(const void* abits, const void* wbits, const bnn_conv_geo
 }  // namespace bnn
 
 using namespace bnn;
+
+extern "C" int bnn_conv_plan(const bnn_conv_geom* g, uint32_t flags, int32_t sms, int32_t* plan) {
+    if (!g || !plan) return BNN_E_NULL;
+    const int Ho = out_dim(g->h, g->kh, g->stride_h, g->pad_h, g->dil_h);
+    const int Wo = out_dim(g->w, g->kw, g->stride_w, g->pad_w, g->dil_w);
+    if (Ho <= 0 || Wo <= 0) return BNN_E_SHAPE;
+    Plan pl;
+    int rc = make_plan(*g, Ho, Wo, flags, sms > 0 ? sms : 148, &pl);
+    if (rc) return rc;
+    const int v[12] = {pl.P, pl.C, pl.kwt, pl.swt, pl.mode, pl.TH, pl.TW, pl.NW, pl.tiles_h * pl.tiles_w * g->n,
+                       ceil_div(ceil_div(g->c_out, 32), pl.C), (int)pl.smem, pl.G};
+    for (int i = 0; i < 12; ++i) plan[i] = v[i];
+    return 0;
+}
 
 extern "C" int bnn_bconv2d_fused_fwd(const void* abits, const void* wbits, const bnn_conv_geom* geom,
                                      const bnn_epilogue* epilogue, uint32_t flags, void* stream) {

@@ -53,6 +53,7 @@ _SIGNATURES = {
     "bnn_blinear_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_int32, c_int32, c_int32, c_uint32, c_void_p]),
     "bnn_ubench": (c_int, [c_int32, c_int32, POINTER(c_double)]),
+    "bnn_conv_plan": (c_int, [POINTER(ConvGeom), c_uint32, c_int32, POINTER(c_int32)]),
 }
 
 _lib = None
@@ -92,6 +93,16 @@ def query(what: int) -> int:
     v = c_int64(0)
     check(lib().bnn_query(what, ctypes.byref(v)), "bnn_query")
     return int(v.value)
+
+
+PLAN_FIELDS = ("P", "C", "kw_inst", "stride_inst", "csa", "TH", "TW", "warps", "units", "channel_tiles", "smem", "groups")
+
+
+def conv_plan(geom: ConvGeom, flags: int = 0, sms: int = 0) -> dict:
+    """Tile plan for a geometry (works without a GPU)."""
+    arr = (c_int32 * 12)()
+    check(lib().bnn_conv_plan(ctypes.byref(geom), flags, sms, arr), "bnn_conv_plan")
+    return dict(zip(PLAN_FIELDS, list(arr)))
 
 
 def launch_count() -> int:

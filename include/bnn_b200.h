@@ -132,7 +132,10 @@ int bnn_bconv2d_fwd(const void *abits, const void *wbits,
  *     out      <- v                 fp32, element strides; skipped if out == NULL
  *     out_bits <- planes of sign(v * nx_scale[co] + nx_shift[co])   (next layer's input, in the
  *                 abits layout for [n, c_out, ho, wo]; nx_* NULL = identity; skipped if NULL)
- * Every product / sum is a separately rounded fp32 operation in this order.
+ * In this fused mode the per-channel constants are folded once per launch --
+ *     k0 = scale*post*bn_scale,  k1 = (bias*post)*bn_scale + bn_shift,  z = fma(k0, dot, k1)
+ * -- the next-layer affine is one fma, and ReLU is fmaxf(z, 0); oracle/bnn_oracle.c restates it
+ * operation for operation.  bnn_bconv2d_fwd (no fusion field set) keeps the reference's exact order.
  */
 typedef struct bnn_epilogue {
     const float *scale, *bias, *post;
@@ -154,6 +157,14 @@ typedef struct bnn_epilogue {
 
 int bnn_bconv2d_fused_fwd(const void *abits, const void *wbits, const bnn_conv_geom *geom,
                           const bnn_epilogue *epilogue, uint32_t flags, void *stream);
+
+/*
+ * Introspection: the tile plan the library would use for a geometry (host only, no GPU needed).
+ * plan[12] = {P pixels/group, C 32-channel blocks/lane, kw instance, stride instance, carry-save mode,
+ *             TH, TW, warps per CTA, pixel units (grid.x), channel tiles (grid.y), smem bytes, groups/unit}.
+ * sms <= 0 assumes 148.
+ */
+int bnn_conv_plan(const bnn_conv_geom *geom, uint32_t flags, int32_t sms, int32_t *plan);
 
 /*
  * bnn.layers.Linear.forward (bnn/layers/linear.py:22-27): rows x in_features

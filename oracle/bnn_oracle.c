@@ -250,6 +250,8 @@ int orc_pack_weight(const float *w, int c_out, int c_in, int kh, int kw, int cen
  *   y = (scale*dot + bias) * post                        reference conv.py:92-97, ops.py:136,202
  *   z = y*bn_scale + bn_shift ; z += res (pre) ; v = act(z) ; v += res (post)     
  *   out <- v ;  out_bits <- planes of sign(v*nx_scale + nx_shift)
+ * When any fusion field is set, the per-channel constants are folded first (k0, k1 below) and the
+ * affine steps are single fused multiply-adds; ReLU is fmaxf(z, 0).
  * Out-of-bounds taps contribute nothing (their m would be 0): zero padding is applied after
  * binarization, bnn/layers/conv.py:91-92.  Every float op is separately rounded (-ffp-contract=off).
  */
@@ -288,19 +290,34 @@ void orc_bconv2d_fused(const uint32_t *abits, const uint32_t *wbits, const orc_g
                                 msum += popc32(u[2]) + popc32(u[3]);
                                 dis += popc32(u[2] & (u[0] ^ t[0])) + popc32(u[3] & (u[1] ^ t[1]));
                             }
-                    float y = (e->scale ? e->scale[co] : 1.0f) * (float)(msum - 2 * dis);
-                    if (e->bias) y = y + e->bias[co];
-                    if (e->post) y = y * e->post[co];
-                    if (e->bn_scale) y = y * e->bn_scale[co] + e->bn_shift[co];
-                    const float r = e->residual ? e->residual[n * e->rn + co * e->rc + ho * e->rh + wo * e->rw] : 0.0f;
-                    if (e->residual && !e->residual_after_act) y = y + r;
-                    if (e->act == 1) y = (y > 0.0f) ? y : ((y != y) ? y : 0.0f);
-                    else if (e->act == 2) y = (y > 0.0f) ? y : e->act_slope[co] * y;
-                    if (e->residual && e->residual_after_act) y = y + r;
+                    const int fused = e->bn_scale || e->residual || e->act != 0 || e->out_bits || e->nx_scale;
+                    float y;
+                    if (!fused) {
+                        /* reference order, conv.py:92-97 + ops.py:136,202 */
+                        y = (e->scale ? e->scale[co] : 1.0f) * (float)(msum - 2 * dis);
+                        y = y + (e->bias ? e->bias[co] : 0.0f);
+                        y = y * (e->post ? e->post[co] : 1.0f);
+                    } else {
+                        /* fused mode folds scale/bias/post/BatchNorm into one multiply-add per channel:
+                         *   k0 = scale*post*bn_scale, k1 = (bias*post)*bn_scale + bn_shift, z = fma(k0, dot, k1) */
+                        const float post = e->post ? e->post[co] : 1.0f;
+                        float k0 = (e->scale ? e->scale[co] : 1.0f) * post;
+                        float k1 = (e->bias ? e->bias[co] : 0.0f) * post;
+                        if (e->bn_scale) {
+                            k0 = k0 * e->bn_scale[co];
+                            k1 = k1 * e->bn_scale[co] + e->bn_shift[co];
+                        }
+                        y = fmaf(k0, (float)(msum - 2 * dis), k1);
+                        const float r = e->residual ? e->residual[n * e->rn + co * e->rc + ho * e->rh + wo * e->rw] : 0.0f;
+                        y = y + (e->residual_after_act ? 0.0f : r);
+                        if (e->act == 1) y = fmaxf(y, 0.0f);
+                        else if (e->act == 2) y = (y > 0.0f) ? y : e->act_slope[co] * y;
+                        y = y + (e->residual_after_act ? r : 0.0f);
+                    }
                     if (e->out) e->out[n * e->on + co * e->oc + ho * e->oh + wo * e->ow] = y;
                     if (e->out_bits) {
                         float b = y;
-                        if (e->nx_scale) b = b * e->nx_scale[co] + e->nx_shift[co];
+                        if (e->nx_scale) b = fmaf(e->nx_scale[co], b, e->nx_shift[co]);
                         uint32_t *u = e->out_bits + ((((int64_t)n * ochunks + co / 64) * ho_n + ho) * wo_n + wo) * 4;
                         const int bit = co % 64;
                         if (b > 0.0f) u[bit >> 5] |= 1u << (bit & 31);

