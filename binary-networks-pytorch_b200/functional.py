@@ -141,10 +141,12 @@ def bconv2d(act: PackedActivations, wts: PackedWeights, bias: Optional[torch.Ten
 def bconv2d_fused(act: PackedActivations, wts: PackedWeights, *, bias=None, post=None, bn=None, residual=None,
                   residual_after_act: bool = False, activation: int = native.ACT_NONE, act_slope=None,
                   want_out: bool = True, want_bits: bool = False, nx=None, stride=(1, 1), padding=(0, 0),
-                  dilation=(1, 1), use_alpha: bool = True, flags: int = 0):
+                  dilation=(1, 1), use_alpha: bool = True, flags: int = 0, channels_last: bool = False):
     """Binary convolution with the cross-module epilogue of ``struct bnn_epilogue``:
     ``y=(alpha*dot+bias)*post; z=y*bn[0]+bn[1]; (+residual); act; (+residual)`` -> fp32 ``out`` and/or the
-    packed planes of ``sign(v*nx[0]+nx[1])`` for the next binarized layer.  Returns (out, PackedActivations)."""
+    packed planes of ``sign(v*nx[0]+nx[1])`` for the next binarized layer.  Returns (out, PackedActivations).
+    ``channels_last`` allocates ``out`` in torch's NHWC memory format: with lanes <-> channels in the kernel a
+    warp then stores (and reads the residual) as whole 128-byte lines, no transposition needed."""
     if act.c != wts.c_in:
         raise native.NativeError(f"channel mismatch: activations {act.c}, weights {wts.c_in}")
     geom = ConvGeom(act.n, act.c, act.h, act.w, wts.c_out, wts.kh, wts.kw, stride[0], stride[1],
@@ -168,7 +170,8 @@ def bconv2d_fused(act: PackedActivations, wts: PackedWeights, *, bias=None, post
     out = bits = None
     with torch.cuda.device(dev):
         if want_out:
-            out = torch.empty((act.n, wts.c_out, ho, wo), dtype=torch.float32, device=dev)
+            out = torch.empty((act.n, wts.c_out, ho, wo), dtype=torch.float32, device=dev,
+                              memory_format=torch.channels_last if channels_last else torch.contiguous_format)
             ep.out = out.data_ptr()
             ep.ostride_n, ep.ostride_c, ep.ostride_h, ep.ostride_w = out.stride()
         if want_bits:

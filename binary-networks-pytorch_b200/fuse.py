@@ -9,7 +9,8 @@ residual block as two (three with a shortcut conv) kernel launches:
   and the *next* layer's sign() are folded into the conv kernel's epilogue (``bnn_bconv2d_fused_fwd``);
 * a conv whose output only feeds another binarized conv never writes fp32 at all -- it emits the
   next layer's sign/mask planes directly (lanes <-> channels makes that one ``ballot`` per word);
-* the residual stream stays fp32 NCHW and is read once / written once per block;
+* the residual stream stays fp32 and is read once / written once per block; between fused blocks it is
+  kept in torch's channels_last (NHWC) memory format, which matches the kernel's lanes <-> channels mapping;
 * the shortcut's AvgPool2d + sign is one pass (``bnn_avgpool_pack_f32``).
 
 Per-channel BatchNorm constants are folded once (``g = weight / sqrt(var + eps)``, ``h = bias -
@@ -160,7 +161,7 @@ class FusedResNet(nn.Module):
             pool, conv_d, bn_d = plan.shortcut
             kw, wts = _conv_args(conv_d)
             pooled = BF.pack_activations(x, pool=_pair(pool.kernel_size)[0], ceil_mode=pool.ceil_mode)
-            shortcut, _ = BF.bconv2d_fused(pooled, wts, bn=bn_d.get(), **kw)
+            shortcut, _ = BF.bconv2d_fused(pooled, wts, bn=bn_d.get(), channels_last=True, **kw)
         else:
             shortcut = x
         a1, p1 = _activation_spec(blk.act1)
@@ -174,14 +175,14 @@ class FusedResNet(nn.Module):
                                       want_out=False, want_bits=True, **kw1)
             y, bits = BF.bconv2d_fused(mid, w2, bn=plan.bn2.get(), residual=shortcut, activation=a2,
                                        act_slope=_slope(p2, c2, x.device), want_out=True, want_bits=want_next_bits,
-                                       nx=nx, **kw2)
+                                       nx=nx, channels_last=True, **kw2)
         else:
             # [bn1 -> sign] -> conv1 -> act1 -> [bn2 -> sign] -> conv2 -> act2 -> (+shortcut)
             _, mid = BF.bconv2d_fused(xbits, w1, activation=a1, act_slope=_slope(p1, c1, x.device), want_out=False,
                                       want_bits=True, nx=plan.bn2.get(), **kw1)
             y, bits = BF.bconv2d_fused(mid, w2, residual=shortcut, residual_after_act=True, activation=a2,
                                        act_slope=_slope(p2, c2, x.device), want_out=True, want_bits=want_next_bits,
-                                       nx=nx, **kw2)
+                                       nx=nx, channels_last=True, **kw2)
         return y, bits
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -192,6 +193,10 @@ class FusedResNet(nn.Module):
             x = m.conv1(x)
             if getattr(m, "stem_type", "basic") == "basic" and hasattr(m, "bn1"):
                 x = m.maxpool(m.relu(m.bn1(x)))
+            # the residual stream lives in NHWC between fused blocks (lanes <-> channels: every load/store of the
+            # conv epilogue is a full 128-byte line)
+            if self.plans and self.plans[0].fused:
+                x = x.contiguous(memory_format=torch.channels_last)
             bits = None
             for i, plan in enumerate(self.plans):
                 nxt = self.plans[i + 1] if i + 1 < len(self.plans) else None

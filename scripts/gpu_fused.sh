@@ -4,19 +4,15 @@ OUT=gpurun_out/$TAG
 mkdir -p $OUT
 timeout 900 python -m pytest tests -m gpu -q -x -s > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?" | tee -a $OUT/pytest_gpu.log
 grep -E "fused vs|passed|failed|Error" $OUT/pytest_gpu.log | tail -8
-for mode in "" mid out; do
+for mode in "" out out_cl; do
 timeout 300 python scripts/profile_layer.py --layers l1,l2s,l2,l3s,l3,l4s,l4 --reps 10 --fused "$mode" | tee -a $OUT/layers_iso.jsonl
 done
 timeout 900 python bench.py --steps 30 --warmup 3 --layers-out $OUT/layers.json > $OUT/bench.log 2>&1
 tail -1 $OUT/bench.log | cut -c1-600
-timeout 900 python bench.py --steps 30 --warmup 3 --no-fuse --no-cpu-baseline --layers-out $OUT/layers_nofuse.json > $OUT/bench_nofuse.log 2>&1
-tail -1 $OUT/bench_nofuse.log | cut -c1-300
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 120 -c 60 --csv \
     --log-file $OUT/launches_fused.csv python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > $OUT/ncu_bench.log 2>&1
 echo "ncu exit $?"
 if [ "${NCU:-1}" = "1" ]; then
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:bconv_kernel -s 1 -c 1 \
-    -o $OUT/prof_l1_out -f python scripts/profile_layer.py --layers l1 --reps 2 --fused out > $OUT/ncu_l1o.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:bconv_kernel -s 1 -c 1 \
-    -o $OUT/prof_l1_plain -f python scripts/profile_layer.py --layers l1 --reps 2 > $OUT/ncu_l1p.log 2>&1
+    -o $OUT/prof_l1_out -f python scripts/profile_layer.py --layers l1 --reps 2 --fused out_cl > $OUT/ncu_l1o.log 2>&1
 fi

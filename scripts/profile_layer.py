@@ -40,11 +40,15 @@ def main():
         out = BF.bconv2d(act, wts, None, None, (s, s), (p, p), (1, 1), flags=args.flags)
         bn = (torch.rand(co, device=dev) + 0.5, torch.randn(co, device=dev) * 0.2)
         res = torch.randn_like(out)
+        res_cl = res.contiguous(memory_format=torch.channels_last)
 
         def run_conv():
             if args.fused == "mid":
                 BF.bconv2d_fused(act, wts, bn=bn, activation=1, want_out=False, want_bits=True, stride=(s, s),
                                  padding=(p, p), flags=args.flags)
+            elif args.fused == "out_cl":
+                BF.bconv2d_fused(act, wts, bn=bn, residual=res_cl, activation=1, want_out=True, want_bits=True,
+                                 stride=(s, s), padding=(p, p), flags=args.flags, channels_last=True)
             elif args.fused == "out":
                 BF.bconv2d_fused(act, wts, bn=bn, residual=res, activation=1, want_out=True, want_bits=True,
                                  stride=(s, s), padding=(p, p), flags=args.flags)
