@@ -74,6 +74,7 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
     uint2* wsm = reinterpret_cast<uint2*>(after_act);
     float* stage_all = reinterpret_cast<float*>(after_act + (size_t)C * a.w_bytes);
     float* epc = stage_all + (blockDim.x >> 5) * (32 * PITCH);      // [EP_N][32*C]
+    int* ms_s = reinterpret_cast<int*>(epc + EP_N * 32 * C);         // [TH][TW] non-zero inputs per window
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     int unit = blockIdx.x;
@@ -148,6 +149,23 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
     const int SW = (KWT > 0) ? SWT : a.SW;
     const int KW = (KWT > 0) ? KWT : a.KW;
     const int DW = (KWT > 0) ? 1 : a.DW;
+    // number of non-zero inputs under every output pixel's window (popc of the m planes already staged):
+    // once per CTA, one or two pixels per thread, instead of POPCs per output channel
+    for (int i = threadIdx.x; i < a.TH * a.TW; i += blockDim.x) {
+        const int r = i / a.TW, q = i - r * a.TW;
+        int cnt = 0;
+        for (int ch = 0; ch < a.nch; ++ch)
+            for (int kh = 0; kh < a.KH; ++kh) {
+                const uint4* arow = act + (size_t)(ch * a.BH + r * a.SH + kh * a.DH) * a.BW + q * SW;
+                for (int kw = 0; kw < KW; ++kw) {
+                    const uint4 v = arow[kw * DW];
+                    cnt += __popc(v.z) + __popc(v.w);
+                }
+            }
+        ms_s[i] = cnt;
+    }
+    __syncthreads();
+
     float* stg = stage_all + warp * (32 * PITCH);
     constexpr int PW = (P > 4) ? 8 : 4;          // lanes per channel row in the transposed phases
     constexpr int ROWS = 32 / PW;                // channel rows per load/store instruction
@@ -173,27 +191,6 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
                                     (long long)wo_first * a.e.rw);
                 }
             }
-        }
-
-        // ---- number of non-zero inputs under each pixel's window: popc of the m planes already in
-        //      shared memory, spread over the lanes (lane = pixel + 8*part), summed by two shuffles
-        int msum = 0;
-        {
-            const int pix = lane & 7, part = lane >> 3;
-            int it = 0;
-            if (pix < P) {
-                for (int ch = 0; ch < a.nch; ++ch)
-                    for (int kh = 0; kh < a.KH; ++kh) {
-                        const uint4* arow = act + (size_t)(ch * a.BH + r * a.SH + kh * a.DH) * a.BW + (wq + pix) * SW;
-                        for (int kw = 0; kw < KW; ++kw, ++it)
-                            if ((it & 3) == part) {
-                                const uint4 v = arow[kw * DW];
-                                msum += __popc(v.z) + __popc(v.w);
-                            }
-                    }
-            }
-            msum += __shfl_xor_sync(0xffffffffu, msum, 8);
-            msum += __shfl_xor_sync(0xffffffffu, msum, 16);
         }
 
         int acc[P][C];
@@ -277,7 +274,7 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
         // ---------------- epilogue ----------------
         int ms[P];
 #pragma unroll
-        for (int p = 0; p < P; ++p) ms[p] = __shfl_sync(0xffffffffu, msum, p);
+        for (int p = 0; p < P; ++p) ms[p] = ms_s[r * a.TW + wq + p];      // broadcast loads
         const bool transposed = (a.e.ow == 1) || (a.e.out == nullptr);
         const bool has_res = (EPI == 1) && a.e.res != nullptr;
         const bool want_bits = (EPI == 1) && a.e.obits != nullptr;
@@ -317,11 +314,11 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
 #pragma unroll
                         for (int p = 0; p < P; ++p) res[p] = stg[lane * PITCH + p];
                     } else {
+                        const float* rptr = rbase + (long long)(cblk + lane) * a.e.rc + (long long)wo_first * a.e.rw;
 #pragma unroll
                         for (int p = 0; p < P; ++p) {
-                            const int wo = wo_first + p;
-                            res[p] = (c_ok && wo < a.Wo)
-                                         ? __ldg(rbase + (long long)(cblk + lane) * a.e.rc + (long long)wo * a.e.rw) : 0.0f;
+                            res[p] = (c_ok && wo_first + p < a.Wo) ? __ldg(rptr) : 0.0f;
+                            rptr += a.e.rw;
                         }
                     }
                 } else {
@@ -352,10 +349,11 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
                 float* obase = a.e.out + (long long)n * a.e.on + (long long)ho * a.e.oh;
                 if (!transposed) {
                     // channel-contiguous output (Linear's [rows, out]): lanes <-> channels is already coalesced
+                    float* optr = obase + (long long)(cblk + lane) * a.e.oc + (long long)wo_first * a.e.ow;
 #pragma unroll
                     for (int p = 0; p < P; ++p) {
-                        const int wo = wo_first + p;
-                        if (c_ok && wo < a.Wo) obase[(long long)(cblk + lane) * a.e.oc + (long long)wo * a.e.ow] = v[p];
+                        if (c_ok && wo_first + p < a.Wo) *optr = v[p];
+                        optr += a.e.ow;
                     }
                 } else {
                     // pixel-contiguous output (NCHW): transpose through shared memory so one store instruction
@@ -364,10 +362,13 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
 #pragma unroll
                     for (int p = 0; p < P; ++p) stg[lane * PITCH + p] = v[p];
                     __syncwarp();
+                    const bool lane_ok = pr < P && wo_first + pr < a.Wo;
+                    float* optr = obase + (long long)(cblk + rr) * a.e.oc + (wo_first + pr);
+                    const long long ostep = (long long)ROWS * a.e.oc;
 #pragma unroll
                     for (int r0 = 0; r0 < 32; r0 += ROWS) {
-                        const int rl = r0 + rr, c = cblk + rl, wo = wo_first + pr;
-                        if (pr < P && wo < a.Wo && c < a.Cout) obase[(long long)c * a.e.oc + wo] = stg[rl * PITCH + pr];
+                        if (lane_ok && cblk + r0 + rr < a.Cout) *optr = stg[(r0 + rr) * PITCH + pr];
+                        optr += ostep;
                     }
                 }
             }
@@ -405,7 +406,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static EncodeTiledFn encode_tiled_fn() {
+EncodeTiledFn encode_tiled_fn() {
     static EncodeTiledFn fn = nullptr;
     static std::once_flag once;
     std::call_once(once, [] {
@@ -452,10 +453,10 @@ static KernelFn pick_kernel(const Plan& p, int epi) {
 
 static int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
-static size_t plan_smem(int nch, int BH, int BW, int C, int nk, int NW, int P) {
+static size_t plan_smem(int nch, int BH, int BW, int C, int nk, int NW, int P, int TH, int TW) {
     const size_t act_bytes = (size_t)nch * BH * BW * 16;
     return 128 + ((act_bytes + 127) & ~(size_t)127) + (size_t)C * nk * 256 + (size_t)NW * 32 * (P | 1) * 4 +
-           (size_t)EP_N * 32 * C * 4;
+           (size_t)EP_N * 32 * C * 4 + (size_t)TH * TW * 4;
 }
 
 // Choose the tile shape for one layer by minimising a small cost model (host only, microseconds):
@@ -499,7 +500,7 @@ static int make_plan(const bnn_conv_geom& g, int Ho, int Wo, uint32_t flags, int
                 for (int TH = 1; TH <= Ho; ++TH) {
                     const int BH = (TH - 1) * g.stride_h + (g.kh - 1) * g.dil_h + 1;
                     if (BH > 256) break;
-                    const size_t smem = plan_smem(nch, BH, BW, C, nk, NW, P);
+                    const size_t smem = plan_smem(nch, BH, BW, C, nk, NW, P, TH, TW);
                     if (smem > smem_cap) break;
                     const int G = TH * gpr, rounds = ceil_div(G, NW);
                     if (rounds > 12 && TH > 1) break;

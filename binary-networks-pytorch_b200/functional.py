@@ -199,6 +199,30 @@ def blinear(act: PackedActivations, wts: PackedWeights, bias: Optional[torch.Ten
     return out
 
 
+def stem(x: torch.Tensor, w_t: torch.Tensor, bn: Tuple[torch.Tensor, torch.Tensor], nx=None,
+         want_bits: bool = True, flags: int = 0):
+    """conv7x7/2 + BatchNorm + ReLU + maxpool3x3/2 of the reference's ResNet stem in one kernel.
+    ``x`` [n,3,h,w] contiguous, ``w_t`` the weight repacked to [3,7,7,64].  Returns (out, PackedActivations):
+    ``out`` is [n,64,hp,wp] in channels_last memory format."""
+    _require_cuda_f32(x, "input")
+    if x.dim() != 4 or x.shape[1] != 3 or not x.is_contiguous():
+        raise native.NativeError(f"stem expects a contiguous [n,3,h,w] tensor, got {tuple(x.shape)}")
+    n, _, h, w = x.shape
+    hp, wp = ctypes.c_int32(0), ctypes.c_int32(0)
+    native.check(native.lib().bnn_stem_out_hw(h, w, ctypes.byref(hp), ctypes.byref(wp)), "bnn_stem_out_hw")
+    hp, wp = hp.value, wp.value
+    dev = x.device
+    with torch.cuda.device(dev):
+        out = torch.empty((n, 64, hp, wp), dtype=torch.float32, device=dev, memory_format=torch.channels_last)
+        bits = torch.empty((n, 1, hp, wp, 4), dtype=torch.int32, device=dev) if want_bits else None
+        rc = native.lib().bnn_stem_fwd(x.data_ptr(), n, h, w, w_t.data_ptr(), bn[0].data_ptr(), bn[1].data_ptr(),
+                                       None if nx is None else nx[0].data_ptr(),
+                                       None if nx is None else nx[1].data_ptr(), out.data_ptr(),
+                                       None if bits is None else bits.data_ptr(), flags, _stream_ptr(dev))
+    native.check(rc, "bnn_stem_fwd")
+    return out, (None if bits is None else PackedActivations(bits, n, 64, hp, wp))
+
+
 def ubench(which: int, iters: int = 200) -> float:
     """Integer-pipe micro-benchmark (giga warp-lane operations / s), see include/bnn_b200.h."""
     v = ctypes.c_double(0.0)

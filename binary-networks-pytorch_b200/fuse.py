@@ -17,8 +17,9 @@ Per-channel BatchNorm constants are folded once (``g = weight / sqrt(var + eps)`
 mean * g``) and re-folded when any of the BatchNorm tensors changes (version counters).
 Blocks the engine does not recognise run through their own ``forward`` (per-layer kernels), so
 the engine is always a drop-in for ``model`` in eval mode.  Results agree with the unfused path
-to fp32 rounding of the BatchNorm fold (tests/test_gpu_fused.py); the stem (fp32 conv7x7 + BN +
-ReLU + max-pool) and the classifier stay torch ops.
+to fp32 rounding of the BatchNorm fold (tests/test_gpu_fused.py).  The fp32 stem (conv7x7/2 + BN + ReLU +
+max-pool, reference resnet.py:85-92) is one kernel too (``bnn_stem_fwd``) when it has the reference's shape;
+global pooling and the classifier stay torch ops.
 """
 from typing import List, Optional, Tuple
 
@@ -124,16 +125,45 @@ def _conv_args(conv: Conv2d):
                 flags=runtime.kernel_flags()), conv._packed_weights(low)
 
 
+class _StemPlan:
+    """conv 7x7/2/3 (3->64, fp32, no bias) + BatchNorm + ReLU + MaxPool 3/2/1 (reference resnet.py:85-92)."""
+
+    def __init__(self, model: nn.Module) -> None:
+        self.ok = False
+        conv, bn, pool = getattr(model, "conv1", None), getattr(model, "bn1", None), getattr(model, "maxpool", None)
+        if type(conv) is not nn.Conv2d or not isinstance(bn, nn.BatchNorm2d) or not isinstance(pool, nn.MaxPool2d):
+            return
+        if not isinstance(getattr(model, "relu", None), nn.ReLU) or getattr(model, "stem_type", "basic") != "basic":
+            return
+        good = (conv.in_channels == 3 and conv.out_channels == 64 and conv.kernel_size == (7, 7) and conv.stride == (2, 2)
+                and conv.padding == (3, 3) and conv.dilation == (1, 1) and conv.groups == 1 and conv.bias is None
+                and conv.padding_mode == "zeros" and bn.track_running_stats)
+        good = good and (_pair(pool.kernel_size) == (3, 3) and _pair(pool.stride) == (2, 2) and _pair(pool.padding) == (1, 1)
+                         and _pair(pool.dilation) == (1, 1) and not pool.ceil_mode)
+        if good:
+            self.ok, self.conv, self.bn = True, conv, _FoldedBN(bn)
+            self.key, self.w_t = None, None
+
+    def weight(self) -> torch.Tensor:
+        w = self.conv.weight
+        key = (w.data_ptr(), w._version)
+        if key != self.key:
+            self.w_t = w.detach().permute(1, 2, 3, 0).contiguous()       # [3,7,7,64]: lane <-> output channel
+            self.key = key
+        return self.w_t
+
+
 class FusedResNet(nn.Module):
     """Inference engine over a prepared ResNet; same call signature as the wrapped model."""
 
-    def __init__(self, model: nn.Module) -> None:
+    def __init__(self, model: nn.Module, fuse_stem: bool = True) -> None:
         super().__init__()
         self.model = model
         blocks: List[nn.Module] = []
         for name in ("layer1", "layer2", "layer3", "layer4"):
             blocks += list(getattr(model, name))
         self.plans = [_BlockPlan(b) for b in blocks]
+        self.stem = _StemPlan(model) if fuse_stem else None
 
     @property
     def fused_blocks(self) -> int:
@@ -190,14 +220,21 @@ class FusedResNet(nn.Module):
         if m.training or (torch.is_grad_enabled() and any(p.requires_grad for p in m.parameters()) and x.requires_grad):
             raise native.NativeError("FusedResNet is an inference engine: call model.eval() and use torch.no_grad()")
         with torch.no_grad():
-            x = m.conv1(x)
-            if getattr(m, "stem_type", "basic") == "basic" and hasattr(m, "bn1"):
-                x = m.maxpool(m.relu(m.bn1(x)))
-            # the residual stream lives in NHWC between fused blocks (lanes <-> channels: every load/store of the
-            # conv epilogue is a full 128-byte line)
-            if self.plans and self.plans[0].fused:
-                x = x.contiguous(memory_format=torch.channels_last)
             bits = None
+            first = self.plans[0] if self.plans else None
+            if (self.stem is not None and self.stem.ok and first is not None and first.fused and x.is_cuda
+                    and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == 3 and min(x.shape[2:]) >= 7):
+                # fp32 stem in one kernel: NHWC residual stream + the first binarized conv's planes
+                x, bits = BF.stem(x.contiguous(), self.stem.weight(), self.stem.bn.get(), nx=self._entry_affine(first),
+                                  flags=runtime.kernel_flags())
+            else:
+                x = m.conv1(x)
+                if getattr(m, "stem_type", "basic") == "basic" and hasattr(m, "bn1"):
+                    x = m.maxpool(m.relu(m.bn1(x)))
+                # the residual stream lives in NHWC between fused blocks (lanes <-> channels: every load/store of
+                # the conv epilogue is a full 128-byte line)
+                if first is not None and first.fused:
+                    x = x.contiguous(memory_format=torch.channels_last)
             for i, plan in enumerate(self.plans):
                 nxt = self.plans[i + 1] if i + 1 < len(self.plans) else None
                 x, bits = self._run_block(plan, x, bits, nxt)
@@ -205,11 +242,11 @@ class FusedResNet(nn.Module):
             return m.fc(x)
 
 
-def optimize(model: nn.Module) -> nn.Module:
+def optimize(model: nn.Module, fuse_stem: bool = True) -> nn.Module:
     """Return the fused inference engine for ``model`` if its layout is recognised, else ``model``."""
     needed = ("conv1", "layer1", "layer2", "layer3", "layer4", "avgpool", "fc")
     if all(hasattr(model, k) for k in needed):
-        engine = FusedResNet(model)
+        engine = FusedResNet(model, fuse_stem=fuse_stem)
         if engine.fused_blocks:
             return engine
     return model

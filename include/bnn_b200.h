@@ -177,6 +177,21 @@ int bnn_blinear_fwd(const void *abits, const void *wbits,
                     uint32_t flags, void *stream);
 
 /*
+ * The fp32 stem of bnn.models.resnet (bnn/models/resnet.py:85-92,147-153) as one kernel:
+ *   conv 7x7 / 2 / pad 3 (3 -> 64 channels) -> eval BatchNorm (folded: v*bn_scale + bn_shift)
+ *   -> ReLU -> MaxPool 3x3 / 2 / pad 1.
+ * x: [n,3,h,w] contiguous fp32.  w_t: the conv weight repacked to [3][7][7][64] (16-byte aligned).
+ * out: [n,hp,wp,64] fp32 (NHWC = torch channels_last), (hp,wp) from bnn_stem_out_hw.
+ * out_bits (may be NULL): planes of sign(out*nx_scale + nx_shift) in the abits layout [n][1][hp][wp]
+ * for the first binarized conv (nx_* NULL = identity).  The conv accumulates one fma chain per output
+ * in (c_in, kh, kw) order; oracle/bnn_oracle.c restates the same order.
+ */
+int bnn_stem_out_hw(int32_t h, int32_t w, int32_t *hp, int32_t *wp);
+int bnn_stem_fwd(const float *x, int32_t n, int32_t h, int32_t w, const float *w_t,
+                 const float *bn_scale, const float *bn_shift, const float *nx_scale,
+                 const float *nx_shift, float *out, void *out_bits, uint32_t flags, void *stream);
+
+/*
  * Integer-pipe micro-benchmarks used for the popcount roofline denominator
  * (bench.py): runs `which` on every SM and returns achieved giga-operations/s
  * (warp-lane operations) in *gops.  Synchronises the device.  which:

@@ -347,3 +347,53 @@ void orc_bconv2d_dot(const uint32_t *abits, const uint32_t *wbits, const orc_geo
     for (int64_t i = 0; i < total; ++i) dot[i] = (int32_t)tmp[i];
     free(tmp);
 }
+
+/*
+ * Stem of bnn.models.resnet (bnn/models/resnet.py:85-92,147-153): conv 7x7/2/pad 3 (3->64, no bias)
+ * -> eval BatchNorm (folded affine) -> ReLU -> MaxPool 3x3/2/pad 1.  x [n,3,h,w], w [64,3,7,7] (torch
+ * layout), out [n,hp,wp,64] (NHWC).  The conv is one fma chain per output in (c_in, kh, kw) order,
+ * the order the CUDA kernel uses, so the comparison is bit-exact.
+ */
+void orc_stem(const float *x, int n, int h, int w, const float *wt, const float *bn_scale,
+              const float *bn_shift, const float *nx_scale, const float *nx_shift, float *out,
+              uint32_t *out_bits) {
+    const int hc = (h + 6 - 7) / 2 + 1, wc = (w + 6 - 7) / 2 + 1;
+    const int hp = (hc + 2 - 3) / 2 + 1, wp = (wc + 2 - 3) / 2 + 1;
+    float *conv = (float *)malloc(sizeof(float) * (size_t)hc * wc * 64);
+    if (!conv) return;
+    for (int in = 0; in < n; ++in) {
+        for (int r = 0; r < hc; ++r)
+            for (int c = 0; c < wc; ++c)
+                for (int co = 0; co < 64; ++co) {
+                    float acc = 0.0f;
+                    for (int ci = 0; ci < 3; ++ci)
+                        for (int kh = 0; kh < 7; ++kh)
+                            for (int kw = 0; kw < 7; ++kw) {
+                                const int hi = 2 * r - 3 + kh, wi = 2 * c - 3 + kw;
+                                const float v = (hi < 0 || hi >= h || wi < 0 || wi >= w)
+                                                    ? 0.0f : x[(((size_t)in * 3 + ci) * h + hi) * w + wi];
+                                acc = fmaf(v, wt[((co * 3 + ci) * 7 + kh) * 7 + kw], acc);
+                            }
+                    conv[((size_t)r * wc + c) * 64 + co] = fmaxf(fmaf(acc, bn_scale[co], bn_shift[co]), 0.0f);
+                }
+        for (int pr = 0; pr < hp; ++pr)
+            for (int pc = 0; pc < wp; ++pc) {
+                uint32_t u[4] = {0, 0, 0, 0};
+                for (int co = 0; co < 64; ++co) {
+                    float m = 0.0f;   /* ReLU output is >= 0, so 0 is neutral for the padded window */
+                    for (int i = 0; i < 3; ++i)
+                        for (int j = 0; j < 3; ++j) {
+                            const int r = 2 * pr - 1 + i, c = 2 * pc - 1 + j;
+                            if (r < 0 || r >= hc || c < 0 || c >= wc) continue;
+                            m = fmaxf(m, conv[((size_t)r * wc + c) * 64 + co]);
+                        }
+                    out[(((size_t)in * hp + pr) * wp + pc) * 64 + co] = m;
+                    const float b = nx_scale ? fmaf(nx_scale[co], m, nx_shift[co]) : m;
+                    if (b > 0.0f) u[co >> 5] |= 1u << (co & 31);
+                    if (b > 0.0f || b < 0.0f) u[2 + (co >> 5)] |= 1u << (co & 31);
+                }
+                if (out_bits) memcpy(out_bits + (((size_t)in * hp + pr) * wp + pc) * 4, u, 16);
+            }
+    }
+    free(conv);
+}

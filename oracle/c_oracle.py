@@ -146,3 +146,17 @@ def bconv2d_fused(abits, wbits, g: Geom, scale=None, bias=None, post=None, bn=No
 
 def _v(a):
     return None if a is None else a.ctypes.data
+
+
+def stem(x, w, bn_scale, bn_shift, nx=None):
+    """ResNet stem (conv7x7/2 + folded BN + ReLU + maxpool3/2/1): returns (out NHWC [n,hp,wp,64], bits [n,1,hp,wp,4])."""
+    x, w = np.ascontiguousarray(x, np.float32), np.ascontiguousarray(w, np.float32)
+    n, _, h, wd = x.shape
+    hc, wc = (h + 6 - 7) // 2 + 1, (wd + 6 - 7) // 2 + 1
+    hp, wp = (hc + 2 - 3) // 2 + 1, (wc + 2 - 3) // 2 + 1
+    out = np.zeros((n, hp, wp, 64), np.float32)
+    bits = np.zeros((n, 1, hp, wp, 4), np.uint32)
+    g, hh = _f32(bn_scale), _f32(bn_shift)
+    nxs, nxh = (None, None) if nx is None else (_f32(nx[0]), _f32(nx[1]))
+    lib().orc_stem(_p(x), n, h, wd, _p(w), _p(g), _p(hh), _p(nxs), _p(nxh), _p(out), _p(bits))
+    return out, bits

@@ -68,6 +68,22 @@ def test_avgpool_pack_bit_exact(shape, k, ceil):
     assert np.array_equal(got.bits.cpu().numpy().view(np.uint32), co.pack_act(x, pre_scale=s, pre_shift=h))
 
 
+@pytest.mark.parametrize("hw,flags", [((64, 64), 0), ((224, 224), 0), ((37, 52), 0), ((64, 64), native.F_STAGE_LDG), ((30, 30), 0)])
+def test_stem_kernel_bit_exact_vs_oracle(hw, flags):
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((2, 3) + hw).astype(np.float32)
+    w = (rng.standard_normal((64, 3, 7, 7)) * 0.1).astype(np.float32)
+    g, h = (0.5 + rng.random(64)).astype(np.float32), (rng.standard_normal(64) * 0.3).astype(np.float32)
+    nx = ((0.5 + rng.random(64)).astype(np.float32), (rng.standard_normal(64) * 0.2).astype(np.float32))
+    for nxa in (None, nx):
+        want_out, want_bits = co.stem(x, w, g, h, nx=nxa)
+        w_t = _d(w).permute(1, 2, 3, 0).contiguous()
+        out, bits = BF.stem(_d(x), w_t, (_d(g), _d(h)), nx=None if nxa is None else (_d(nxa[0]), _d(nxa[1])), flags=flags)
+        assert out.shape == (2, 64) + want_out.shape[1:3] and out.is_contiguous(memory_format=torch.channels_last)
+        assert np.array_equal(out.permute(0, 2, 3, 1).cpu().numpy(), want_out)
+        assert np.array_equal(bits.bits.cpu().numpy().view(np.uint32), want_bits)
+
+
 @pytest.fixture(autouse=True)
 def _fp32_glue():
     prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
@@ -88,7 +104,11 @@ def test_fused_engine_matches_reference_and_unfused(variant, golden_models):
         before = native.launch_count()
         fused = engine(x).cpu().numpy()
     launches = native.launch_count() - before
-    assert launches <= 1 + 16 + 3 * 2 + 2          # pack + 2 per block + (pool-pack, conv) per shortcut
+    assert launches == 1 + 16 + 3 * 2              # stem + 2 per block + (pool-pack, conv) per shortcut
+    with torch.no_grad():
+        no_stem = fuse.optimize(m, fuse_stem=False)(x).cpu().numpy()
+    print(variant, "stem kernel vs torch stem", rel_err(fused, no_stem))
+    assert rel_err(fused, no_stem) <= 1e-3
     ref = golden_models[variant + "_logits"]
     print(variant, "fused vs reference", rel_err(fused, ref), "fused vs unfused", rel_err(fused, eager))
     assert rel_err(fused, ref) <= 1e-3

@@ -230,3 +230,19 @@ def test_avgpool_pack_matches_torch():
     x = rng.standard_normal((2, 64, 5, 5)).astype(np.float32)
     s, h = (0.5 + rng.random(64)).astype(np.float32), rng.standard_normal(64).astype(np.float32)
     assert np.array_equal(co.pack_act(x, pre_scale=s, pre_shift=h), co.pack_act(x * s[None, :, None, None] + h[None, :, None, None]))
+
+
+def test_stem_oracle_matches_torch_modules():
+    """orc_stem == conv7x7/2 -> BatchNorm(eval) -> ReLU -> MaxPool(3,2,1) as torch executes the reference's stem."""
+    rng = np.random.default_rng(11)
+    for hw in ((64, 64), (37, 52)):
+        x = rng.standard_normal((2, 3) + hw).astype(np.float32)
+        w = (rng.standard_normal((64, 3, 7, 7)) * 0.1).astype(np.float32)
+        g, h = (0.5 + rng.random(64)).astype(np.float32), (rng.standard_normal(64) * 0.3).astype(np.float32)
+        out, bits = co.stem(x, w, g, h)
+        y = torch.nn.functional.conv2d(_t(x), _t(w), None, 2, 3)
+        y = torch.relu(y * _t(g).view(1, -1, 1, 1) + _t(h).view(1, -1, 1, 1))
+        y = torch.nn.functional.max_pool2d(y, 3, 2, 1).permute(0, 2, 3, 1).numpy()
+        assert out.shape == y.shape
+        assert rel_err(out, y) <= 1e-5
+        assert np.array_equal(bits, co.pack_act(np.ascontiguousarray(out.transpose(0, 3, 1, 2))))
