@@ -35,7 +35,7 @@ struct StemArgs {
     const float *bn_scale, *bn_shift, *nx_scale, *nx_shift;
     float* out;               // [n,hp,wp,64]
     uint4* obits;             // [n][1][hp][wp]
-    int N, H, W, Hc, Wc, Hp, Wp, tiles_h, tiles_w, stage_ldg;
+    int N, H, W, Hc, Wc, Hp, Wp, tiles_h, tiles_w, stage;
 };
 
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
@@ -62,20 +62,22 @@ stem_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ St
     const int cr0 = 2 * ph0 - 1, cc0 = 2 * pw0 - 1;            // first conv row / col of the tile
     const int hi0 = 2 * cr0 - 3, wi0 = 2 * cc0 - 3;            // first input row / col
 
-    if (!a.stage_ldg) {
+    // staging: bit 0 of `stage` = input window by TMA tensor load, bit 1 = weights by TMA bulk copy
+    const bool tma_in = (a.stage & 1) != 0, tma_w = (a.stage & 2) != 0;
+    if (tma_in || tma_w) {
         if (threadIdx.x == 0) {
-            prefetch_tensormap(&tmap);
+            if (tma_in) prefetch_tensormap(&tmap);
             mbar_init(bar, 1);
             fence_mbar_init();
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            mbar_expect_tx(bar, (unsigned)(ST_IN_BYTES + ST_W_BYTES));
-            tma_load_4d(in_s, &tmap, bar, wi0, hi0, 0, n);
-            bulk_load_1d(w_s, a.wt, (unsigned)ST_W_BYTES, bar);
+            mbar_expect_tx(bar, (unsigned)((tma_in ? ST_IN_BYTES : 0) + (tma_w ? ST_W_BYTES : 0)));
+            if (tma_in) tma_load_4d(in_s, &tmap, bar, wi0, hi0, 0, n);
+            if (tma_w) bulk_load_1d(w_s, a.wt, (unsigned)ST_W_BYTES, bar);
         }
-        mbar_wait(bar, 0);
-    } else {
+    }
+    if (!tma_in) {
         for (int i = threadIdx.x; i < ST_CI * ST_IR * ST_ICP; i += blockDim.x) {
             const int c = i % ST_ICP, r = (i / ST_ICP) % ST_IR, ci = i / (ST_ICP * ST_IR);
             const int hi = hi0 + r, wi = wi0 + c;
@@ -84,9 +86,14 @@ stem_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ St
                 v = __ldg(a.x + (((size_t)n * ST_CI + ci) * a.H + hi) * a.W + wi);
             in_s[i] = v;
         }
-        for (int i = threadIdx.x; i < ST_CI * ST_K * ST_K * ST_CO; i += blockDim.x) w_s[i] = __ldg(a.wt + i);
-        __syncthreads();
     }
+    if (!tma_w) {
+        const float4* src = reinterpret_cast<const float4*>(a.wt);
+        float4* dst = reinterpret_cast<float4*>(w_s);
+        for (int i = threadIdx.x; i < ST_CI * ST_K * ST_K * ST_CO / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    if (tma_in || tma_w) mbar_wait(bar, 0);
 
     // ---------------- conv + BN + ReLU into the shared conv tile ----------------
     for (int task = warp; task < ST_CR * 2; task += ST_WARPS) {
@@ -179,12 +186,15 @@ extern "C" int bnn_stem_fwd(const float* x, int32_t n, int32_t h, int32_t w, con
     a.Hc = (h + 6 - 7) / 2 + 1; a.Wc = (w + 6 - 7) / 2 + 1;
     a.Hp = (a.Hc + 2 - 3) / 2 + 1; a.Wp = (a.Wc + 2 - 3) / 2 + 1;
     a.tiles_h = (a.Hp + ST_PH - 1) / ST_PH; a.tiles_w = (a.Wp + ST_PW - 1) / ST_PW;
-    // TMA needs 16-byte aligned rows; otherwise stage with plain loads
-    a.stage_ldg = ((flags & BNN_F_STAGE_LDG) || (w % 4) != 0 || ((uintptr_t)x & 15)) ? 1 : 0;
+    // staging mode: weights by TMA bulk copy; the input window by TMA only on request (BNN_F_STEM_TMA_IN) and
+    // only when rows are 16-byte aligned -- plain coalesced loads otherwise
+    a.stage = (flags & BNN_F_STAGE_LDG) ? 0 : 2;
+    if ((flags & BNN_F_STEM_TMA_IN) && (w % 4) == 0 && ((uintptr_t)x & 15) == 0) a.stage |= 1;
+    if (flags & BNN_F_STEM_NO_BULK) a.stage &= ~2;
 
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
-    if (!a.stage_ldg) {
+    if (a.stage & 1) {
         EncodeTiledFn enc = encode_tiled_fn();
         if (!enc) return BNN_E_DRIVER;
         const cuuint64_t gdim[4] = {(cuuint64_t)w, (cuuint64_t)h, 3, (cuuint64_t)n};

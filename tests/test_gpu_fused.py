@@ -68,7 +68,7 @@ def test_avgpool_pack_bit_exact(shape, k, ceil):
     assert np.array_equal(got.bits.cpu().numpy().view(np.uint32), co.pack_act(x, pre_scale=s, pre_shift=h))
 
 
-@pytest.mark.parametrize("hw,flags", [((64, 64), 0), ((224, 224), 0), ((37, 52), 0), ((64, 64), native.F_STAGE_LDG), ((30, 30), 0)])
+@pytest.mark.parametrize("hw,flags", [((64, 64), 0), ((224, 224), 0), ((37, 52), 0), ((64, 64), native.F_STAGE_LDG), ((30, 30), 0), ((64, 64), 8)])
 def test_stem_kernel_bit_exact_vs_oracle(hw, flags):
     rng = np.random.default_rng(5)
     x = rng.standard_normal((2, 3) + hw).astype(np.float32)
