@@ -235,7 +235,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
     # fp32 glue (stem conv, fc) in true fp32: the reference's CPU float-sim is the parity target
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -288,26 +289,33 @@ def main():
         sync_all()
 
         graph = None
-        if not args.no_graph and world == 1:
+        if not args.no_graph:
             # the whole forward as one CUDA graph: ~60 launches per step stop costing host time
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 step_resident()
                 side.synchronize()
+                engine(x_dev)
+                side.synchronize()
                 graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph, stream=side):
-                    graph_out = step_resident()
+                with torch.cuda.graph(graph, stream=side):      # the forward only; the collective stays outside
+                    graph_out = engine(x_dev)
             torch.cuda.current_stream().wait_stream(side)
-            for _ in range(2):
+
+            def step_graph():
                 graph.replay()
+                return sharded.gather_logits(graph_out) if world > 1 else graph_out
+
+            for _ in range(2):
+                step_graph()
             sync_all()
 
         launches0 = native.launch_count()
         t_region0 = time.perf_counter()
         launches_per_step = None
         if graph is not None:
-            ms = timed(graph.replay, args.steps)
+            ms = timed(step_graph, args.steps)
             # a replay re-issues every captured launch; count them from one eager step
             l0 = native.launch_count(); step_resident(); launches_per_step = native.launch_count() - l0
         else:
@@ -367,7 +375,7 @@ def main():
                      for n, m in model.named_modules() if isinstance(m, bnn.layers.Conv2d)]
             reps = max(3, min(args.steps, 10))
             for _ in range(reps):
-                step_resident()
+                engine(x_dev)                      # rank-local: no collective in this pass
             torch.cuda.synchronize()
             BF.pack_activations, BF.bconv2d, BF.bconv2d_fused = orig_pack, orig_conv, orig_fused
             for h in hooks:

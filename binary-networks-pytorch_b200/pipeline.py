@@ -33,21 +33,19 @@ class HostPipeline:
             for k in range(2):
                 self.bufs[k].copy_(example.to(self.device, non_blocking=True))
                 with torch.cuda.stream(self.compute_stream):
-                    out = self._forward(self.bufs[k])       # warm-up: packs weights, folds BN
+                    out = self.engine(self.bufs[k])         # warm-up: packs weights, folds BN
                     self.compute_stream.synchronize()
                     if use_graphs:
                         g = torch.cuda.CUDAGraph()
-                        with torch.cuda.graph(g, stream=self.compute_stream):
-                            out = self._forward(self.bufs[k])
+                        with torch.cuda.graph(g, stream=self.compute_stream):   # forward only, collectives outside
+                            out = self.engine(self.bufs[k])
                         self.graphs[k] = g
-                self.outs[k] = out
-                self.host_out[k] = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+                    self.outs[k] = out
+                    final = self.post(out) if self.post is not None else out
+                    self.compute_stream.synchronize()
+                self.host_out[k] = torch.empty(final.shape, dtype=final.dtype).pin_memory()
                 self.done[k].record(self.compute_stream)
         torch.cuda.synchronize(self.device)
-
-    def _forward(self, x: torch.Tensor) -> torch.Tensor:
-        y = self.engine(x)
-        return self.post(y) if self.post is not None else y
 
     @property
     def h2d_bytes(self) -> int:
@@ -72,8 +70,9 @@ class HostPipeline:
             if self.graphs[k] is not None:
                 self.graphs[k].replay()
             else:
-                self.outs[k] = self._forward(self.bufs[k])
-            self.host_out[k].copy_(self.outs[k], non_blocking=True)
+                self.outs[k] = self.engine(self.bufs[k])
+            final = self.post(self.outs[k]) if self.post is not None else self.outs[k]
+            self.host_out[k].copy_(final, non_blocking=True)
             self.done[k].record(self.compute_stream)
         fin = torch.cuda.Event()
         fin.record(self.compute_stream)
