@@ -58,7 +58,7 @@ struct ConvArgs {
 //                                                k2 = PReLU slope, k3/k4 = next layer's pre-sign affine
 enum { EP_N = 5 };
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ int word_dis(uint32_t m, uint32_t s, uint32_t t) { return __popc(m & (s ^ t)); }
 __device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (c & (a ^ b)); }
@@ -180,15 +180,20 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
         if (ho >= a.Ho || wo_first >= a.Wo) continue;   // warp-uniform
 
         if constexpr (EPI == 1) {
-            // the residual tile is needed only after the K loop: pull its lines into L2 now so the epilogue
-            // does not sit on DRAM latency (one 32-byte pixel run per channel row)
+            // the residual tile is needed only after the K loop: start pulling its lines toward the SM now so the
+            // epilogue does not sit on DRAM latency
             if (a.e.res != nullptr) {
+                const float* rb = a.e.res + (long long)n * a.e.rn + (long long)ho * a.e.rh;
+                if (a.e.rw == 1) {            // NCHW: one 32-byte pixel run per channel row
 #pragma unroll
-                for (int j = 0; j < C; ++j) {
-                    const int c = (blk0 + j) * 32 + lane;
-                    if (c < a.Cout)
-                        prefetch_l2(a.e.res + (long long)n * a.e.rn + (long long)c * a.e.rc + (long long)ho * a.e.rh +
-                                    (long long)wo_first * a.e.rw);
+                    for (int j = 0; j < C; ++j) {
+                        const int c = (blk0 + j) * 32 + lane;
+                        if (c < a.Cout) prefetch_l1(rb + (long long)c * a.e.rc + wo_first);
+                    }
+                } else if (lane < P * C) {    // channels-last: one 128-byte line per (pixel, 32-channel block)
+                    const int j = lane / P, p = lane - j * P;
+                    if ((blk0 + j) * 32 < a.Cout && wo_first + p < a.Wo)
+                        prefetch_l1(rb + (long long)((blk0 + j) * 32) * a.e.rc + (long long)(wo_first + p) * a.e.rw);
                 }
             }
         }

@@ -4,13 +4,13 @@
 // passes on a GPU).  Output: the residual stream in NHWC fp32 plus the sign/mask planes the first
 // binarized conv needs, so the 112x112x64 conv output never goes to HBM.
 //
-// CTA = 7x8 pooled pixels x 64 channels.  The 35x39x3 input window arrives by one 4-D TMA tensor load
-// (zero fill = the conv's padding), the repacked [tap][64] weights by one TMA bulk copy.  Lanes <->
+// CTA = 4x8 pooled pixels x 64 channels, two CTAs per SM.  The repacked [tap][64] weights arrive by one TMA
+// bulk copy; the 23x39x3 input window is staged with coalesced loads (zero fill = the conv's padding).  Lanes <->
 // output channels: a weight is a conflict-free per-lane LDS, an input row segment is broadcast and kept
 // in registers for the 7 horizontal taps, 17 conv pixels x 1 channel of fp32 accumulators per thread
 // (sequential fma chain in (c_in, kh, kw) order -- the oracle restates exactly this order).  The
-// 15x17x64 conv tile goes through shared memory to the 3x3 max, and the pooled pixel's planes are two
-// ballots.  FP32-FMA bound: 118 M multiply-adds per 224x224 image, ~19 % recomputed halo.
+// 9x17x64 conv tile goes through shared memory to the 3x3 max, and the pooled pixel's planes are two
+// ballots.  FP32-FMA bound: 118 M multiply-adds per 224x224 image, ~20 % recomputed halo.
 #include "common.cuh"
 
 #include <cudaTypedefs.h>
@@ -18,12 +18,12 @@
 
 namespace bnn {
 
-constexpr int ST_PH = 7, ST_PW = 8;                       // pooled tile
-constexpr int ST_CR = 2 * ST_PH + 1, ST_CC = 2 * ST_PW + 1;   // conv tile 15 x 17
-constexpr int ST_IR = 2 * ST_CR + 5, ST_IC = 2 * ST_CC + 5;   // input tile 35 x 39
+constexpr int ST_PH = 4, ST_PW = 8;                       // pooled tile
+constexpr int ST_CR = 2 * ST_PH + 1, ST_CC = 2 * ST_PW + 1;   // conv tile 9 x 17
+constexpr int ST_IR = 2 * ST_CR + 5, ST_IC = 2 * ST_CC + 5;   // input tile 23 x 39
 constexpr int ST_ICP = 40;                                // input row pitch (floats), 160 B
 constexpr int ST_CO = 64, ST_CI = 3, ST_K = 7;
-constexpr int ST_WARPS = 10;
+constexpr int ST_WARPS = 9;
 constexpr size_t ST_IN_BYTES = (size_t)ST_CI * ST_IR * ST_ICP * 4;            // 16800
 constexpr size_t ST_W_BYTES = (size_t)ST_CI * ST_K * ST_K * ST_CO * 4;        // 37632
 constexpr size_t ST_CONV_BYTES = (size_t)ST_CR * ST_CC * ST_CO * 4;          // 65280
@@ -45,7 +45,7 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
         : "memory");
 }
 
-__global__ void __launch_bounds__(ST_WARPS * 32, 1)
+__global__ void __launch_bounds__(ST_WARPS * 32, 2)
 stem_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StemArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
