@@ -81,6 +81,50 @@ pack_act_kernel(const float* __restrict__ x, long long sn, long long sc, long lo
 }
 
 // ---------------------------------------------------------------------------
+// channel-contiguous input (stride_c == 1: torch channels_last, or Linear's [rows, features]):
+// one warp per output pixel, lanes <-> channels, so every load is one 128-byte line and the
+// 32 sign / mask bits of a block are one ballot each.  Same pooling / affine semantics as above.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pack_act_cl_kernel(const float* __restrict__ x, long long sn, long long sh, long long sw,
+                   int N, int C, int H, int W, int nch, int pool, int Hin, int Win,
+                   const float* __restrict__ pre_scale, const float* __restrict__ pre_shift,
+                   uint32_t* __restrict__ abits) {
+    const long long pixels = (long long)N * H * W;
+    const long long pix = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (pix >= pixels) return;                               // warp-uniform
+    const int lane = threadIdx.x & 31;
+    const int w = (int)(pix % W);
+    const long long r = pix / W;
+    const int h = (int)(r % H), n = (int)(r / H);
+    const int k = pool > 1 ? pool : 1;
+    const float* base = x + n * sn + (long long)h * k * sh + (long long)w * k * sw;
+    const int hmax = min(k, Hin - h * k), wmax = min(k, Win - w * k);
+    const float inv_cnt_den = (float)(hmax * wmax);
+    for (int blk = 0; blk < 2 * nch; ++blk) {
+        const int c = blk * 32 + lane;
+        float v = 0.0f;
+        if (c < C) {
+            if (k == 1) v = __ldg(base + c);
+            else {
+                float sum = 0.0f;
+                for (int i = 0; i < hmax; ++i)
+                    for (int j = 0; j < wmax; ++j) sum = __fadd_rn(sum, __ldg(base + i * sh + j * sw + c));
+                v = __fdiv_rn(sum, inv_cnt_den);
+            }
+            if (pre_scale != nullptr) v = __fadd_rn(__fmul_rn(v, __ldg(pre_scale + c)), __ldg(pre_shift + c));
+        }
+        const uint32_t sw_ = __ballot_sync(0xffffffffu, c < C && v > 0.0f);
+        const uint32_t mw_ = __ballot_sync(0xffffffffu, c < C && (v > 0.0f || v < 0.0f));
+        if (lane == 0) {
+            uint32_t* u = abits + ((((size_t)n * nch + (blk >> 1)) * H + h) * W + w) * 4;
+            u[blk & 1] = sw_;
+            u[2 + (blk & 1)] = mw_;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // weights: one CTA per output channel.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ double block_sum(double v, double* scratch) {
@@ -181,8 +225,18 @@ static int launch_pack(const float* x, int64_t sn, int64_t sc, int64_t sh, int64
         wo = ceil_mode ? (w + pool - 1) / pool : w / pool;
         if (ho <= 0 || wo <= 0) return BNN_E_SHAPE;
     }
-    const long long total = (long long)n * nch * ho * wo;
     const int threads = 256;
+    if (sc == 1 && c >= 32) {
+        // channels are contiguous: warp-per-pixel ballot kernel
+        const long long pixels = (long long)n * ho * wo;
+        const long long blocks = (pixels + 7) / 8;
+        if (blocks > 0x7fffffffLL) return BNN_E_UNSUPPORTED;
+        pack_act_cl_kernel<<<(unsigned)blocks, threads, 0, stream>>>(x, sn, sh, sw, n, c, ho, wo, nch, pool, h, w,
+                                                                    pre_scale, pre_shift, (uint32_t*)abits);
+        count_launch(1);
+        return (int)cudaGetLastError();
+    }
+    const long long total = (long long)n * nch * ho * wo;
     const long long blocks = (total + threads - 1) / threads;
     if (blocks > 0x7fffffffLL) return BNN_E_UNSUPPORTED;
     pack_act_kernel<<<(unsigned)blocks, threads, 0, stream>>>(x, sn, sc, sh, sw, n, c, ho, wo, nch, pool, h, w,

@@ -63,6 +63,12 @@ def test_avgpool_pack_bit_exact(shape, k, ceil):
     x = np.maximum(rng.standard_normal(shape), 0).astype(np.float32)
     got = BF.pack_activations(_d(x), pool=k, ceil_mode=ceil)
     assert np.array_equal(got.bits.cpu().numpy().view(np.uint32), co.pack_act(x, pool=k, ceil_mode=ceil))
+    xcl = _d(x).contiguous(memory_format=torch.channels_last)          # warp-per-pixel ballot kernel
+    got = BF.pack_activations(xcl, pool=k, ceil_mode=ceil)
+    assert np.array_equal(got.bits.cpu().numpy().view(np.uint32), co.pack_act(x, pool=k, ceil_mode=ceil))
+    s2, h2 = (0.5 + rng.random(shape[1])).astype(np.float32), rng.standard_normal(shape[1]).astype(np.float32)
+    got = BF.pack_activations(xcl, pre=(_d(s2), _d(h2)))
+    assert np.array_equal(got.bits.cpu().numpy().view(np.uint32), co.pack_act(x, pre_scale=s2, pre_shift=h2))
     s, h = (0.5 + rng.random(shape[1])).astype(np.float32), rng.standard_normal(shape[1]).astype(np.float32)
     got = BF.pack_activations(_d(x), pre=(_d(s), _d(h)))
     assert np.array_equal(got.bits.cpu().numpy().view(np.uint32), co.pack_act(x, pre_scale=s, pre_shift=h))
