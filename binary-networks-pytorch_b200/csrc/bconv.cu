@@ -285,6 +285,7 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
         const bool want_bits = (EPI == 1) && a.e.obits != nullptr;
         // ReLU output with no affine in front of the next sign(): "non-zero" and "positive" coincide
         const bool relu_bits = a.e.act == BNN_ACT_RELU && a.e.nx_scale == nullptr && !(has_res && a.e.res_after_act);
+        const bool full = (wo_first + P <= a.Wo) && ((blk0 + C) * 32 <= a.Cout);
         uint32_t sbits[C], mbits[C];     // lane p keeps the packed words of pixel p
 #pragma unroll
         for (int j = 0; j < C; ++j) { sbits[j] = 0u; mbits[j] = 0u; }
@@ -302,51 +303,77 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
                 for (int p = 0; p < P; ++p)
                     v[p] = __fmul_rn(__fadd_rn(__fmul_rn(k0, (float)(ms[p] - 2 * acc[p][j])), k1), k2);
             } else {
+                // ---- fused epilogue.  `full` groups (all P pixels and all 32 channels valid) take the
+                //      predicate-free path; strides are 32-bit here (the host checked the tensors fit)
                 float res[P];
-                if (has_res) {
-                    // residual tile [32 ch][P px] -> per-lane channel rows, coalesced along pixels when rw == 1
+                const bool res_direct = has_res && a.e.rw != 1;
+                if (has_res && !res_direct) {
+                    // NCHW residual: tile [32 ch][P px] through shared memory, coalesced along pixels
                     const float* rbase = a.e.res + (long long)n * a.e.rn + (long long)ho * a.e.rh;
-                    if (a.e.rw == 1) {
-                        __syncwarp();
+                    __syncwarp();
 #pragma unroll
-                        for (int r0 = 0; r0 < 32; r0 += ROWS) {
-                            const int rl = r0 + rr, c = cblk + rl, wo = wo_first + pr;
-                            float t = 0.0f;
-                            if (pr < P && wo < a.Wo && c < a.Cout) t = __ldg(rbase + (long long)c * a.e.rc + wo);
-                            if (pr < P) stg[rl * PITCH + pr] = t;
-                        }
-                        __syncwarp();
-#pragma unroll
-                        for (int p = 0; p < P; ++p) res[p] = stg[lane * PITCH + p];
-                    } else {
-                        const float* rptr = rbase + (long long)(cblk + lane) * a.e.rc + (long long)wo_first * a.e.rw;
-#pragma unroll
-                        for (int p = 0; p < P; ++p) {
-                            res[p] = (c_ok && wo_first + p < a.Wo) ? __ldg(rptr) : 0.0f;
-                            rptr += a.e.rw;
-                        }
+                    for (int r0 = 0; r0 < 32; r0 += ROWS) {
+                        const int rl = r0 + rr, c = cblk + rl, wo = wo_first + pr;
+                        float t = 0.0f;
+                        if (pr < P && wo < a.Wo && c < a.Cout) t = __ldg(rbase + (long long)c * a.e.rc + wo);
+                        if (pr < P) stg[rl * PITCH + pr] = t;
                     }
-                } else {
+                    __syncwarp();
 #pragma unroll
-                    for (int p = 0; p < P; ++p) res[p] = 0.0f;
+                    for (int p = 0; p < P; ++p) res[p] = stg[lane * PITCH + p];
+                } else if (res_direct) {
+                    // channel-contiguous residual (NHWC): lanes <-> channels reads whole 128-byte lines
+                    const float* rp = a.e.res + (long long)n * a.e.rn + (long long)ho * a.e.rh +
+                                      (long long)wo_first * a.e.rw + (cblk + lane) * (int)a.e.rc;
+                    const int rw = (int)a.e.rw;
+                    if (full) {
+#pragma unroll
+                        for (int p = 0; p < P; ++p) res[p] = __ldg(rp + p * rw);
+                    } else {
+#pragma unroll
+                        for (int p = 0; p < P; ++p) res[p] = (c_ok && wo_first + p < a.Wo) ? __ldg(rp + p * rw) : 0.0f;
+                    }
                 }
-                const bool after = a.e.res_after_act != 0;
 #pragma unroll
-                for (int p = 0; p < P; ++p) {
-                    float z = __fmaf_rn(k0, (float)(ms[p] - 2 * acc[p][j]), k1);
-                    z = __fadd_rn(z, after ? 0.0f : res[p]);
-                    if (a.e.act == BNN_ACT_RELU) z = fmaxf(z, 0.0f);
-                    else if (a.e.act == BNN_ACT_PRELU) z = (z > 0.0f) ? z : __fmul_rn(k2, z);
-                    v[p] = __fadd_rn(z, after ? res[p] : 0.0f);
+                for (int p = 0; p < P; ++p) v[p] = __fmaf_rn(k0, (float)(ms[p] - 2 * acc[p][j]), k1);
+                if (has_res && !a.e.res_after_act) {
+#pragma unroll
+                    for (int p = 0; p < P; ++p) v[p] = __fadd_rn(v[p], res[p]);
+                }
+                if (a.e.act == BNN_ACT_RELU) {
+#pragma unroll
+                    for (int p = 0; p < P; ++p) v[p] = fmaxf(v[p], 0.0f);
+                } else if (a.e.act == BNN_ACT_PRELU) {
+#pragma unroll
+                    for (int p = 0; p < P; ++p) v[p] = (v[p] > 0.0f) ? v[p] : __fmul_rn(k2, v[p]);
+                }
+                if (has_res && a.e.res_after_act) {
+#pragma unroll
+                    for (int p = 0; p < P; ++p) v[p] = __fadd_rn(v[p], res[p]);
                 }
                 if (want_bits) {
-                    const float k3 = epc[3 * 32 * C + cl], k4 = epc[4 * 32 * C + cl];
+                    float b[P];
+                    if (a.e.nx_scale) {
+                        const float k3 = epc[3 * 32 * C + cl], k4 = epc[4 * 32 * C + cl];
 #pragma unroll
-                    for (int p = 0; p < P; ++p) {
-                        const float b = a.e.nx_scale ? __fmaf_rn(k3, v[p], k4) : v[p];
-                        const uint32_t sw = __ballot_sync(0xffffffffu, c_ok && b > 0.0f);
-                        const uint32_t mw = relu_bits ? sw : __ballot_sync(0xffffffffu, c_ok && (b > 0.0f || b < 0.0f));
-                        if (lane == p) { sbits[j] = sw; mbits[j] = mw; }
+                        for (int p = 0; p < P; ++p) b[p] = __fmaf_rn(k3, v[p], k4);
+                    } else {
+#pragma unroll
+                        for (int p = 0; p < P; ++p) b[p] = v[p];
+                    }
+                    if (relu_bits) {
+#pragma unroll
+                        for (int p = 0; p < P; ++p) {
+                            const uint32_t sw = __ballot_sync(0xffffffffu, c_ok && b[p] > 0.0f);
+                            if (lane == p) { sbits[j] = sw; mbits[j] = sw; }
+                        }
+                    } else {
+#pragma unroll
+                        for (int p = 0; p < P; ++p) {
+                            const uint32_t sw = __ballot_sync(0xffffffffu, c_ok && b[p] > 0.0f);
+                            const uint32_t mw = __ballot_sync(0xffffffffu, c_ok && (b[p] > 0.0f || b[p] < 0.0f));
+                            if (lane == p) { sbits[j] = sw; mbits[j] = mw; }
+                        }
                     }
                 }
             }
@@ -354,11 +381,15 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
                 float* obase = a.e.out + (long long)n * a.e.on + (long long)ho * a.e.oh;
                 if (!transposed) {
                     // channel-contiguous output (Linear's [rows, out]): lanes <-> channels is already coalesced
-                    float* optr = obase + (long long)(cblk + lane) * a.e.oc + (long long)wo_first * a.e.ow;
+                    float* op = obase + (long long)wo_first * a.e.ow + (cblk + lane) * (int)a.e.oc;
+                    const int ow = (int)a.e.ow;
+                    if (full) {
 #pragma unroll
-                    for (int p = 0; p < P; ++p) {
-                        if (c_ok && wo_first + p < a.Wo) *optr = v[p];
-                        optr += a.e.ow;
+                        for (int p = 0; p < P; ++p) op[p * ow] = v[p];
+                    } else {
+#pragma unroll
+                        for (int p = 0; p < P; ++p)
+                            if (c_ok && wo_first + p < a.Wo) op[p * ow] = v[p];
                     }
                 } else {
                     // pixel-contiguous output (NCHW): transpose through shared memory so one store instruction
@@ -557,6 +588,12 @@ static int launch_bconv(const void* abits, const void* wbits, const bnn_conv_geo
     }
 
     const int epi = (ep.bn_scale || ep.residual || ep.act != BNN_ACT_NONE || ep.out_bits || ep.nx_scale) ? 1 : 0;
+    {   // the kernel indexes inside one image row with 32-bit element offsets
+        const long long lim = 0x7fffffffLL;
+        auto span = [&](int64_t sc_, int64_t sw_) { return (long long)g.c_out * (sc_ < 0 ? -sc_ : sc_) + (long long)Wo * (sw_ < 0 ? -sw_ : sw_); };
+        if ((ep.out && span(ep.ostride_c, ep.ostride_w) > lim) || (ep.residual && span(ep.rstride_c, ep.rstride_w) > lim))
+            return BNN_E_UNSUPPORTED;
+    }
     if (epi) flags &= ~BNN_F_NO_CSA;
     Plan pl;
     int rc = make_plan(g, Ho, Wo, flags, sms, &pl);

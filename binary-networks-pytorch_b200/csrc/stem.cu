@@ -96,11 +96,11 @@ stem_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ St
     if (tma_in || tma_w) mbar_wait(bar, 0);
 
     // ---------------- conv + BN + ReLU into the shared conv tile ----------------
-    for (int task = warp; task < ST_CR * 2; task += ST_WARPS) {
-        const int r = task >> 1, ch = (task & 1) * 32 + lane;
-        float acc[ST_CC];
+    // one warp = one conv row of the tile, both 32-channel blocks: the broadcast input row feeds 2 x 17 fma chains
+    for (int r = warp; r < ST_CR; r += ST_WARPS) {
+        float acc0[ST_CC], acc1[ST_CC];
 #pragma unroll
-        for (int c = 0; c < ST_CC; ++c) acc[c] = 0.0f;
+        for (int c = 0; c < ST_CC; ++c) { acc0[c] = 0.0f; acc1[c] = 0.0f; }
         for (int ci = 0; ci < ST_CI; ++ci) {
 #pragma unroll 1
             for (int kh = 0; kh < ST_K; ++kh) {
@@ -111,22 +111,27 @@ stem_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ St
                     const float4 v = irow[q];              // warp-uniform address: broadcast
                     iv[4 * q] = v.x; iv[4 * q + 1] = v.y; iv[4 * q + 2] = v.z; iv[4 * q + 3] = v.w;
                 }
-                const float* wrow = w_s + ((ci * ST_K + kh) * ST_K) * ST_CO + ch;
+                const float* wrow = w_s + ((ci * ST_K + kh) * ST_K) * ST_CO + lane;
 #pragma unroll
                 for (int kw = 0; kw < ST_K; ++kw) {
-                    const float wv = wrow[kw * ST_CO];
+                    const float w0 = wrow[kw * ST_CO], w1 = wrow[kw * ST_CO + 32];
 #pragma unroll
-                    for (int c = 0; c < ST_CC; ++c) acc[c] = __fmaf_rn(iv[2 * c + kw], wv, acc[c]);
+                    for (int c = 0; c < ST_CC; ++c) {
+                        acc0[c] = __fmaf_rn(iv[2 * c + kw], w0, acc0[c]);
+                        acc1[c] = __fmaf_rn(iv[2 * c + kw], w1, acc1[c]);
+                    }
                 }
             }
         }
-        const float g = __ldg(a.bn_scale + ch), h = __ldg(a.bn_shift + ch);
+        const float g0 = __ldg(a.bn_scale + lane), h0 = __ldg(a.bn_shift + lane);
+        const float g1 = __ldg(a.bn_scale + 32 + lane), h1 = __ldg(a.bn_shift + 32 + lane);
         const bool row_ok = (unsigned)(cr0 + r) < (unsigned)a.Hc;
 #pragma unroll
         for (int c = 0; c < ST_CC; ++c) {
             const bool ok = row_ok && (unsigned)(cc0 + c) < (unsigned)a.Wc;
             // positions outside the conv output are max-pool padding: 0 is neutral after the ReLU
-            conv_s[(r * ST_CC + c) * ST_CO + ch] = ok ? fmaxf(__fmaf_rn(acc[c], g, h), 0.0f) : 0.0f;
+            conv_s[(r * ST_CC + c) * ST_CO + lane] = ok ? fmaxf(__fmaf_rn(acc0[c], g0, h0), 0.0f) : 0.0f;
+            conv_s[(r * ST_CC + c) * ST_CO + 32 + lane] = ok ? fmaxf(__fmaf_rn(acc1[c], g1, h1), 0.0f) : 0.0f;
         }
     }
     __syncthreads();
