@@ -31,7 +31,7 @@ constexpr size_t ST_SMEM = 128 + ((ST_IN_BYTES + 127) & ~(size_t)127) + ST_W_BYT
 
 struct StemArgs {
     const float* x;           // [n,3,h,w] contiguous
-    const float* wt;          // [3][7][7][64]
+    const float* wt;          // [3][7][7][32][2]: (w[l], w[l + 32]) pairs
     const float *bn_scale, *bn_shift, *nx_scale, *nx_shift;
     float* out;               // [n,hp,wp,64]
     uint4* obits;             // [n][1][hp][wp]
@@ -43,6 +43,20 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
+}
+
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));    // SASS: FFMA2 (sm_100)
+    return r;
 }
 
 __global__ void __launch_bounds__(ST_WARPS * 32, 2)
@@ -98,9 +112,13 @@ stem_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ St
     // ---------------- conv + BN + ReLU into the shared conv tile ----------------
     // one warp = one conv row of the tile, both 32-channel blocks: the broadcast input row feeds 2 x 17 fma chains
     for (int r = warp; r < ST_CR; r += ST_WARPS) {
-        float acc0[ST_CC], acc1[ST_CC];
+        // packed accumulators: (lo, hi) = (channel lane, channel lane + 32) of conv pixel c.  One FFMA2
+        // (fma.rn.f32x2: input broadcast to both halves, weight pair from one LDS.64) does both channels --
+        // the loop is issue-bound, so halving the FMA instruction count is what matters.  Each half is an
+        // ordinary IEEE fma, so the result is bit-identical to the scalar chain the oracle restates.
+        unsigned long long acc[ST_CC];
 #pragma unroll
-        for (int c = 0; c < ST_CC; ++c) { acc0[c] = 0.0f; acc1[c] = 0.0f; }
+        for (int c = 0; c < ST_CC; ++c) acc[c] = 0ull;
         for (int ci = 0; ci < ST_CI; ++ci) {
 #pragma unroll 1
             for (int kh = 0; kh < ST_K; ++kh) {
@@ -111,15 +129,13 @@ stem_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ St
                     const float4 v = irow[q];              // warp-uniform address: broadcast
                     iv[4 * q] = v.x; iv[4 * q + 1] = v.y; iv[4 * q + 2] = v.z; iv[4 * q + 3] = v.w;
                 }
-                const float* wrow = w_s + ((ci * ST_K + kh) * ST_K) * ST_CO + lane;
+                const float2* wrow = reinterpret_cast<const float2*>(w_s) + ((ci * ST_K + kh) * ST_K) * 32 + lane;
 #pragma unroll
                 for (int kw = 0; kw < ST_K; ++kw) {
-                    const float w0 = wrow[kw * ST_CO], w1 = wrow[kw * ST_CO + 32];
+                    const float2 w2 = wrow[kw * 32];
+                    const unsigned long long ww = pack2(w2.x, w2.y);
 #pragma unroll
-                    for (int c = 0; c < ST_CC; ++c) {
-                        acc0[c] = __fmaf_rn(iv[2 * c + kw], w0, acc0[c]);
-                        acc1[c] = __fmaf_rn(iv[2 * c + kw], w1, acc1[c]);
-                    }
+                    for (int c = 0; c < ST_CC; ++c) acc[c] = fma2(pack2(iv[2 * c + kw], iv[2 * c + kw]), ww, acc[c]);
                 }
             }
         }
@@ -129,9 +145,11 @@ stem_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ St
 #pragma unroll
         for (int c = 0; c < ST_CC; ++c) {
             const bool ok = row_ok && (unsigned)(cc0 + c) < (unsigned)a.Wc;
+            float lo, hi;
+            unpack2(acc[c], lo, hi);
             // positions outside the conv output are max-pool padding: 0 is neutral after the ReLU
-            conv_s[(r * ST_CC + c) * ST_CO + lane] = ok ? fmaxf(__fmaf_rn(acc0[c], g0, h0), 0.0f) : 0.0f;
-            conv_s[(r * ST_CC + c) * ST_CO + 32 + lane] = ok ? fmaxf(__fmaf_rn(acc1[c], g1, h1), 0.0f) : 0.0f;
+            conv_s[(r * ST_CC + c) * ST_CO + lane] = ok ? fmaxf(__fmaf_rn(lo, g0, h0), 0.0f) : 0.0f;
+            conv_s[(r * ST_CC + c) * ST_CO + 32 + lane] = ok ? fmaxf(__fmaf_rn(hi, g1, h1), 0.0f) : 0.0f;
         }
     }
     __syncthreads();

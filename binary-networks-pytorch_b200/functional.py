@@ -199,10 +199,15 @@ def blinear(act: PackedActivations, wts: PackedWeights, bias: Optional[torch.Ten
     return out
 
 
+def stem_weight_layout(w: torch.Tensor) -> torch.Tensor:
+    """[64,3,7,7] conv weight -> [3,7,7,32,2] with out[ci,kh,kw,l,b] = w[b*32+l,ci,kh,kw] (bnn_stem_fwd's w_t)."""
+    return w.detach().permute(1, 2, 3, 0).reshape(3, 7, 7, 2, 32).transpose(3, 4).contiguous()
+
+
 def stem(x: torch.Tensor, w_t: torch.Tensor, bn: Tuple[torch.Tensor, torch.Tensor], nx=None,
          want_bits: bool = True, flags: int = 0):
     """conv7x7/2 + BatchNorm + ReLU + maxpool3x3/2 of the reference's ResNet stem in one kernel.
-    ``x`` [n,3,h,w] contiguous, ``w_t`` the weight repacked to [3,7,7,64].  Returns (out, PackedActivations):
+    ``x`` [n,3,h,w] contiguous, ``w_t`` the weight repacked to [3,7,7,32,2] (``stem_weight_layout``).  Returns (out, PackedActivations):
     ``out`` is [n,64,hp,wp] in channels_last memory format."""
     _require_cuda_f32(x, "input")
     if x.dim() != 4 or x.shape[1] != 3 or not x.is_contiguous():

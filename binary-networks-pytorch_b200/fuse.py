@@ -148,7 +148,8 @@ class _StemPlan:
         w = self.conv.weight
         key = (w.data_ptr(), w._version)
         if key != self.key:
-            self.w_t = w.detach().permute(1, 2, 3, 0).contiguous()       # [3,7,7,64]: lane <-> output channel
+            # [3,7,7,32,2]: lane l holds channels (l, l+32) as one 8-byte pair for the packed-fma stem kernel
+            self.w_t = w.detach().permute(1, 2, 3, 0).reshape(3, 7, 7, 2, 32).transpose(3, 4).contiguous()
             self.key = key
         return self.w_t
 

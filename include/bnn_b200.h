@@ -182,7 +182,8 @@ int bnn_blinear_fwd(const void *abits, const void *wbits,
  * The fp32 stem of bnn.models.resnet (bnn/models/resnet.py:85-92,147-153) as one kernel:
  *   conv 7x7 / 2 / pad 3 (3 -> 64 channels) -> eval BatchNorm (folded: v*bn_scale + bn_shift)
  *   -> ReLU -> MaxPool 3x3 / 2 / pad 1.
- * x: [n,3,h,w] contiguous fp32.  w_t: the conv weight repacked to [3][7][7][64] (16-byte aligned).
+ * x: [n,3,h,w] contiguous fp32.  w_t: the conv weight [64,3,7,7] repacked to [3][7][7][32][2] with
+ * w_t[ci][kh][kw][l][b] = w[b*32 + l][ci][kh][kw] (16-byte aligned): a lane's two channels are one 8-byte load.
  * out: [n,hp,wp,64] fp32 (NHWC = torch channels_last), (hp,wp) from bnn_stem_out_hw.
  * out_bits (may be NULL): planes of sign(out*nx_scale + nx_shift) in the abits layout [n][1][hp][wp]
  * for the first binarized conv (nx_* NULL = identity).  The conv accumulates one fma chain per output

@@ -12,7 +12,7 @@ x = rng.standard_normal((2, 3, h, w)).astype(np.float32)
 wt = (rng.standard_normal((64, 3, 7, 7)) * 0.1).astype(np.float32)
 g, hh = (0.5 + rng.random(64)).astype(np.float32), (rng.standard_normal(64) * 0.3).astype(np.float32)
 d = lambda a: torch.from_numpy(a).cuda()
-w_t = d(wt).permute(1, 2, 3, 0).contiguous()
+w_t = BF.stem_weight_layout(d(wt))
 out, bits = BF.stem(d(x), w_t, (d(g), d(hh)), flags=flags)
 torch.cuda.synchronize()
 want_out, want_bits = co.stem(x, wt, g, hh)

@@ -83,7 +83,7 @@ def test_stem_kernel_bit_exact_vs_oracle(hw, flags):
     nx = ((0.5 + rng.random(64)).astype(np.float32), (rng.standard_normal(64) * 0.2).astype(np.float32))
     for nxa in (None, nx):
         want_out, want_bits = co.stem(x, w, g, h, nx=nxa)
-        w_t = _d(w).permute(1, 2, 3, 0).contiguous()
+        w_t = BF.stem_weight_layout(_d(w))
         out, bits = BF.stem(_d(x), w_t, (_d(g), _d(h)), nx=None if nxa is None else (_d(nxa[0]), _d(nxa[1])), flags=flags)
         assert out.shape == (2, 64) + want_out.shape[1:3] and out.is_contiguous(memory_format=torch.channels_last)
         assert np.array_equal(out.permute(0, 2, 3, 1).cpu().numpy(), want_out)
