@@ -27,7 +27,7 @@ constexpr int ST_WARPS = 9;
 constexpr size_t ST_IN_BYTES = (size_t)ST_CI * ST_IR * ST_ICP * 4;            // 16800
 constexpr size_t ST_W_BYTES = (size_t)ST_CI * ST_K * ST_K * ST_CO * 4;        // 37632
 constexpr size_t ST_CONV_BYTES = (size_t)ST_CR * ST_CC * ST_CO * 4;          // 65280
-constexpr size_t ST_SMEM = 128 + ST_W_BYTES + 2 * ((ST_IN_BYTES + 127) & ~(size_t)127) + ST_CONV_BYTES;
+constexpr size_t ST_SMEM = 128 + ((ST_IN_BYTES + 127) & ~(size_t)127) + ST_W_BYTES + ST_CONV_BYTES;
 
 struct StemArgs {
     const float* x;           // [n,3,h,w] contiguous
@@ -37,6 +37,13 @@ struct StemArgs {
     uint4* obits;             // [n][1][hp][wp]
     int N, H, W, Hc, Wc, Hp, Wp, tiles_h, tiles_w, stage;
 };
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
 
 __device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
     unsigned long long r;
@@ -52,143 +59,128 @@ __device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigne
     return r;
 }
 
-__device__ __forceinline__ void cp_async_4_zfill(float* dst, const float* src, bool valid) {
-    // 4-byte asynchronous copy global -> shared; src-size 0 zero-fills (the conv's zero padding)
-    const unsigned sz = valid ? 4u : 0u;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__global__ void __launch_bounds__(ST_WARPS * 32, 2)
+stem_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ StemArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+    float* in_s = reinterpret_cast<float*>(smem + 128);
+    float* w_s = reinterpret_cast<float*>(smem + 128 + ((ST_IN_BYTES + 127) & ~(size_t)127));
+    float* conv_s = w_s + ST_CI * ST_K * ST_K * ST_CO;
 
-// stage the 23 x 40 x 3 input window of pooled tile (n, th, tw) into `dst` (asynchronously)
-__device__ __forceinline__ void stem_stage_input(const StemArgs& a, float* dst, int tile) {
-    int t = tile;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int t = blockIdx.x;
     const int tw = t % a.tiles_w; t /= a.tiles_w;
     const int th = t % a.tiles_h;
     const int n = t / a.tiles_h;
-    const int hi0 = 2 * (2 * th * ST_PH - 1) - 3, wi0 = 2 * (2 * tw * ST_PW - 1) - 3;
-    for (int i = threadIdx.x; i < ST_CI * ST_IR * ST_ICP; i += blockDim.x) {
-        const int c = i % ST_ICP, r = (i / ST_ICP) % ST_IR, ci = i / (ST_ICP * ST_IR);
-        const int hi = hi0 + r, wi = wi0 + c;
-        const bool ok = (unsigned)hi < (unsigned)a.H && (unsigned)wi < (unsigned)a.W;
-        const float* src = a.x + (((size_t)n * ST_CI + ci) * a.H + (ok ? hi : 0)) * a.W + (ok ? wi : 0);
-        cp_async_4_zfill(dst + i, src, ok);
-    }
-}
+    const int ph0 = th * ST_PH, pw0 = tw * ST_PW;
+    const int cr0 = 2 * ph0 - 1, cc0 = 2 * pw0 - 1;            // first conv row / col of the tile
+    const int hi0 = 2 * cr0 - 3, wi0 = 2 * cc0 - 3;            // first input row / col
 
-// Persistent: each CTA keeps the weights in shared memory and walks over pooled tiles; the input window of
-// the next tile is copied (cp.async) while the current tile is being convolved.
-__global__ void __launch_bounds__(ST_WARPS * 32, 2)
-stem_kernel(const __grid_constant__ StemArgs a) {
-    extern __shared__ __align__(1024) unsigned char smem[];
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
-    float* w_s = reinterpret_cast<float*>(smem + 128);
-    float* in_s0 = w_s + ST_CI * ST_K * ST_K * ST_CO;
-    constexpr int IN_FLOATS = (int)(((ST_IN_BYTES + 127) & ~(size_t)127) / 4);
-    float* conv_s = in_s0 + 2 * IN_FLOATS;
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int total_tiles = a.N * a.tiles_h * a.tiles_w;
-
-    // weights: one TMA bulk copy per CTA (or plain loads), then the first input window
-    const bool bulk = (a.stage & 2) != 0;
-    if (bulk) {
-        if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+    // staging: bit 0 of `stage` = input window by TMA tensor load, bit 1 = weights by TMA bulk copy
+    const bool tma_in = (a.stage & 1) != 0, tma_w = (a.stage & 2) != 0;
+    if (tma_in || tma_w) {
+        if (threadIdx.x == 0) {
+            if (tma_in) prefetch_tensormap(&tmap);
+            mbar_init(bar, 1);
+            fence_mbar_init();
+        }
         __syncthreads();
         if (threadIdx.x == 0) {
-            mbar_expect_tx(bar, (unsigned)ST_W_BYTES);
-            bulk_load_1d(w_s, a.wt, (unsigned)ST_W_BYTES, bar);
+            mbar_expect_tx(bar, (unsigned)((tma_in ? ST_IN_BYTES : 0) + (tma_w ? ST_W_BYTES : 0)));
+            if (tma_in) tma_load_4d(in_s, &tmap, bar, wi0, hi0, 0, n);
+            if (tma_w) bulk_load_1d(w_s, a.wt, (unsigned)ST_W_BYTES, bar);
         }
-    } else {
+    }
+    if (!tma_in) {
+        for (int i = threadIdx.x; i < ST_CI * ST_IR * ST_ICP; i += blockDim.x) {
+            const int c = i % ST_ICP, r = (i / ST_ICP) % ST_IR, ci = i / (ST_ICP * ST_IR);
+            const int hi = hi0 + r, wi = wi0 + c;
+            float v = 0.0f;
+            if ((unsigned)hi < (unsigned)a.H && (unsigned)wi < (unsigned)a.W)
+                v = __ldg(a.x + (((size_t)n * ST_CI + ci) * a.H + hi) * a.W + wi);
+            in_s[i] = v;
+        }
+    }
+    if (!tma_w) {
         const float4* src = reinterpret_cast<const float4*>(a.wt);
         float4* dst = reinterpret_cast<float4*>(w_s);
         for (int i = threadIdx.x; i < ST_CI * ST_K * ST_K * ST_CO / 4; i += blockDim.x) dst[i] = __ldg(src + i);
     }
-    int tile = blockIdx.x;
-    if (tile < total_tiles) stem_stage_input(a, in_s0, tile);
-    if (bulk) mbar_wait(bar, 0);
+    __syncthreads();
+    if (tma_in || tma_w) mbar_wait(bar, 0);
 
-    const float g0 = __ldg(a.bn_scale + lane), h0 = __ldg(a.bn_shift + lane);
-    const float g1 = __ldg(a.bn_scale + 32 + lane), h1 = __ldg(a.bn_shift + 32 + lane);
-
-    for (int buf = 0; tile < total_tiles; tile += gridDim.x, buf ^= 1) {
-        const float* in_s = in_s0 + buf * IN_FLOATS;
-        cp_async_wait_all();
-        __syncthreads();                 // input window (and, first time, weights) visible; previous pool phase done
-        if (tile + (int)gridDim.x < total_tiles) stem_stage_input(a, in_s0 + (buf ^ 1) * IN_FLOATS, tile + gridDim.x);
-
-        int t = tile;
-        const int tw = t % a.tiles_w; t /= a.tiles_w;
-        const int th = t % a.tiles_h;
-        const int n = t / a.tiles_h;
-        const int ph0 = th * ST_PH, pw0 = tw * ST_PW;
-        const int cr0 = 2 * ph0 - 1, cc0 = 2 * pw0 - 1;        // first conv row / col of the tile
-
-        // ---------------- conv + BN + ReLU into the shared conv tile ----------------
-        for (int r = warp; r < ST_CR; r += ST_WARPS) {
-            // packed accumulators: (lo, hi) = (channel lane, channel lane + 32) of conv pixel c.  One FFMA2
-            // (fma.rn.f32x2: input broadcast to both halves, weight pair from one LDS.64) does both channels --
-            // the loop is issue-bound, so halving the FMA instruction count is what matters.  Each half is an
-            // ordinary IEEE fma, so the result is bit-identical to the scalar chain the oracle restates.
-            unsigned long long acc[ST_CC];
+    // ---------------- conv + BN + ReLU into the shared conv tile ----------------
+    // one warp = one conv row of the tile, both 32-channel blocks: the broadcast input row feeds 2 x 17 fma chains
+    for (int r = warp; r < ST_CR; r += ST_WARPS) {
+        // packed accumulators: (lo, hi) = (channel lane, channel lane + 32) of conv pixel c.  One FFMA2
+        // (fma.rn.f32x2: input broadcast to both halves, weight pair from one LDS.64) does both channels --
+        // the loop is issue-bound, so halving the FMA instruction count is what matters.  Each half is an
+        // ordinary IEEE fma, so the result is bit-identical to the scalar chain the oracle restates.
+        unsigned long long acc[ST_CC];
 #pragma unroll
-            for (int c = 0; c < ST_CC; ++c) acc[c] = 0ull;
-            for (int ci = 0; ci < ST_CI; ++ci) {
+        for (int c = 0; c < ST_CC; ++c) acc[c] = 0ull;
+        for (int ci = 0; ci < ST_CI; ++ci) {
 #pragma unroll 1
-                for (int kh = 0; kh < ST_K; ++kh) {
-                    const float4* irow = reinterpret_cast<const float4*>(in_s + (ci * ST_IR + 2 * r + kh) * ST_ICP);
-                    float iv[ST_ICP];
+            for (int kh = 0; kh < ST_K; ++kh) {
+                const float4* irow = reinterpret_cast<const float4*>(in_s + (ci * ST_IR + 2 * r + kh) * ST_ICP);
+                float iv[ST_ICP];
 #pragma unroll
-                    for (int q = 0; q < ST_ICP / 4; ++q) {
-                        const float4 v = irow[q];              // warp-uniform address: broadcast
-                        iv[4 * q] = v.x; iv[4 * q + 1] = v.y; iv[4 * q + 2] = v.z; iv[4 * q + 3] = v.w;
-                    }
-                    const float2* wrow = reinterpret_cast<const float2*>(w_s) + ((ci * ST_K + kh) * ST_K) * 32 + lane;
+                for (int q = 0; q < ST_ICP / 4; ++q) {
+                    const float4 v = irow[q];              // warp-uniform address: broadcast
+                    iv[4 * q] = v.x; iv[4 * q + 1] = v.y; iv[4 * q + 2] = v.z; iv[4 * q + 3] = v.w;
+                }
+                const float2* wrow = reinterpret_cast<const float2*>(w_s) + ((ci * ST_K + kh) * ST_K) * 32 + lane;
 #pragma unroll
-                    for (int kw = 0; kw < ST_K; ++kw) {
-                        const float2 w2 = wrow[kw * 32];
-                        const unsigned long long ww = pack2(w2.x, w2.y);
+                for (int kw = 0; kw < ST_K; ++kw) {
+                    const float2 w2 = wrow[kw * 32];
+                    const unsigned long long ww = pack2(w2.x, w2.y);
 #pragma unroll
-                        for (int c = 0; c < ST_CC; ++c) acc[c] = fma2(pack2(iv[2 * c + kw], iv[2 * c + kw]), ww, acc[c]);
-                    }
+                    for (int c = 0; c < ST_CC; ++c) acc[c] = fma2(pack2(iv[2 * c + kw], iv[2 * c + kw]), ww, acc[c]);
                 }
             }
-            const bool row_ok = (unsigned)(cr0 + r) < (unsigned)a.Hc;
-#pragma unroll
-            for (int c = 0; c < ST_CC; ++c) {
-                const bool ok = row_ok && (unsigned)(cc0 + c) < (unsigned)a.Wc;
-                float lo, hi;
-                unpack2(acc[c], lo, hi);
-                // positions outside the conv output are max-pool padding: 0 is neutral after the ReLU
-                conv_s[(r * ST_CC + c) * ST_CO + lane] = ok ? fmaxf(__fmaf_rn(lo, g0, h0), 0.0f) : 0.0f;
-                conv_s[(r * ST_CC + c) * ST_CO + 32 + lane] = ok ? fmaxf(__fmaf_rn(hi, g1, h1), 0.0f) : 0.0f;
-            }
         }
-        __syncthreads();
-
-        // ---------------- 3x3 / stride 2 max, NHWC store, planes for the first binarized conv ----------------
-        for (int task = warp; task < ST_PH * ST_PW; task += ST_WARPS) {
-            const int pr = task / ST_PW, pc = task - pr * ST_PW;
-            const int ph = ph0 + pr, pw = pw0 + pc;
-            if (ph >= a.Hp || pw >= a.Wp) continue;              // warp-uniform
-            uint32_t sw[2], mw[2];
+        const float g0 = __ldg(a.bn_scale + lane), h0 = __ldg(a.bn_shift + lane);
+        const float g1 = __ldg(a.bn_scale + 32 + lane), h1 = __ldg(a.bn_shift + 32 + lane);
+        const bool row_ok = (unsigned)(cr0 + r) < (unsigned)a.Hc;
 #pragma unroll
-            for (int cb = 0; cb < 2; ++cb) {
-                const int ch = cb * 32 + lane;
-                float m = 0.0f;
-#pragma unroll
-                for (int i = 0; i < 3; ++i)
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) m = fmaxf(m, conv_s[((2 * pr + i) * ST_CC + 2 * pc + j) * ST_CO + ch]);
-                a.out[(((size_t)n * a.Hp + ph) * a.Wp + pw) * ST_CO + ch] = m;
-                const float b = a.nx_scale ? __fmaf_rn(__ldg(a.nx_scale + ch), m, __ldg(a.nx_shift + ch)) : m;
-                sw[cb] = __ballot_sync(0xffffffffu, b > 0.0f);
-                mw[cb] = __ballot_sync(0xffffffffu, b > 0.0f || b < 0.0f);
-            }
-            if (lane == 0 && a.obits) a.obits[((size_t)n * a.Hp + ph) * a.Wp + pw] = make_uint4(sw[0], sw[1], mw[0], mw[1]);
+        for (int c = 0; c < ST_CC; ++c) {
+            const bool ok = row_ok && (unsigned)(cc0 + c) < (unsigned)a.Wc;
+            float lo, hi;
+            unpack2(acc[c], lo, hi);
+            // positions outside the conv output are max-pool padding: 0 is neutral after the ReLU
+            conv_s[(r * ST_CC + c) * ST_CO + lane] = ok ? fmaxf(__fmaf_rn(lo, g0, h0), 0.0f) : 0.0f;
+            conv_s[(r * ST_CC + c) * ST_CO + 32 + lane] = ok ? fmaxf(__fmaf_rn(hi, g1, h1), 0.0f) : 0.0f;
         }
     }
-    cp_async_wait_all();
+    __syncthreads();
+
+    // ---------------- 3x3 / stride 2 max, NHWC store, planes for the first binarized conv ----------------
+    for (int task = warp; task < ST_PH * ST_PW; task += ST_WARPS) {
+        const int pr = task / ST_PW, pc = task - pr * ST_PW;
+        const int ph = ph0 + pr, pw = pw0 + pc;
+        if (ph >= a.Hp || pw >= a.Wp) continue;              // warp-uniform
+        uint32_t sw[2], mw[2];
+#pragma unroll
+        for (int cb = 0; cb < 2; ++cb) {
+            const int ch = cb * 32 + lane;
+            float m = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) m = fmaxf(m, conv_s[((2 * pr + i) * ST_CC + 2 * pc + j) * ST_CO + ch]);
+            a.out[(((size_t)n * a.Hp + ph) * a.Wp + pw) * ST_CO + ch] = m;
+            const float b = a.nx_scale ? __fmaf_rn(__ldg(a.nx_scale + ch), m, __ldg(a.nx_shift + ch)) : m;
+            sw[cb] = __ballot_sync(0xffffffffu, b > 0.0f);
+            mw[cb] = __ballot_sync(0xffffffffu, b > 0.0f || b < 0.0f);
+        }
+        if (lane == 0 && a.obits) a.obits[((size_t)n * a.Hp + ph) * a.Wp + pw] = make_uint4(sw[0], sw[1], mw[0], mw[1]);
+    }
 }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn();      // bconv.cu
 
 }  // namespace bnn
 
@@ -217,17 +209,31 @@ extern "C" int bnn_stem_fwd(const float* x, int32_t n, int32_t h, int32_t w, con
     a.Hc = (h + 6 - 7) / 2 + 1; a.Wc = (w + 6 - 7) / 2 + 1;
     a.Hp = (a.Hc + 2 - 3) / 2 + 1; a.Wp = (a.Wc + 2 - 3) / 2 + 1;
     a.tiles_h = (a.Hp + ST_PH - 1) / ST_PH; a.tiles_w = (a.Wp + ST_PW - 1) / ST_PW;
-    // weights by one TMA bulk copy per (persistent) CTA unless plain loads are requested
-    a.stage = (flags & (BNN_F_STAGE_LDG | BNN_F_STEM_NO_BULK)) ? 0 : 2;
+    // staging mode: weights by TMA bulk copy; the input window by TMA only on request (BNN_F_STEM_TMA_IN) and
+    // only when rows are 16-byte aligned -- plain coalesced loads otherwise
+    a.stage = (flags & BNN_F_STAGE_LDG) ? 0 : 2;
+    if ((flags & BNN_F_STEM_TMA_IN) && (w % 4) == 0 && ((uintptr_t)x & 15) == 0) a.stage |= 1;
+    if (flags & BNN_F_STEM_NO_BULK) a.stage &= ~2;
+
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    if (a.stage & 1) {
+        EncodeTiledFn enc = encode_tiled_fn();
+        if (!enc) return BNN_E_DRIVER;
+        const cuuint64_t gdim[4] = {(cuuint64_t)w, (cuuint64_t)h, 3, (cuuint64_t)n};
+        const cuuint64_t gstr[3] = {(cuuint64_t)w * 4, (cuuint64_t)w * h * 4, (cuuint64_t)w * h * 3 * 4};
+        const cuuint32_t box[4] = {ST_ICP, ST_IR, ST_CI, 1};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return BNN_E_DRIVER;
+    }
     cudaError_t ce = cudaFuncSetAttribute((const void*)stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM);
     if (ce != cudaSuccess) return (int)ce;
-    const long long tiles = (long long)n * a.tiles_h * a.tiles_w;
-    if (tiles > 0x7fffffffLL) return BNN_E_UNSUPPORTED;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long long ctas = tiles < 2LL * sms ? tiles : 2LL * sms;      // persistent: two CTAs per SM
-    stem_kernel<<<(unsigned)ctas, ST_WARPS * 32, ST_SMEM, (cudaStream_t)stream_>>>(a);
+    const long long ctas = (long long)n * a.tiles_h * a.tiles_w;
+    if (ctas > 0x7fffffffLL) return BNN_E_UNSUPPORTED;
+    stem_kernel<<<(unsigned)ctas, ST_WARPS * 32, ST_SMEM, (cudaStream_t)stream_>>>(tmap, a);
     count_launch(1);
     return (int)cudaGetLastError();
 }

@@ -66,6 +66,7 @@ typedef struct bnn_conv_geom {
 /* flags for bnn_bconv2d_fwd / bnn_blinear_fwd */
 #define BNN_F_STAGE_LDG   1u    /* stage tiles with plain loads instead of TMA (debug / A-B) */
 #define BNN_F_NO_CSA      2u    /* force the one-POPC-per-word inner loop                     */
+#define BNN_F_STEM_TMA_IN 4u    /* bnn_stem_fwd: stage the input window with a 4-D TMA tensor load (experimental) */
 #define BNN_F_STEM_NO_BULK 8u   /* bnn_stem_fwd: stage the weights with plain loads instead of a TMA bulk copy   */
 
 int         bnn_query(int what, int64_t *value);
