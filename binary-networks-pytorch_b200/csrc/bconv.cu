@@ -24,8 +24,11 @@
 //     (2 more LOP3) so that 3 words cost 2 POPC -- POPC is the slow pipe.
 #include "common.cuh"
 
+#include <algorithm>
 #include <cudaTypedefs.h>
+#include <map>
 #include <mutex>
+#include <vector>
 
 namespace bnn {
 
@@ -495,11 +498,15 @@ static size_t plan_smem(int nch, int BH, int BW, int C, int nk, int NW, int P, i
            (size_t)EP_N * 32 * C * 4 + (size_t)TH * TW * 4;
 }
 
-// Choose the tile shape for one layer by minimising a small cost model (host only, microseconds):
-//   time ~ waves x (rounds x work_per_round + staging), waves = ceil(CTAs / (SMs x CTAs_per_SM)).
-// It captures the three measured loss terms: idle lanes of partial pixel groups / idle warps in the last
-// round, the tail of the last wave, and the staging latency of very small CTAs.
-static int make_plan(const bnn_conv_geom& g, int Ho, int Wo, uint32_t flags, int sms, Plan* out) {
+// Candidate tile shapes for one layer, ranked by a small cost model (host only, microseconds):
+//   time ~ waves x (rounds x work_per_round x warps_on_fullest_scheduler + staging),
+//   waves = ceil(CTAs / (SMs x CTAs_per_SM)).
+// It captures the measured loss terms: idle lanes of partial pixel groups / idle warps in the last round,
+// the tail of the last wave, uneven warps per scheduler, and the staging latency of very small CTAs.
+// The model only ranks; bnn_conv_tune times the best few on the device and caches the winner.
+struct Cand { Plan pl; double cost; };
+
+static int enumerate_plans(const bnn_conv_geom& g, int Ho, int Wo, uint32_t flags, int sms, std::vector<Cand>& out) {
     const int nch = ceil_div(g.c_in, 64), nk = nch * g.kh * g.kw;
     if (nch > 256) return BNN_E_UNSUPPORTED;
     int kwt = 0, swt = 0;            // unrolled instances: kernel width x horizontal stride, dilation_w == 1
@@ -510,9 +517,6 @@ static int make_plan(const bnn_conv_geom& g, int Ho, int Wo, uint32_t flags, int
     const int mode = (kwt == 3 && !(flags & BNN_F_NO_CSA)) ? 1 : 0;
     const int nblk32 = ceil_div(g.c_out, 32);
     const size_t smem_cap = 220 * 1024;
-
-    double best = 1e300;
-    Plan bp{};
     const int candP[3] = {8, 7, 4}, candC[3] = {4, 2, 1};
     for (int ci = 0; ci < 3; ++ci) {
         const int C = candC[ci];
@@ -544,27 +548,54 @@ static int make_plan(const bnn_conv_geom& g, int Ho, int Wo, uint32_t flags, int
                     const long long ctas = (long long)g.n * ceil_div(Ho, TH) * tiles_w * cout_tiles;
                     const long long slots = (long long)sms * occ;
                     const double waves = (double)((ctas + slots - 1) / slots);
-                    // warps of co-resident CTAs share the SM's issue slots: 8*occ warps over 4 schedulers
-                    const double share = (double)(NW * occ) / 4.0;
+                    const double share = (double)((NW * occ + 3) / 4);       // warps on the fullest scheduler
                     const double stage = 1500.0 + 0.02 * (double)(smem);
-                    const double t = waves * (rounds * round_work * share + stage);
-                    if (t < best) {
-                        best = t;
-                        bp.P = P; bp.C = C; bp.kwt = kwt; bp.swt = swt; bp.mode = mode;
-                        bp.TH = TH; bp.TW = TW; bp.BH = BH; bp.BW = BW; bp.NW = NW; bp.gpr = gpr; bp.G = G;
-                        bp.tiles_h = ceil_div(Ho, TH); bp.tiles_w = tiles_w; bp.smem = smem;
-                    }
+                    Cand c{};
+                    c.cost = waves * (rounds * round_work * share + stage);
+                    c.pl.P = P; c.pl.C = C; c.pl.kwt = kwt; c.pl.swt = swt; c.pl.mode = mode;
+                    c.pl.TH = TH; c.pl.TW = TW; c.pl.BH = BH; c.pl.BW = BW; c.pl.NW = NW; c.pl.gpr = gpr; c.pl.G = G;
+                    c.pl.tiles_h = ceil_div(Ho, TH); c.pl.tiles_w = tiles_w; c.pl.smem = smem;
+                    out.push_back(c);
                 }
             }
         }
     }
-    if (best >= 1e300) return BNN_E_UNSUPPORTED;
-    *out = bp;
+    if (out.empty()) return BNN_E_UNSUPPORTED;
+    std::sort(out.begin(), out.end(), [](const Cand& a, const Cand& b) { return a.cost < b.cost; });
+    return 0;
+}
+
+// tuned plans, keyed by geometry + epilogue kind + flags that change the kernel
+struct PlanKey {
+    int v[16];
+    bool operator<(const PlanKey& o) const { return memcmp(v, o.v, sizeof(v)) < 0; }
+};
+static std::map<PlanKey, Plan> g_tuned;
+static std::mutex g_tuned_mu;
+
+static PlanKey plan_key(const bnn_conv_geom& g, int epi, uint32_t flags) {
+    PlanKey k{};
+    const int vals[16] = {g.n, g.c_in, g.h, g.w, g.c_out, g.kh, g.kw, g.stride_h, g.stride_w, g.pad_h, g.pad_w,
+                          g.dil_h, g.dil_w, epi, (int)(flags & BNN_F_NO_CSA), 0};
+    memcpy(k.v, vals, sizeof(vals));
+    return k;
+}
+
+static int make_plan(const bnn_conv_geom& g, int Ho, int Wo, uint32_t flags, int sms, Plan* out, int epi = 0) {
+    {
+        std::lock_guard<std::mutex> lock(g_tuned_mu);
+        auto it = g_tuned.find(plan_key(g, epi, flags));
+        if (it != g_tuned.end()) { *out = it->second; return 0; }
+    }
+    std::vector<Cand> cands;
+    int rc = enumerate_plans(g, Ho, Wo, flags, sms, cands);
+    if (rc) return rc;
+    *out = cands[0].pl;
     return 0;
 }
 
 static int launch_bconv(const void* abits, const void* wbits, const bnn_conv_geom& g, const bnn_epilogue& ep,
-                        uint32_t flags, cudaStream_t stream) {
+                        uint32_t flags, cudaStream_t stream, const Plan* forced = nullptr) {
     if (!abits || !wbits || (!ep.out && !ep.out_bits)) return BNN_E_NULL;
     if (g.n <= 0 || g.c_in <= 0 || g.h <= 0 || g.w <= 0 || g.c_out <= 0 || g.kh <= 0 || g.kw <= 0 ||
         g.stride_h <= 0 || g.stride_w <= 0 || g.pad_h < 0 || g.pad_w < 0 || g.dil_h <= 0 || g.dil_w <= 0)
@@ -596,7 +627,9 @@ static int launch_bconv(const void* abits, const void* wbits, const bnn_conv_geo
     }
     if (epi) flags &= ~BNN_F_NO_CSA;
     Plan pl;
-    int rc = make_plan(g, Ho, Wo, flags, sms, &pl);
+    int rc = 0;
+    if (forced) pl = *forced;
+    else rc = make_plan(g, Ho, Wo, flags, sms, &pl, epi);
     if (rc) return rc;
     KernelFn fn = pick_kernel(pl, epi);
     if (!fn) return BNN_E_UNSUPPORTED;
@@ -653,6 +686,63 @@ static int launch_bconv(const void* abits, const void* wbits, const bnn_conv_geo
 }  // namespace bnn
 
 using namespace bnn;
+
+extern "C" int bnn_bconv2d_tune(const void* abits, const void* wbits, const bnn_conv_geom* geom,
+                                const bnn_epilogue* epilogue, uint32_t flags, int32_t top_k, void* stream_) {
+    if (!geom || !epilogue) return BNN_E_NULL;
+    const bnn_conv_geom& g = *geom;
+    const bnn_epilogue& ep = *epilogue;
+    const int Ho = out_dim(g.h, g.kh, g.stride_h, g.pad_h, g.dil_h);
+    const int Wo = out_dim(g.w, g.kw, g.stride_w, g.pad_w, g.dil_w);
+    if (Ho <= 0 || Wo <= 0) return BNN_E_SHAPE;
+    const int epi = (ep.bn_scale || ep.residual || ep.act != BNN_ACT_NONE || ep.out_bits || ep.nx_scale) ? 1 : 0;
+    if (epi) flags &= ~BNN_F_NO_CSA;
+    const PlanKey key = plan_key(g, epi, flags);
+    {
+        std::lock_guard<std::mutex> lock(g_tuned_mu);
+        if (g_tuned.count(key)) return 0;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    std::vector<Cand> cands;
+    int rc = enumerate_plans(g, Ho, Wo, flags, sms, cands);
+    if (rc) return rc;
+    // keep the model's best few, but make sure different (P, C, warps) families are represented
+    std::vector<Plan> tries;
+    for (const Cand& c : cands) {
+        int same = 0;
+        for (const Plan& t : tries) same += (t.P == c.pl.P && t.C == c.pl.C && t.NW == c.pl.NW);
+        if (same < 2) tries.push_back(c.pl);
+        if ((int)tries.size() >= (top_k > 0 ? top_k : 8)) break;
+    }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    Plan best_pl = tries[0];
+    for (const Plan& pl : tries) {
+        rc = launch_bconv(abits, wbits, g, ep, flags, stream, &pl);            // warm-up
+        if (rc) continue;
+        float ms_min = 1e30f;
+        for (int rep = 0; rep < 3; ++rep) {
+            cudaEventRecord(e0, stream);
+            launch_bconv(abits, wbits, g, ep, flags, stream, &pl);
+            cudaEventRecord(e1, stream);
+            if (cudaEventSynchronize(e1) != cudaSuccess) { ms_min = 1e30f; break; }
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            ms_min = ms < ms_min ? ms : ms_min;
+        }
+        if (ms_min < best) { best = ms_min; best_pl = pl; }
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) return (int)ce;
+    std::lock_guard<std::mutex> lock(g_tuned_mu);
+    g_tuned[key] = best_pl;
+    return 0;
+}
 
 extern "C" int bnn_conv_plan(const bnn_conv_geom* g, uint32_t flags, int32_t sms, int32_t* plan) {
     if (!g || !plan) return BNN_E_NULL;

@@ -107,6 +107,22 @@ def _opt_ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+_tuned = set()
+
+
+def _maybe_tune(act, wts, geom, ep, flags, dev) -> None:
+    """First (non-captured) launch of a geometry: let the library time its candidate tile plans."""
+    from . import runtime
+    key = (tuple(getattr(geom, f) for f, _ in ConvGeom._fields_), bool(ep.bn_scale or ep.residual or ep.act or ep.out_bits
+                                                                      or ep.nx_scale), flags & native.F_NO_CSA, dev.index)
+    if key in _tuned or not runtime.autotune() or torch.cuda.is_current_stream_capturing():
+        return
+    rc = native.lib().bnn_bconv2d_tune(act.bits.data_ptr(), wts.bits.data_ptr(), ctypes.byref(geom), ctypes.byref(ep),
+                                       flags, 8, _stream_ptr(dev))
+    native.check(rc, "bnn_bconv2d_tune")
+    _tuned.add(key)
+
+
 def _out_hw(act, wts, stride, padding, dilation):
     ho = (act.h + 2 * padding[0] - dilation[0] * (wts.kh - 1) - 1) // stride[0] + 1
     wo = (act.w + 2 * padding[1] - dilation[1] * (wts.kw - 1) - 1) // stride[1] + 1
@@ -130,6 +146,11 @@ def bconv2d(act: PackedActivations, wts: PackedWeights, bias: Optional[torch.Ten
         if out is None:
             out = torch.empty((act.n, wts.c_out, ho, wo), dtype=torch.float32, device=dev)
         on, oc, oh, ow = out.stride()
+        ep = native.Epilogue()
+        ep.scale = wts.alpha.data_ptr() if use_alpha else None
+        ep.bias, ep.post, ep.out = _opt_ptr(bias), _opt_ptr(post), out.data_ptr()
+        ep.ostride_n, ep.ostride_c, ep.ostride_h, ep.ostride_w = on, oc, oh, ow
+        _maybe_tune(act, wts, geom, ep, flags, dev)
         rc = native.lib().bnn_bconv2d_fwd(act.bits.data_ptr(), wts.bits.data_ptr(),
                                           wts.alpha.data_ptr() if use_alpha else None, _opt_ptr(bias),
                                           _opt_ptr(post), out.data_ptr(), on, oc, oh, ow, ctypes.byref(geom),
@@ -177,6 +198,7 @@ def bconv2d_fused(act: PackedActivations, wts: PackedWeights, *, bias=None, post
         if want_bits:
             bits = torch.empty((act.n, (wts.c_out + 63) // 64, ho, wo, 4), dtype=torch.int32, device=dev)
             ep.out_bits = bits.data_ptr()
+        _maybe_tune(act, wts, geom, ep, flags, dev)
         rc = native.lib().bnn_bconv2d_fused_fwd(act.bits.data_ptr(), wts.bits.data_ptr(), ctypes.byref(geom),
                                                 ctypes.byref(ep), flags, _stream_ptr(dev))
     native.check(rc, "bnn_bconv2d_fused_fwd")

@@ -34,3 +34,11 @@ def kernel_flags(value: int = None) -> int:
     if value is not None:
         _state.flags = int(value)
     return getattr(_state, "flags", 0)
+
+
+def autotune(enabled: bool = None) -> bool:
+    """Get / set tile-plan autotuning (default on): the first launch of each conv geometry outside a
+    CUDA-graph capture times the cost model's best few plans on the device and caches the winner."""
+    if enabled is not None:
+        _state.autotune = bool(enabled)
+    return getattr(_state, "autotune", True)

@@ -161,6 +161,16 @@ int bnn_bconv2d_fused_fwd(const void *abits, const void *wbits, const bnn_conv_g
                           const bnn_epilogue *epilogue, uint32_t flags, void *stream);
 
 /*
+ * Autotune: time the cost model's best `top_k` tile plans for this geometry / epilogue kind with real
+ * launches on the caller's buffers (same arguments as bnn_bconv2d_fused_fwd; results are the same for
+ * every plan, so the buffers end up holding the correct output), and remember the fastest in a
+ * process-wide cache that later launches of the same geometry use.  Synchronises `stream`; call it at
+ * warm-up, never inside a CUDA-graph capture.  A geometry that is already tuned returns immediately.
+ */
+int bnn_bconv2d_tune(const void *abits, const void *wbits, const bnn_conv_geom *geom,
+                     const bnn_epilogue *epilogue, uint32_t flags, int32_t top_k, void *stream);
+
+/*
  * Introspection: the tile plan the library would use for a geometry (host only, no GPU needed).
  * plan[12] = {P pixels/group, C 32-channel blocks/lane, kw instance, stride instance, carry-save mode,
  *             TH, TW, warps per CTA, pixel units (grid.x), channel tiles (grid.y), smem bytes, groups/unit}.
