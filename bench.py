@@ -452,8 +452,8 @@ def main():
                    "l2": f"input batch {B * 3 * RES * RES * 4 / 1e6:.0f} MB + activations exceed the 126 MB L2",
                    "launch": "cuda_graph" if graph is not None else "eager",
                    "fusion": "per-layer" if args.no_fuse else "bnn_b200.fuse.optimize (BN/act/residual/sign in conv epilogues)",
-                   "glue": "torch fp32 (TF32 off): stem conv7x7+BN+ReLU+maxpool, avgpool, fc"
-                           + (", BN/act/add per layer" if args.no_fuse else "")},
+                   "glue": ("torch fp32 (TF32 off): stem conv7x7+BN+ReLU+maxpool, BN/act/add per layer, avgpool, fc"
+                            if args.no_fuse else "stem = bnn_stem_fwd; torch fp32 only for global avgpool + fc")},
         "clocks": clocks,
         "e2e": {"value": images / (ms_e2e / args.steps * 1e-3), "unit": "images/s",
                 "h2d_bytes_per_step": B * 3 * RES * RES * 4 * world, "d2h_bytes_per_step": images * 1000 * 4 * world,

@@ -122,3 +122,37 @@ def test_forward_is_cuda_graph_capturable():
         g.replay()
         torch.cuda.synchronize()
     assert torch.equal(out, eager)
+
+
+def test_baseline_config3_resnet50_xnor_plus_plus():
+    """BASELINE configs[2]: ResNet-50 (fc patched to 2048), XNOR-Net++ recipe = learned BasicScaleBinarizer
+    (examples/recepies/xnor-net-plus.yaml:13-25), 52 binarized convs, vs the oracle's float-simulated twin."""
+    torch.manual_seed(0)
+    m = workloads.resnet50()
+    m = bnn.prepare_binary_model(m, xnor_cfg(BasicScaleBinarizer), ignore_layers_name=["_first_", "_last_"])
+    assert sum(isinstance(x, bnn.layers.Conv2d) for x in m.modules()) == 52
+    workloads.randomize_batchnorm(m, seed=1)
+    m.eval()
+    twin = fs.mirror_model(m)
+    x = torch.randn(2, 3, 96, 96, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        want = twin(x).numpy()
+        got = m.to(DEV)(x.to(DEV)).cpu().numpy()
+    assert rel_err(got, want) <= 1e-3, rel_err(got, want)
+
+
+def test_baseline_config4_hierarchical_block_net():
+    """BASELINE configs[3]: Hierarchical-Block harness, ReLU-fed => {0,+1} activations, 16
+    binarized 3x3/1x1 convs incl. 128->64 and 64->64 (C=2 / C=1 channel tiles), vs the float-simulated twin."""
+    torch.manual_seed(0)
+    m = workloads.HBlockNet(depth=2)
+    m = bnn.prepare_binary_model(m, xnor_cfg(), ignore_layers_name=["_first_", "_last_"])
+    workloads.randomize_batchnorm(m, seed=1)
+    m.eval()
+    assert sum(isinstance(x, bnn.layers.Conv2d) for x in m.modules()) == 10
+    twin = fs.mirror_model(m)
+    x = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(4))
+    with torch.no_grad():
+        want = twin(x).numpy()
+        got = m.to(DEV)(x.to(DEV)).cpu().numpy()
+    assert rel_err(got, want) <= 1e-3, rel_err(got, want)

@@ -221,3 +221,27 @@ def test_plugs_into_the_reference_prepare_binary_model():
     refmodel = ref.prepare_binary_model(small_net(), rcfg)
     model2 = ref.prepare_binary_model(refmodel, rcfg, modules_mapping=mapping)
     assert type(model2[0]) is Conv2d and type(model2[8]) is Linear
+
+
+def test_binary_chef_runs_staged_recipes():
+    """reference test/test_engine.py:39-66 re-stated: step count, per-step types, learned scales unchanged
+    (fresh ones, like upstream) across re-conversion."""
+    from bnn_b200.engine import BinaryChef
+    from conftest import ROOT
+    chef = BinaryChef(os.path.join(ROOT, "tests", "assets", "recipe.yaml"))
+    assert len(chef) == chef.get_num_steps() == 3
+    model = small_net()
+    model = chef.next(model)
+    assert type(model[0]) is nn.Conv2d and hasattr(model[3], "bconfig")
+    assert isinstance(model[3].weight_pre_process, nn.Identity)
+    model = chef.next(model)
+    assert isinstance(model[3].weight_pre_process, XNORWeightBinarizer) and model[3].weight_pre_process.center_weights
+    alpha = model[3].activation_post_process.alpha
+    model = chef.next(model)
+    assert isinstance(model[0], Conv2d) and isinstance(model[8], Linear)         # nothing ignored in the last stage
+    assert isinstance(model[3].activation_pre_process, AdvancedInputBinarizer) and model[3].activation_pre_process.t == 3
+    assert model[3].activation_pre_process.derivative_funct is torch.tanh
+    assert not model[3].weight_pre_process.center_weights
+    assert torch.equal(alpha, torch.ones_like(alpha))
+    with pytest.raises(AssertionError):
+        chef.next(model)
