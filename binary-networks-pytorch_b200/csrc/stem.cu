@@ -23,7 +23,7 @@ constexpr int ST_CR = 2 * ST_PH + 1, ST_CC = 2 * ST_PW + 1;   // conv tile 9 x 1
 constexpr int ST_IR = 2 * ST_CR + 5, ST_IC = 2 * ST_CC + 5;   // input tile 23 x 39
 constexpr int ST_ICP = 40;                                // input row pitch (floats), 160 B
 constexpr int ST_CO = 64, ST_CI = 3, ST_K = 7;
-constexpr int ST_WARPS = 9;
+constexpr int ST_WARPS = 8;                                // = ST_CR - 1, see the conv phase
 constexpr size_t ST_IN_BYTES = (size_t)ST_CI * ST_IR * ST_ICP * 4;            // 16800
 constexpr size_t ST_W_BYTES = (size_t)ST_CI * ST_K * ST_K * ST_CO * 4;        // 37632
 constexpr size_t ST_CONV_BYTES = (size_t)ST_CR * ST_CC * ST_CO * 4;          // 65280
@@ -111,14 +111,20 @@ stem_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ St
 
     // ---------------- conv + BN + ReLU into the shared conv tile ----------------
     // one warp = one conv row of the tile, both 32-channel blocks: the broadcast input row feeds 2 x 17 fma chains
-    for (int r = warp; r < ST_CR; r += ST_WARPS) {
+    // 8 warps: warp w owns conv row w of the tile; the ninth row is shared out, three pixels per warp
+    // ({2w, 2w+1, 2w+2}: neighbours overlap by one pixel and write the same value) so that every warp -- and
+    // therefore every scheduler of the SM -- carries the same 20 fma chains.
+    {
+        const int r = warp;                      // ST_WARPS == ST_CR - 1
+        const int e0 = 2 * warp;                 // first pixel of this warp's share of row ST_CR - 1
         // packed accumulators: (lo, hi) = (channel lane, channel lane + 32) of conv pixel c.  One FFMA2
         // (fma.rn.f32x2: input broadcast to both halves, weight pair from one LDS.64) does both channels --
         // the loop is issue-bound, so halving the FMA instruction count is what matters.  Each half is an
         // ordinary IEEE fma, so the result is bit-identical to the scalar chain the oracle restates.
-        unsigned long long acc[ST_CC];
+        unsigned long long acc[ST_CC], acx[3];
 #pragma unroll
         for (int c = 0; c < ST_CC; ++c) acc[c] = 0ull;
+        acx[0] = acx[1] = acx[2] = 0ull;
         for (int ci = 0; ci < ST_CI; ++ci) {
 #pragma unroll 1
             for (int kh = 0; kh < ST_K; ++kh) {
@@ -129,6 +135,14 @@ stem_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ St
                     const float4 v = irow[q];              // warp-uniform address: broadcast
                     iv[4 * q] = v.x; iv[4 * q + 1] = v.y; iv[4 * q + 2] = v.z; iv[4 * q + 3] = v.w;
                 }
+                // last conv row, pixels e0..e0+2: input columns 2*e0 .. 2*e0+10 (16-byte aligned start)
+                const float4* xrow = reinterpret_cast<const float4*>(in_s + (ci * ST_IR + 2 * (ST_CR - 1) + kh) * ST_ICP + 2 * e0);
+                float xv[12];
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const float4 v = xrow[q];
+                    xv[4 * q] = v.x; xv[4 * q + 1] = v.y; xv[4 * q + 2] = v.z; xv[4 * q + 3] = v.w;
+                }
                 const float2* wrow = reinterpret_cast<const float2*>(w_s) + ((ci * ST_K + kh) * ST_K) * 32 + lane;
 #pragma unroll
                 for (int kw = 0; kw < ST_K; ++kw) {
@@ -136,6 +150,8 @@ stem_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ St
                     const unsigned long long ww = pack2(w2.x, w2.y);
 #pragma unroll
                     for (int c = 0; c < ST_CC; ++c) acc[c] = fma2(pack2(iv[2 * c + kw], iv[2 * c + kw]), ww, acc[c]);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) acx[c] = fma2(pack2(xv[2 * c + kw], xv[2 * c + kw]), ww, acx[c]);
                 }
             }
         }
@@ -150,6 +166,16 @@ stem_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ St
             // positions outside the conv output are max-pool padding: 0 is neutral after the ReLU
             conv_s[(r * ST_CC + c) * ST_CO + lane] = ok ? fmaxf(__fmaf_rn(lo, g0, h0), 0.0f) : 0.0f;
             conv_s[(r * ST_CC + c) * ST_CO + 32 + lane] = ok ? fmaxf(__fmaf_rn(hi, g1, h1), 0.0f) : 0.0f;
+        }
+        const bool last_ok = (unsigned)(cr0 + ST_CR - 1) < (unsigned)a.Hc;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int cc = e0 + c;
+            const bool ok = last_ok && (unsigned)(cc0 + cc) < (unsigned)a.Wc;
+            float lo, hi;
+            unpack2(acx[c], lo, hi);
+            conv_s[((ST_CR - 1) * ST_CC + cc) * ST_CO + lane] = ok ? fmaxf(__fmaf_rn(lo, g0, h0), 0.0f) : 0.0f;
+            conv_s[((ST_CR - 1) * ST_CC + cc) * ST_CO + 32 + lane] = ok ? fmaxf(__fmaf_rn(hi, g1, h1), 0.0f) : 0.0f;
         }
     }
     __syncthreads();
