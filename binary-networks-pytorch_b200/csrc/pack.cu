@@ -100,27 +100,40 @@ pack_act_cl_kernel(const float* __restrict__ x, long long sn, long long sh, long
     const int k = pool > 1 ? pool : 1;
     const float* base = x + n * sn + (long long)h * k * sh + (long long)w * k * sw;
     const int hmax = min(k, Hin - h * k), wmax = min(k, Win - w * k);
-    const float inv_cnt_den = (float)(hmax * wmax);
-    for (int blk = 0; blk < 2 * nch; ++blk) {
-        const int c = blk * 32 + lane;
-        float v = 0.0f;
-        if (c < C) {
-            if (k == 1) v = __ldg(base + c);
-            else {
-                float sum = 0.0f;
-                for (int i = 0; i < hmax; ++i)
-                    for (int j = 0; j < wmax; ++j) sum = __fadd_rn(sum, __ldg(base + i * sh + j * sw + c));
-                v = __fdiv_rn(sum, inv_cnt_den);
+    const float cnt_f = (float)(hmax * wmax);
+    // two 32-channel blocks (one 64-channel unit) per iteration: all loads of the unit are issued before the
+    // first ballot, and lane 0 writes the unit with one 16-byte store
+    for (int ch = 0; ch < nch; ++ch) {
+        float v[2];
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const int c = ch * 64 + b * 32 + lane;
+            float t = 0.0f;
+            if (c < C) {
+                if (k == 1) t = __ldg(base + c);
+                else if (k == 2 && hmax == 2 && wmax == 2) {
+                    const float t00 = __ldg(base + c), t01 = __ldg(base + sw + c);
+                    const float t10 = __ldg(base + sh + c), t11 = __ldg(base + sh + sw + c);
+                    t = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(t00, t01), t10), t11), 4.0f);
+                } else {
+                    float sum = 0.0f;
+                    for (int i = 0; i < hmax; ++i)
+                        for (int j = 0; j < wmax; ++j) sum = __fadd_rn(sum, __ldg(base + i * sh + j * sw + c));
+                    t = __fdiv_rn(sum, cnt_f);
+                }
+                if (pre_scale != nullptr) t = __fadd_rn(__fmul_rn(t, __ldg(pre_scale + c)), __ldg(pre_shift + c));
             }
-            if (pre_scale != nullptr) v = __fadd_rn(__fmul_rn(v, __ldg(pre_scale + c)), __ldg(pre_shift + c));
+            v[b] = t;
         }
-        const uint32_t sw_ = __ballot_sync(0xffffffffu, c < C && v > 0.0f);
-        const uint32_t mw_ = __ballot_sync(0xffffffffu, c < C && (v > 0.0f || v < 0.0f));
-        if (lane == 0) {
-            uint32_t* u = abits + ((((size_t)n * nch + (blk >> 1)) * H + h) * W + w) * 4;
-            u[blk & 1] = sw_;
-            u[2 + (blk & 1)] = mw_;
+        uint32_t s_[2], m_[2];
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const bool ok = ch * 64 + b * 32 + lane < C;
+            s_[b] = __ballot_sync(0xffffffffu, ok && v[b] > 0.0f);
+            m_[b] = __ballot_sync(0xffffffffu, ok && (v[b] > 0.0f || v[b] < 0.0f));
         }
+        if (lane == 0)
+            reinterpret_cast<uint4*>(abits)[(((size_t)n * nch + ch) * H + h) * W + w] = make_uint4(s_[0], s_[1], m_[0], m_[1]);
     }
 }
 
