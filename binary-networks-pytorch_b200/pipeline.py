@@ -55,12 +55,16 @@ class HostPipeline:
     def d2h_bytes(self) -> int:
         return self.host_out[0].numel() * self.host_out[0].element_size()
 
-    def submit(self, host_batch: torch.Tensor) -> None:
-        """Enqueue one batch (pinned host memory for a truly asynchronous copy)."""
+    def submit(self, host_batch: torch.Tensor):
+        """Enqueue one batch (pinned host memory for a truly asynchronous copy).  When both slots are in flight
+        the oldest batch is retired first and its logits (a clone of the pinned buffer) are returned."""
         k = self.k
         self.k ^= 1
+        retired = None
         if len(self.pending) == 2:                          # both slots in flight: retire the oldest first
-            self.pending.popleft()[1].synchronize()
+            ko, ev = self.pending.popleft()
+            ev.synchronize()
+            retired = self.host_out[ko].clone()
         self.copy_stream.wait_event(self.done[k])           # slot k's previous forward has consumed its input
         with torch.cuda.stream(self.copy_stream):
             self.bufs[k].copy_(host_batch, non_blocking=True)
@@ -77,6 +81,14 @@ class HostPipeline:
         fin = torch.cuda.Event()
         fin.record(self.compute_stream)
         self.pending.append((k, fin))
+        return retired
+
+    def results(self):
+        """Retire everything still in flight, oldest first; yields the logits of each batch."""
+        while self.pending:
+            k, ev = self.pending.popleft()
+            ev.synchronize()
+            yield self.host_out[k].clone()
 
     def drain(self):
         """Wait for everything submitted; returns the logits of the last batch (pinned host tensor)."""

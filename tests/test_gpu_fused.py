@@ -167,3 +167,22 @@ def test_unrecognised_blocks_fall_back_to_their_own_forward():
         y = m(x)
         want = fs.mirror_model(m)(x.cpu()).numpy()
     assert rel_err(y.cpu().numpy(), want) <= 1e-3
+
+
+def test_host_pipeline_returns_the_same_logits_in_order():
+    from bnn_b200.pipeline import HostPipeline
+    m = build("basic_relu").to(DEV)
+    engine = fuse.optimize(m)
+    batches = [torch.randn(4, 3, 64, 64, generator=torch.Generator().manual_seed(s)).pin_memory() for s in range(5)]
+    pipe = HostPipeline(engine, batches[0])
+    assert pipe.h2d_bytes == 4 * 3 * 64 * 64 * 4 and pipe.d2h_bytes == 4 * 1000 * 4
+    got = []
+    for b in batches:
+        done = pipe.submit(b)
+        if done is not None:
+            got.append(done)
+    got += list(pipe.results())
+    assert len(got) == len(batches)
+    with torch.no_grad():
+        for b, y in zip(batches, got):
+            assert torch.equal(engine(b.to(DEV)).cpu(), y)

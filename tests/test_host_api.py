@@ -217,6 +217,12 @@ def test_plugs_into_the_reference_prepare_binary_model():
     assert type(model[0]) is Conv2d and type(model[3]) is Conv2d and type(model[8]) is nn.Linear
     low = model[3]._lowering()
     assert low.center_weights and low.fused_post
+    # the reference's own ResNet object, converted through the reference's entry point, is fusable as a whole
+    from bnn_b200 import fuse
+    rr = importlib.import_module("bnn_ref.models.resnet")
+    r18 = ref.prepare_binary_model(rr.resnet18(), rcfg, modules_mapping=mapping, ignore_layers_name=["_first_", "_last_"])
+    eng = fuse.optimize(r18.eval())
+    assert isinstance(eng, fuse.FusedResNet) and eng.fused_blocks == 8 and eng.stem.ok
     # a model already converted by the reference converts too
     refmodel = ref.prepare_binary_model(small_net(), rcfg)
     model2 = ref.prepare_binary_model(refmodel, rcfg, modules_mapping=mapping)
