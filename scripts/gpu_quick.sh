@@ -4,6 +4,8 @@ OUT=gpurun_out/$TAG
 mkdir -p $OUT
 timeout 900 python -m pytest tests -m gpu -q -x > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -2 $OUT/pytest_gpu.log
 timeout 600 python bench.py --steps 30 --warmup 3 --layers-out $OUT/layers.json > $OUT/bench.log 2>&1; tail -1 $OUT/bench.log | cut -c1-220
+timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:stem_kernel -c 1 \
+    -o $OUT/prof_stem -f python scripts/one_forward.py > $OUT/ncu_stem.log 2>&1; echo "ncu stem $?"
 timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
     --log-file $OUT/launches_one_forward.csv python scripts/one_forward.py > $OUT/ncu_one.log 2>&1; echo "ncu $?"
-grep -E "stem_kernel" $OUT/launches_one_forward.csv | head -2 | cut -c1-200
+grep -E "stem_kernel|pack_act" $OUT/launches_one_forward.csv | cut -d, -f5,14- | head -5
