@@ -175,9 +175,18 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
     const int pr = lane % PW, rr = lane / PW;
 
     // ---------------- pixel groups ----------------
+    // per-image bases (the image is fixed for the CTA); inside an image 32-bit element offsets suffice (host-checked)
+    const float* res_n = (EPI == 1 && a.e.res) ? a.e.res + (long long)n * a.e.rn : nullptr;
+    float* out_n = a.e.out ? a.e.out + (long long)n * a.e.on : nullptr;
+    const int e_rc = (int)a.e.rc, e_rh = (int)a.e.rh, e_rw = (int)a.e.rw;
+    const int e_oc = (int)a.e.oc, e_oh = (int)a.e.oh, e_ow = (int)a.e.ow;
+    int g_row = warp / a.gpr, g_col = warp - g_row * a.gpr;      // one division per warp, then incremental
+    const int step_row = nwarps / a.gpr, step_col = nwarps - step_row * a.gpr;
     for (int g = warp; g < a.G; g += nwarps) {
-        const int r = g / a.gpr;
-        const int wq = (g - r * a.gpr) * P;      // first output column inside the tile
+        const int r = g_row;
+        const int wq = g_col * P;                // first output column inside the tile
+        g_row += step_row; g_col += step_col;
+        if (g_col >= a.gpr) { g_col -= a.gpr; ++g_row; }
         const int ho = ho0 + r;
         const int wo_first = wo0 + wq;
         if (ho >= a.Ho || wo_first >= a.Wo) continue;   // warp-uniform
@@ -186,17 +195,17 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
             // the residual tile is needed only after the K loop: start pulling its lines toward the SM now so the
             // epilogue does not sit on DRAM latency
             if (a.e.res != nullptr) {
-                const float* rb = a.e.res + (long long)n * a.e.rn + (long long)ho * a.e.rh;
-                if (a.e.rw == 1) {            // NCHW: one 32-byte pixel run per channel row
+                const float* rb = res_n + ho * e_rh;
+                if (e_rw == 1) {              // NCHW: one 32-byte pixel run per channel row
 #pragma unroll
                     for (int j = 0; j < C; ++j) {
                         const int c = (blk0 + j) * 32 + lane;
-                        if (c < a.Cout) prefetch_l1(rb + (long long)c * a.e.rc + wo_first);
+                        if (c < a.Cout) prefetch_l1(rb + c * e_rc + wo_first);
                     }
                 } else if (lane < P * C) {    // channels-last: one 128-byte line per (pixel, 32-channel block)
                     const int j = lane / P, p = lane - j * P;
                     if ((blk0 + j) * 32 < a.Cout && wo_first + p < a.Wo)
-                        prefetch_l1(rb + (long long)((blk0 + j) * 32) * a.e.rc + (long long)(wo_first + p) * a.e.rw);
+                        prefetch_l1(rb + (blk0 + j) * 32 * e_rc + (wo_first + p) * e_rw);
                 }
             }
         }
@@ -312,13 +321,13 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
                 const bool res_direct = has_res && a.e.rw != 1;
                 if (has_res && !res_direct) {
                     // NCHW residual: tile [32 ch][P px] through shared memory, coalesced along pixels
-                    const float* rbase = a.e.res + (long long)n * a.e.rn + (long long)ho * a.e.rh;
+                    const float* rbase = res_n + ho * e_rh;
                     __syncwarp();
 #pragma unroll
                     for (int r0 = 0; r0 < 32; r0 += ROWS) {
                         const int rl = r0 + rr, c = cblk + rl, wo = wo_first + pr;
                         float t = 0.0f;
-                        if (pr < P && wo < a.Wo && c < a.Cout) t = __ldg(rbase + (long long)c * a.e.rc + wo);
+                        if (pr < P && wo < a.Wo && c < a.Cout) t = __ldg(rbase + c * e_rc + wo);
                         if (pr < P) stg[rl * PITCH + pr] = t;
                     }
                     __syncwarp();
@@ -326,9 +335,8 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
                     for (int p = 0; p < P; ++p) res[p] = stg[lane * PITCH + p];
                 } else if (res_direct) {
                     // channel-contiguous residual (NHWC): lanes <-> channels reads whole 128-byte lines
-                    const float* rp = a.e.res + (long long)n * a.e.rn + (long long)ho * a.e.rh +
-                                      (long long)wo_first * a.e.rw + (cblk + lane) * (int)a.e.rc;
-                    const int rw = (int)a.e.rw;
+                    const float* rp = res_n + (ho * e_rh + wo_first * e_rw + (cblk + lane) * e_rc);
+                    const int rw = e_rw;
                     if (full) {
 #pragma unroll
                         for (int p = 0; p < P; ++p) res[p] = __ldg(rp + p * rw);
@@ -381,11 +389,11 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
                 }
             }
             if (a.e.out != nullptr) {
-                float* obase = a.e.out + (long long)n * a.e.on + (long long)ho * a.e.oh;
+                float* obase = out_n + ho * e_oh;
                 if (!transposed) {
                     // channel-contiguous output (Linear's [rows, out]): lanes <-> channels is already coalesced
-                    float* op = obase + (long long)wo_first * a.e.ow + (cblk + lane) * (int)a.e.oc;
-                    const int ow = (int)a.e.ow;
+                    float* op = obase + (wo_first * e_ow + (cblk + lane) * e_oc);
+                    const int ow = e_ow;
                     if (full) {
 #pragma unroll
                         for (int p = 0; p < P; ++p) op[p * ow] = v[p];
@@ -402,8 +410,8 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
                     for (int p = 0; p < P; ++p) stg[lane * PITCH + p] = v[p];
                     __syncwarp();
                     const bool lane_ok = pr < P && wo_first + pr < a.Wo;
-                    float* optr = obase + (long long)(cblk + rr) * a.e.oc + (wo_first + pr);
-                    const long long ostep = (long long)ROWS * a.e.oc;
+                    float* optr = obase + ((cblk + rr) * e_oc + wo_first + pr);
+                    const int ostep = ROWS * e_oc;
 #pragma unroll
                     for (int r0 = 0; r0 < 32; r0 += ROWS) {
                         if (lane_ok && cblk + r0 + rr < a.Cout) *optr = stg[(r0 + rr) * PITCH + pr];
@@ -621,8 +629,12 @@ static int launch_bconv(const void* abits, const void* wbits, const bnn_conv_geo
     const int epi = (ep.bn_scale || ep.residual || ep.act != BNN_ACT_NONE || ep.out_bits || ep.nx_scale) ? 1 : 0;
     {   // the kernel indexes inside one image row with 32-bit element offsets
         const long long lim = 0x7fffffffLL;
-        auto span = [&](int64_t sc_, int64_t sw_) { return (long long)g.c_out * (sc_ < 0 ? -sc_ : sc_) + (long long)Wo * (sw_ < 0 ? -sw_ : sw_); };
-        if ((ep.out && span(ep.ostride_c, ep.ostride_w) > lim) || (ep.residual && span(ep.rstride_c, ep.rstride_w) > lim))
+        auto ab = [](int64_t v) { return (long long)(v < 0 ? -v : v); };
+        auto span = [&](int64_t sc_, int64_t sh_, int64_t sw_) {
+            return (long long)g.c_out * ab(sc_) + (long long)Ho * ab(sh_) + (long long)Wo * ab(sw_);
+        };
+        if ((ep.out && span(ep.ostride_c, ep.ostride_h, ep.ostride_w) > lim) ||
+            (ep.residual && span(ep.rstride_c, ep.rstride_h, ep.rstride_w) > lim))
             return BNN_E_UNSUPPORTED;
     }
     if (epi) flags &= ~BNN_F_NO_CSA;

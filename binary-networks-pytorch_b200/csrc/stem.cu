@@ -130,9 +130,8 @@ stem_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ St
 #pragma unroll
         for (int c = 0; c < ST_CC; ++c) acc[c] = 0ull;
         acx[0] = acx[1] = acx[2] = 0ull;
-#pragma unroll 1
         for (int ci = 0; ci < ST_CI; ++ci) {
-#pragma unroll          // the 7 kernel rows are unrolled: accumulator register rotation then costs moves once per ci
+#pragma unroll 1        // (fully unrolling the 7 kernel rows was measured slower: 128 registers, spills)
             for (int kh = 0; kh < ST_K; ++kh) {
                 const float4* irow = reinterpret_cast<const float4*>(in_s + (ci * ST_IR + 2 * r + kh) * ST_ICP);
                 float iv[ST_ICP];
