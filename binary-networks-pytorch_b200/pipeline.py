@@ -57,14 +57,16 @@ class HostPipeline:
 
     def submit(self, host_batch: torch.Tensor):
         """Enqueue one batch (pinned host memory for a truly asynchronous copy).  When both slots are in flight
-        the oldest batch is retired first and its logits (a clone of the pinned buffer) are returned."""
+        the oldest batch is retired first and its logits are returned: a view of that slot's pinned buffer, valid
+        until the next ``submit`` (copy it if it has to live longer; note that ``clone()`` of a pinned tensor
+        allocates pinned memory, which is slow -- use ``torch.empty_like(t, pin_memory=False).copy_(t)``)."""
         k = self.k
         self.k ^= 1
         retired = None
         if len(self.pending) == 2:                          # both slots in flight: retire the oldest first
             ko, ev = self.pending.popleft()
             ev.synchronize()
-            retired = self.host_out[ko].clone()
+            retired = self.host_out[ko]
         self.copy_stream.wait_event(self.done[k])           # slot k's previous forward has consumed its input
         with torch.cuda.stream(self.copy_stream):
             self.bufs[k].copy_(host_batch, non_blocking=True)
@@ -84,11 +86,11 @@ class HostPipeline:
         return retired
 
     def results(self):
-        """Retire everything still in flight, oldest first; yields the logits of each batch."""
+        """Retire everything still in flight, oldest first; yields the logits of each batch (pinned views)."""
         while self.pending:
             k, ev = self.pending.popleft()
             ev.synchronize()
-            yield self.host_out[k].clone()
+            yield self.host_out[k]
 
     def drain(self):
         """Wait for everything submitted; returns the logits of the last batch (pinned host tensor)."""

@@ -180,8 +180,8 @@ def test_host_pipeline_returns_the_same_logits_in_order():
     for b in batches:
         done = pipe.submit(b)
         if done is not None:
-            got.append(done)
-    got += list(pipe.results())
+            got.append(torch.empty_like(done, pin_memory=False).copy_(done))   # the view is reused two submits later
+    got += [torch.empty_like(t, pin_memory=False).copy_(t) for t in pipe.results()]
     assert len(got) == len(batches)
     with torch.no_grad():
         for b, y in zip(batches, got):
