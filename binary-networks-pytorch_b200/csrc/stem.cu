@@ -92,18 +92,13 @@ stem_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ St
         }
     }
     if (!tma_in) {
-        // one warp per input row (3 x 23 rows of 40 columns): lanes run along the row, no index arithmetic
-        for (int row = warp; row < ST_CI * ST_IR; row += ST_WARPS) {
-            const int ci = row / ST_IR, r = row - ci * ST_IR;
-            const int hi = hi0 + r;
-            const bool row_ok = (unsigned)hi < (unsigned)a.H;
-            const float* src = a.x + (((size_t)n * ST_CI + ci) * a.H + (row_ok ? hi : 0)) * a.W;
-            float* dst = in_s + row * ST_ICP;
-#pragma unroll
-            for (int c = lane; c < ST_ICP; c += 32) {
-                const int wi = wi0 + c;
-                dst[c] = (row_ok && (unsigned)wi < (unsigned)a.W) ? __ldg(src + wi) : 0.0f;
-            }
+        for (int i = threadIdx.x; i < ST_CI * ST_IR * ST_ICP; i += blockDim.x) {
+            const int c = i % ST_ICP, r = (i / ST_ICP) % ST_IR, ci = i / (ST_ICP * ST_IR);
+            const int hi = hi0 + r, wi = wi0 + c;
+            float v = 0.0f;
+            if ((unsigned)hi < (unsigned)a.H && (unsigned)wi < (unsigned)a.W)
+                v = __ldg(a.x + (((size_t)n * ST_CI + ci) * a.H + hi) * a.W + wi);
+            in_s[i] = v;
         }
     }
     if (!tma_w) {
@@ -131,7 +126,7 @@ stem_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ St
         for (int c = 0; c < ST_CC; ++c) acc[c] = 0ull;
         acx[0] = acx[1] = acx[2] = 0ull;
         for (int ci = 0; ci < ST_CI; ++ci) {
-#pragma unroll 1        // (fully unrolling the 7 kernel rows was measured slower: 128 registers, spills)
+#pragma unroll 1
             for (int kh = 0; kh < ST_K; ++kh) {
                 const float4* irow = reinterpret_cast<const float4*>(in_s + (ci * ST_IR + 2 * r + kh) * ST_ICP);
                 float iv[ST_ICP];
@@ -148,11 +143,11 @@ stem_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ St
                     const float4 v = xrow[q];
                     xv[4 * q] = v.x; xv[4 * q + 1] = v.y; xv[4 * q + 2] = v.z; xv[4 * q + 3] = v.w;
                 }
-                const unsigned long long* wrow =
-                    reinterpret_cast<const unsigned long long*>(w_s) + ((ci * ST_K + kh) * ST_K) * 32 + lane;
+                const float2* wrow = reinterpret_cast<const float2*>(w_s) + ((ci * ST_K + kh) * ST_K) * 32 + lane;
 #pragma unroll
                 for (int kw = 0; kw < ST_K; ++kw) {
-                    const unsigned long long ww = wrow[kw * 32];       // (w[lane], w[lane+32]) as one LDS.64
+                    const float2 w2 = wrow[kw * 32];
+                    const unsigned long long ww = pack2(w2.x, w2.y);
 #pragma unroll
                     for (int c = 0; c < ST_CC; ++c) acc[c] = fma2(pack2(iv[2 * c + kw], iv[2 * c + kw]), ww, acc[c]);
 #pragma unroll

@@ -26,8 +26,9 @@ class HostPipeline:
         self.done = [torch.cuda.Event() for _ in range(2)]
         self.graphs = [None, None]
         self.outs = [None, None]
-        self.host_out = [None, None]
+        self.host_out = [None, None, None]      # three pinned result buffers: a retired view survives one more submit
         self.k = 0
+        self.step = 0
         self.pending: Deque[Tuple[int, torch.cuda.Event]] = deque()
         with torch.no_grad():
             for k in range(2):
@@ -44,6 +45,8 @@ class HostPipeline:
                     final = self.post(out) if self.post is not None else out
                     self.compute_stream.synchronize()
                 self.host_out[k] = torch.empty(final.shape, dtype=final.dtype).pin_memory()
+                if k == 1:
+                    self.host_out[2] = torch.empty(final.shape, dtype=final.dtype).pin_memory()
                 self.done[k].record(self.compute_stream)
         torch.cuda.synchronize(self.device)
 
@@ -62,6 +65,8 @@ class HostPipeline:
         allocates pinned memory, which is slow -- use ``torch.empty_like(t, pin_memory=False).copy_(t)``)."""
         k = self.k
         self.k ^= 1
+        hk = self.step % 3
+        self.step += 1
         retired = None
         if len(self.pending) == 2:                          # both slots in flight: retire the oldest first
             ko, ev = self.pending.popleft()
@@ -78,11 +83,11 @@ class HostPipeline:
             else:
                 self.outs[k] = self.engine(self.bufs[k])
             final = self.post(self.outs[k]) if self.post is not None else self.outs[k]
-            self.host_out[k].copy_(final, non_blocking=True)
+            self.host_out[hk].copy_(final, non_blocking=True)
             self.done[k].record(self.compute_stream)
         fin = torch.cuda.Event()
         fin.record(self.compute_stream)
-        self.pending.append((k, fin))
+        self.pending.append((hk, fin))
         return retired
 
     def results(self):
