@@ -145,6 +145,8 @@ def bconv2d(act: PackedActivations, wts: PackedWeights, bias: Optional[torch.Ten
     with torch.cuda.device(dev):
         if out is None:
             out = torch.empty((act.n, wts.c_out, ho, wo), dtype=torch.float32, device=dev)
+        elif tuple(out.shape) != (act.n, wts.c_out, ho, wo) or out.dtype != torch.float32 or not out.is_cuda:
+            raise native.NativeError(f"out must be a float32 CUDA tensor of shape {(act.n, wts.c_out, ho, wo)}")
         on, oc, oh, ow = out.stride()
         ep = native.Epilogue()
         ep.scale = wts.alpha.data_ptr() if use_alpha else None

@@ -2,8 +2,8 @@
 
 ``optimize(model)`` wraps a prepared ResNet-style model (``bnn.models.resnet`` layout: ``conv1,
 bn1, relu, maxpool, layer1..4, avgpool, fc``; blocks of the reference's ``BasicBlock`` /
-``PreBasicBlock`` shape, bnn/models/layers/res_block.py:8-56,121-167) in an engine that runs each
-residual block as two (three with a shortcut conv) kernel launches:
+``PreBasicBlock`` / ``Bottleneck`` / ``PreBottleneck`` shape, bnn/models/layers/res_block.py:8-229) in an
+engine that runs each residual block as one kernel launch per binarized conv (plus two for a shortcut):
 
 * the eval-mode BatchNorm after (or before) a binarized conv, the ReLU / PReLU, the residual add
   and the *next* layer's sign() are folded into the conv kernel's epilogue (``bnn_bconv2d_fused_fwd``);
@@ -75,36 +75,55 @@ def _fusable_conv(conv) -> bool:
     return (not low.has_post) or low.fused_post
 
 
+_BLOCK_LAYOUTS = {
+    # block class name -> (pre-activation?, ((conv, bn, act), ...)) in execution order
+    "BasicBlock": (False, (("conv1", "bn1", "act1"), ("conv2", "bn2", "act2"))),
+    "PreBasicBlock": (True, (("conv1", "bn1", "act1"), ("conv2", "bn2", "act2"))),
+    "Bottleneck": (False, (("conv1", "bn1", "act1"), ("conv2", "bn2", "act2"), ("conv3", "bn3", "act3"))),
+    "PreBottleneck": (True, (("conv1", "bn1", "act1"), ("conv2", "bn2", "act2"), ("conv3", "bn3", "act3"))),
+}
+
+
 class _BlockPlan:
-    """One residual block: which modules it is made of and how it is laid out."""
+    """One residual block of the reference's zoo (bnn/models/layers/res_block.py): a chain of binarized convs,
+    each with a BatchNorm behind it (post-activation blocks: conv-bn-act ... conv-bn, +identity, act) or in front
+    of it (pre-activation blocks: bn-conv-act ... , +identity), and an optional AvgPool-conv1x1-BN shortcut."""
 
     def __init__(self, block: nn.Module) -> None:
         self.block = block
         self.kind = None
-        name = type(block).__name__
-        needed = ("conv1", "bn1", "conv2", "bn2", "act1", "act2")
-        if name in ("BasicBlock", "PreBasicBlock") and all(hasattr(block, k) for k in needed):
-            ok = _fusable_conv(block.conv1) and _fusable_conv(block.conv2)
-            ok = ok and isinstance(block.bn1, nn.BatchNorm2d) and isinstance(block.bn2, nn.BatchNorm2d)
-            ok = ok and block.bn1.track_running_stats and block.bn2.track_running_stats
-            ok = ok and _activation_spec(block.act1) is not None and _activation_spec(block.act2) is not None
-            ds = getattr(block, "downsample", None)
-            self.shortcut = None
-            if ds is not None:
-                # reference resnet.py:129-133: AvgPool2d(k=stride) -> binarized conv1x1 -> BatchNorm
-                good = (isinstance(ds, nn.Sequential) and len(ds) == 3 and isinstance(ds[0], nn.AvgPool2d)
-                        and _fusable_conv(ds[1]) and isinstance(ds[2], nn.BatchNorm2d))
-                if good:
-                    pool = ds[0]
-                    k, s = _pair(pool.kernel_size), _pair(pool.stride)
-                    good = (k[0] == k[1] == s[0] == s[1] and _pair(pool.padding) == (0, 0)
-                            and not pool.count_include_pad and pool.divisor_override is None)
-                ok = ok and good
-                if good:
-                    self.shortcut = (ds[0], ds[1], _FoldedBN(ds[2]))
-            if ok:
-                self.kind = "pre" if name == "PreBasicBlock" else "basic"
-                self.bn1, self.bn2 = _FoldedBN(block.bn1), _FoldedBN(block.bn2)
+        layout = _BLOCK_LAYOUTS.get(type(block).__name__)
+        if layout is None:
+            return
+        pre, stages = layout
+        if not all(hasattr(block, k) for stage in stages for k in stage):
+            return
+        ok = True
+        for conv, bn, act in stages:
+            b = getattr(block, bn)
+            ok = ok and _fusable_conv(getattr(block, conv)) and isinstance(b, nn.BatchNorm2d) and b.track_running_stats
+            ok = ok and _activation_spec(getattr(block, act)) is not None
+        if ok and pre:
+            # a pre-activation block normalises the INPUT of conv i with bn i: channel counts must line up
+            ok = all(getattr(block, bn).num_features == getattr(block, conv).in_channels for conv, bn, _ in stages)
+        ds = getattr(block, "downsample", None)
+        self.shortcut = None
+        if ok and ds is not None:
+            # reference resnet.py:129-133: AvgPool2d(k=stride) -> binarized conv1x1 -> BatchNorm
+            good = (isinstance(ds, nn.Sequential) and len(ds) == 3 and isinstance(ds[0], nn.AvgPool2d)
+                    and _fusable_conv(ds[1]) and isinstance(ds[2], nn.BatchNorm2d))
+            if good:
+                pool = ds[0]
+                k, st = _pair(pool.kernel_size), _pair(pool.stride)
+                good = (k[0] == k[1] == st[0] == st[1] and _pair(pool.padding) == (0, 0)
+                        and not pool.count_include_pad and pool.divisor_override is None)
+            ok = good
+            if good:
+                self.shortcut = (ds[0], ds[1], _FoldedBN(ds[2]))
+        if ok:
+            self.kind = "pre" if pre else "basic"
+            self.stages = [(getattr(block, c), _FoldedBN(getattr(block, b)), getattr(block, a)) for c, b, a in stages]
+            self.bn1 = self.stages[0][1]
 
     @property
     def fused(self) -> bool:
@@ -195,25 +214,32 @@ class FusedResNet(nn.Module):
             shortcut, _ = BF.bconv2d_fused(pooled, wts, bn=bn_d.get(), channels_last=True, **kw)
         else:
             shortcut = x
-        a1, p1 = _activation_spec(blk.act1)
-        a2, p2 = _activation_spec(blk.act2)
-        kw1, w1 = _conv_args(blk.conv1)
-        kw2, w2 = _conv_args(blk.conv2)
-        c1, c2 = blk.conv1.out_channels, blk.conv2.out_channels
-        if plan.kind == "basic":
-            # conv1 -> bn1 -> act1 -> [sign] -> conv2 -> bn2 -> (+shortcut) -> act2
-            _, mid = BF.bconv2d_fused(xbits, w1, bn=plan.bn1.get(), activation=a1, act_slope=_slope(p1, c1, x.device),
-                                      want_out=False, want_bits=True, **kw1)
-            y, bits = BF.bconv2d_fused(mid, w2, bn=plan.bn2.get(), residual=shortcut, activation=a2,
-                                       act_slope=_slope(p2, c2, x.device), want_out=True, want_bits=want_next_bits,
-                                       nx=nx, channels_last=True, **kw2)
-        else:
-            # [bn1 -> sign] -> conv1 -> act1 -> [bn2 -> sign] -> conv2 -> act2 -> (+shortcut)
-            _, mid = BF.bconv2d_fused(xbits, w1, activation=a1, act_slope=_slope(p1, c1, x.device), want_out=False,
-                                      want_bits=True, nx=plan.bn2.get(), **kw1)
-            y, bits = BF.bconv2d_fused(mid, w2, residual=shortcut, residual_after_act=True, activation=a2,
-                                       act_slope=_slope(p2, c2, x.device), want_out=True, want_bits=want_next_bits,
-                                       nx=nx, channels_last=True, **kw2)
+        dev = x.device
+        bits = xbits
+        last = len(plan.stages) - 1
+        for i, (conv, bn, act_mod) in enumerate(plan.stages):
+            code, prelu = _activation_spec(act_mod)
+            kw, wts = _conv_args(conv)
+            slope = _slope(prelu, conv.out_channels, dev)
+            if plan.kind == "basic":
+                # conv -> bn -> act -> [sign of the next conv]; the last conv adds the shortcut before its activation
+                if i < last:
+                    _, bits = BF.bconv2d_fused(bits, wts, bn=bn.get(), activation=code, act_slope=slope,
+                                               want_out=False, want_bits=True, **kw)
+                else:
+                    y, bits = BF.bconv2d_fused(bits, wts, bn=bn.get(), residual=shortcut, activation=code,
+                                               act_slope=slope, want_out=True, want_bits=want_next_bits, nx=nx,
+                                               channels_last=True, **kw)
+            else:
+                # [bn -> sign] -> conv -> act; the planes handed on go through the NEXT conv's BatchNorm;
+                # the shortcut is added after the last activation
+                if i < last:
+                    _, bits = BF.bconv2d_fused(bits, wts, activation=code, act_slope=slope, want_out=False,
+                                               want_bits=True, nx=plan.stages[i + 1][1].get(), **kw)
+                else:
+                    y, bits = BF.bconv2d_fused(bits, wts, residual=shortcut, residual_after_act=True, activation=code,
+                                               act_slope=slope, want_out=True, want_bits=want_next_bits, nx=nx,
+                                               channels_last=True, **kw)
         return y, bits
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:

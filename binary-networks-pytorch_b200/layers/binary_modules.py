@@ -190,8 +190,6 @@ def _pair(v):
 
 class _ConvNd(_BinaryLayer):
     def _check_geometry(self) -> None:
-        if self.groups != 1:
-            raise NotLowerable(f"groups={self.groups}")
         if self.padding_mode != "zeros":
             raise NotLowerable(f"padding_mode={self.padding_mode}")
         self._resolved_padding()
@@ -233,11 +231,47 @@ class Conv2d(_ConvNd, nn.Conv2d):
     def _forward_packed(self, x: torch.Tensor, low: _Lowering) -> torch.Tensor:
         if x.dim() != 4:
             raise NativeError(f"Conv2d expects a 4-D input, got {tuple(x.shape)}")
-        wts = self._packed_weights(low)
-        act = BF.pack_activations(x)
-        return BF.bconv2d(act, wts, self._bias(), self._post_scale(low), _pair(self.stride),
-                          self._resolved_padding(), _pair(self.dilation), use_alpha=low.compute_alpha,
-                          flags=runtime.kernel_flags())
+        if self.groups == 1:
+            wts = self._packed_weights(low)
+            act = BF.pack_activations(x)
+            return BF.bconv2d(act, wts, self._bias(), self._post_scale(low), _pair(self.stride),
+                              self._resolved_padding(), _pair(self.dilation), use_alpha=low.compute_alpha,
+                              flags=runtime.kernel_flags())
+        return self._forward_grouped(x, low)
+
+    def _forward_grouped(self, x: torch.Tensor, low: _Lowering) -> torch.Tensor:
+        """groups > 1 (e.g. the BATS cells, bnn/models/layers/bats_ops.py:41-52): one launch pair per group on
+        strided channel slices of the input and of the output -- the kernels take element strides, so no copies."""
+        g = self.groups
+        cin_g, cout_g = self.in_channels // g, self.out_channels // g
+        packed = self._packed_group_weights(low)
+        kh, kw = self.kernel_size
+        sh, sw = _pair(self.stride)
+        ph, pw = self._resolved_padding()
+        dh, dw = _pair(self.dilation)
+        ho = (x.shape[2] + 2 * ph - dh * (kh - 1) - 1) // sh + 1
+        wo = (x.shape[3] + 2 * pw - dw * (kw - 1) - 1) // sw + 1
+        out = torch.empty((x.shape[0], self.out_channels, ho, wo), dtype=torch.float32, device=x.device)
+        bias, post = self._bias(), self._post_scale(low)
+        for i in range(g):
+            act = BF.pack_activations(x[:, i * cin_g:(i + 1) * cin_g])
+            sl = slice(i * cout_g, (i + 1) * cout_g)
+            BF.bconv2d(act, packed[i], None if bias is None else bias[sl], None if post is None else post[sl],
+                       (sh, sw), (ph, pw), (dh, dw), use_alpha=low.compute_alpha, flags=runtime.kernel_flags(),
+                       out=out[:, sl])
+        return out
+
+    def _packed_group_weights(self, low: _Lowering):
+        w = self.weight
+        key = ("groups", w.data_ptr(), w._version, w.device, tuple(w.shape), low.center_weights, low.compute_alpha)
+        if self._pack_key != key:
+            cout_g = self.out_channels // self.groups
+            packed = [BF.pack_weights(w[i * cout_g:(i + 1) * cout_g], low.center_weights, low.compute_alpha)
+                      for i in range(self.groups)]
+            if any(p.n_zero for p in packed):
+                raise NativeError("exactly-zero (centred) weights cannot be held by the 1-bit weight plane")
+            self._packed, self._pack_key = packed, key
+        return self._packed
 
 
 class Conv1d(_ConvNd, nn.Conv1d):
@@ -249,6 +283,11 @@ class Conv1d(_ConvNd, nn.Conv1d):
         nn.Conv1d.__init__(self, in_channels, out_channels, kernel_size, stride=stride, padding=padding,
                            dilation=dilation, groups=groups, bias=bias, padding_mode=padding_mode)
         self._attach(bconfig)
+
+    def _check_geometry(self) -> None:
+        if self.groups != 1:
+            raise NotLowerable(f"groups={self.groups}")
+        super()._check_geometry()
 
     def _forward_packed(self, x: torch.Tensor, low: _Lowering) -> torch.Tensor:
         if x.dim() != 3:

@@ -90,6 +90,23 @@ class Bottleneck(nn.Module):
         return self.act3(y)
 
 
+class PreBottleneck(Bottleneck):
+    """bn-conv-act three times, then + identity (reference res_block.py:170-229)."""
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None, norm=nn.BatchNorm2d, activation=nn.ReLU):
+        super().__init__(inplanes, planes, stride, downsample, norm, activation)
+        self.bn1 = norm(inplanes)
+        self.bn3 = norm(planes)
+
+    def forward(self, x):
+        shortcut = x if self.downsample is None else self.downsample(x)
+        y = self.act1(self.conv1(self.bn1(x)))
+        y = self.act2(self.conv2(self.bn2(y)))
+        y = self.act3(self.conv3(self.bn3(y)))
+        y += shortcut
+        return y
+
+
 class HBlock(nn.Module):
     """Hierarchical block: three bn-act-conv stages whose outputs are concatenated
     (reference hierarchical_block.py:8-60)."""

@@ -39,9 +39,9 @@ def binarize_weight(w: torch.Tensor, compute_alpha: bool, center_weights: bool) 
 
 
 def conv2d(x, weight, bias=None, post=None, stride=1, padding=0, dilation=1, compute_alpha=True,
-           center_weights=False):
+           center_weights=False, groups=1):
     y = F.conv2d(torch.sign(x), binarize_weight(weight, compute_alpha, center_weights), bias, stride, padding,
-                 dilation)
+                 dilation, groups)
     return y if post is None else y * post.reshape(1, -1, 1, 1)
 
 
@@ -58,15 +58,15 @@ def linear(x, weight, bias=None, post=None, compute_alpha=True, center_weights=F
 
 
 class FloatSimConv2d(nn.Module):
-    def __init__(self, weight, bias, post, stride, padding, dilation, compute_alpha, center_weights):
+    def __init__(self, weight, bias, post, stride, padding, dilation, compute_alpha, center_weights, groups=1):
         super().__init__()
         self.weight, self.bias, self.post = weight, bias, post
-        self.stride, self.padding, self.dilation = stride, padding, dilation
+        self.stride, self.padding, self.dilation, self.groups = stride, padding, dilation, groups
         self.compute_alpha, self.center_weights = compute_alpha, center_weights
 
     def forward(self, x):
         return conv2d(x, self.weight, self.bias, self.post, self.stride, self.padding, self.dilation,
-                      self.compute_alpha, self.center_weights)
+                      self.compute_alpha, self.center_weights, self.groups)
 
 
 class FloatSimLinear(nn.Module):
@@ -96,7 +96,7 @@ def mirror_model(prepared: nn.Module) -> nn.Module:
         post = _cpu(post_mod.alpha).reshape(-1) if hasattr(post_mod, "alpha") else None
         if isinstance(mod, nn.Conv2d):
             new = FloatSimConv2d(_cpu(mod.weight), _cpu(mod.bias), post, mod.stride, mod.padding, mod.dilation,
-                                 bool(wpre.compute_alpha), bool(wpre.center_weights))
+                                 bool(wpre.compute_alpha), bool(wpre.center_weights), mod.groups)
         elif isinstance(mod, nn.Linear):
             new = FloatSimLinear(_cpu(mod.weight), _cpu(mod.bias), post, bool(wpre.compute_alpha),
                                  bool(wpre.center_weights))

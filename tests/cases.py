@@ -21,6 +21,8 @@ CASES = [
     dict(name="wide_300", kind="conv2d", x=(1, 64, 3, 300), w=(32, 64, 3, 3), pad=(1, 1), relu=True),
     dict(name="valid_pad0", kind="conv2d", x=(2, 64, 9, 9), w=(96, 64, 3, 3), center=True, post=True),
     dict(name="w28_c128", kind="conv2d", x=(1, 128, 28, 28), w=(128, 128, 3, 3), pad=(1, 1), center=True, relu=True),
+    dict(name="groups2", kind="conv2d", x=(2, 64, 9, 9), w=(64, 32, 3, 3), pad=(1, 1), groups=2, center=True, bias=True, post=True),
+    dict(name="groups12_dil2", kind="conv2d", x=(1, 96, 10, 10), w=(96, 8, 3, 3), pad=(2, 2), dil=(2, 2), groups=12, relu=True),
     dict(name="lin_small", kind="linear", x=(5, 100), w=(10, 100), bias=True, post=True),
     dict(name="lin_fc", kind="linear", x=(64, 512), w=(1000, 512), bias=True, center=True),
     dict(name="lin_row1", kind="linear", x=(1, 64), w=(64, 64)),
@@ -56,4 +58,4 @@ def hyper(case):
     one = (1,) * nd
     return dict(stride=tuple(case.get("stride", one)), pad=tuple(case.get("pad", (0,) * nd)),
                 dil=tuple(case.get("dil", one)), center=bool(case.get("center", False)),
-                alpha=bool(case.get("alpha", True)))
+                alpha=bool(case.get("alpha", True)), groups=int(case.get("groups", 1)))

@@ -48,8 +48,8 @@ def ref_layer(case):
                           activation_post_process=ref_ops.BasicScaleBinarizer if post is not None else bnn_ref.Identity,
                           weight_pre_process=wb)
     if case["kind"] == "conv2d":
-        m = nn.Conv2d(w.shape[1], w.shape[0], w.shape[2:], stride=hp["stride"], padding=hp["pad"],
-                      dilation=hp["dil"], bias=bias is not None)
+        m = nn.Conv2d(w.shape[1] * hp["groups"], w.shape[0], w.shape[2:], stride=hp["stride"], padding=hp["pad"],
+                      dilation=hp["dil"], groups=hp["groups"], bias=bias is not None)
     elif case["kind"] == "conv1d":
         m = nn.Conv1d(w.shape[1], w.shape[0], w.shape[2], stride=hp["stride"], padding=hp["pad"],
                       dilation=hp["dil"], bias=bias is not None)

@@ -155,18 +155,33 @@ def test_fused_engine_tracks_batchnorm_updates_and_graph_capture():
     assert torch.equal(out, y1)
 
 
-def test_unrecognised_blocks_fall_back_to_their_own_forward():
+@pytest.mark.parametrize("pre", [False, True], ids=["bottleneck", "prebottleneck"])
+def test_fused_engine_resnet50_blocks(pre):
+    """BASELINE configs[2] through the fused engine: 16 (Pre)Bottleneck blocks, 52 binarized convs, learned XNOR-Net++
+    scales in the folded epilogue, AvgPool(k=1 and k=2) shortcuts."""
     torch.manual_seed(0)
-    m = workloads.resnet50()
-    m = bnn.prepare_binary_model(m, xnor_cfg(), ignore_layers_name=["_first_", "_last_"])
+    m = workloads.ResNet(workloads.PreBottleneck, [3, 4, 6, 3], activation=nn.PReLU, fc_in=2048) if pre else workloads.resnet50()
+    m = bnn.prepare_binary_model(m, xnor_cfg(BasicScaleBinarizer), ignore_layers_name=["_first_", "_last_"])
     workloads.randomize_batchnorm(m)
-    m = m.eval().to(DEV)
-    assert fuse.optimize(m) is m                            # Bottleneck blocks: nothing to fuse yet
-    x = torch.randn(2, 3, 64, 64, device=DEV)
+    m = m.eval()
+    twin = fs.mirror_model(m)
+    engine = fuse.optimize(m.to(DEV))
+    assert isinstance(engine, fuse.FusedResNet) and engine.fused_blocks == 16
+    x = torch.randn(2, 3, 96, 96, generator=torch.Generator().manual_seed(5))
     with torch.no_grad():
-        y = m(x)
-        want = fs.mirror_model(m)(x.cpu()).numpy()
-    assert rel_err(y.cpu().numpy(), want) <= 1e-3
+        want = twin(x).numpy()
+        got = engine(x.to(DEV)).cpu().numpy()
+        eager = m(x.to(DEV)).cpu().numpy()
+    print("resnet50", "pre" if pre else "post", "fused vs twin", rel_err(got, want), "unfused vs twin", rel_err(eager, want))
+    assert rel_err(got, want) <= 1e-3
+    assert rel_err(eager, want) <= 1e-3
+
+
+def test_unrecognised_models_are_returned_unchanged():
+    torch.manual_seed(0)
+    m = workloads.HBlockNet(depth=1)
+    m = bnn.prepare_binary_model(m, xnor_cfg(), ignore_layers_name=["_first_", "_last_"]).eval().to(DEV)
+    assert fuse.optimize(m) is m
 
 
 def test_host_pipeline_returns_the_same_logits_in_order():

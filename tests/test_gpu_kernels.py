@@ -76,8 +76,11 @@ def test_pack_weights_counts_exact_zeros():
 FLAG_SETS = [native.F_STAGE_LDG, 0, native.F_NO_CSA]
 
 
+UNGROUPED = [c for c in cases.CASES if c.get("groups", 1) == 1]
+
+
 @pytest.mark.parametrize("flags", FLAG_SETS, ids=["ldg", "tma", "nocsa"])
-@pytest.mark.parametrize("case", cases.CASES, ids=[c["name"] for c in cases.CASES])
+@pytest.mark.parametrize("case", UNGROUPED, ids=[c["name"] for c in UNGROUPED])
 def test_conv_kernel_against_oracle_and_reference(case, flags, golden_layers):
     """C ABI level: packed conv == oracle integer path bit-exactly (dot), == reference within TOL."""
     x4, w4, bias, post, g, hp, unflat = _as_conv2d(case)
@@ -108,8 +111,8 @@ def test_module_api_against_reference(case, golden_layers):
     cfg = bnn.BConfig(BasicInputBinarizer, BasicScaleBinarizer if post is not None else bnn.Identity,
                       XNORWeightBinarizer.with_args(compute_alpha=hp["alpha"], center_weights=hp["center"]))
     if case["kind"] == "conv2d":
-        m = nn.Conv2d(w.shape[1], w.shape[0], w.shape[2:], stride=hp["stride"], padding=hp["pad"], dilation=hp["dil"],
-                      bias=bias is not None)
+        m = nn.Conv2d(w.shape[1] * hp["groups"], w.shape[0], w.shape[2:], stride=hp["stride"], padding=hp["pad"],
+                      dilation=hp["dil"], groups=hp["groups"], bias=bias is not None)
     elif case["kind"] == "conv1d":
         m = nn.Conv1d(w.shape[1], w.shape[0], w.shape[2], stride=hp["stride"], padding=hp["pad"], dilation=hp["dil"],
                       bias=bias is not None)
@@ -124,7 +127,7 @@ def test_module_api_against_reference(case, golden_layers):
     before = native.launch_count()
     with torch.no_grad():
         y = m(torch.from_numpy(x).to(DEV))
-    assert native.launch_count() >= before + 2          # pack + conv really ran in the native library
+    assert native.launch_count() >= before + 2 * hp["groups"]   # pack + conv (per group) really ran in the native library
     assert rel_err(y.cpu().numpy(), golden_layers[case["name"]]) <= TOL
 
 

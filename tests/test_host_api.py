@@ -183,8 +183,9 @@ def test_lowering_analysis():
     low = ok._lowering()
     assert low.fused_post and low.compute_alpha and not low.center_weights
     assert ok._resolved_padding() == (1, 1)
+    assert Conv2d.from_module(nn.Conv2d(64, 64, 3, groups=2), CFG)._lowering().compute_alpha     # grouped: per-group launches
     with pytest.raises(NotLowerable):
-        Conv2d.from_module(nn.Conv2d(64, 64, 3, groups=2), CFG)._lowering()
+        Conv1d.from_module(nn.Conv1d(64, 64, 3, groups=2), CFG)._lowering()
     with pytest.raises(NotLowerable):
         Conv2d.from_module(nn.Conv2d(64, 64, 3, padding=1, padding_mode="reflect"), CFG)._lowering()
     sto = bnn.BConfig(StochasticInputBinarizer, bnn.Identity, XNORWeightBinarizer)

@@ -57,10 +57,15 @@ def _run_floatsim_torch(case):
     x, w, bias, post = cases.make_inputs(case)
     hp = cases.hyper(case)
     if case["kind"] == "conv2d":
-        return fs.conv2d(_t(x), _t(w), _t(bias), _t(post), hp["stride"], hp["pad"], hp["dil"], hp["alpha"], hp["center"]).numpy()
+        return fs.conv2d(_t(x), _t(w), _t(bias), _t(post), hp["stride"], hp["pad"], hp["dil"], hp["alpha"], hp["center"],
+                         hp["groups"]).numpy()
     if case["kind"] == "conv1d":
         return fs.conv1d(_t(x), _t(w), _t(bias), _t(post), hp["stride"], hp["pad"], hp["dil"], hp["alpha"], hp["center"]).numpy()
     return fs.linear(_t(x), _t(w), _t(bias), _t(post), hp["alpha"], hp["center"]).numpy()
+
+
+def hp_groups(case):
+    return int(case.get("groups", 1))
 
 
 def _as_conv2d(case):
@@ -89,6 +94,23 @@ def test_layer_cases_against_reference_outputs(case, golden_layers):
     y = _run_floatsim_torch(case)
     assert y.shape == ref.shape
     assert rel_err(y, ref) <= 1e-6, rel_err(y, ref)
+    if hp_groups(case) > 1:
+        # the C restatement has no groups argument: run it per group on channel slices, like the product does
+        x, w, bias, post = cases.make_inputs(case)
+        hp = cases.hyper(case)
+        G, cin_g, cout_g = hp["groups"], w.shape[1], w.shape[0] // hp["groups"]
+        outs = []
+        for i in range(G):
+            xs = np.ascontiguousarray(x[:, i * cin_g:(i + 1) * cin_g])
+            ws = np.ascontiguousarray(w[i * cout_g:(i + 1) * cout_g])
+            geo = co.geom(xs.shape[0], cin_g, xs.shape[2], xs.shape[3], cout_g, w.shape[2], w.shape[3], hp["stride"], hp["pad"], hp["dil"])
+            sl = slice(i * cout_g, (i + 1) * cout_g)
+            wb, alpha, nz = co.pack_weight(ws, hp["center"], hp["alpha"])
+            assert nz == 0
+            outs.append(co.bconv2d(co.pack_act(xs), wb, alpha if hp["alpha"] else None, None if bias is None else bias[sl],
+                                   None if post is None else post[sl], geo))
+        assert rel_err(np.concatenate(outs, 1), ref) <= 1e-5
+        return
     # (2) plain-C float restatement and (3) packed integer formulation
     x4, w4, bias, post, g, hp, unflat = _as_conv2d(case)
     yc = unflat(co.floatsim_conv2d(x4, w4, bias, post, g, hp["center"], hp["alpha"]))
