@@ -402,21 +402,26 @@ def main():
                 h.remove()
             packs = [r for r in records if r[0] == "pack"]
             convs = [r for r in records if r[0] == "conv"]
+            # median over the repetitions: a single preempted launch must not skew a layer's time
+            per_step_c, per_step_p = len(convs) // reps, len(packs) // reps
+
+            def med(recs, per_step, slot):
+                if per_step == 0:
+                    return 0.0
+                return statistics.median(recs[rep * per_step + slot][1].elapsed_time(recs[rep * per_step + slot][2])
+                                         for rep in range(reps))
+
             if order:                                   # unfused: module hooks give the layer names
-                for i, name in enumerate(order):
-                    d = per_layer.setdefault(name, {"pack_ms": 0.0, "conv_ms": 0.0})
-                    d["pack_ms"] += packs[i][1].elapsed_time(packs[i][2]) / reps
-                    d["conv_ms"] += convs[i][1].elapsed_time(convs[i][2]) / reps
+                for i, name in enumerate(order[:per_step_c]):
+                    per_layer[name] = {"pack_ms": med(packs, per_step_p, i) if per_step_p == per_step_c else 0.0,
+                                       "conv_ms": med(convs, per_step_c, i)}
             else:                                       # fused engine: conv launches in execution order
                 names = fused_layer_order(model)
-                per_step = len(convs) // reps
-                for i, rec in enumerate(convs):
-                    name = names[i % per_step] if per_step == len(names) else f"conv{i % per_step}"
-                    d = per_layer.setdefault(name, {"pack_ms": 0.0, "conv_ms": 0.0})
-                    d["conv_ms"] += rec[1].elapsed_time(rec[2]) / reps
-                pack_total = sum(r[1].elapsed_time(r[2]) for r in packs) / reps
-                per_layer["_pack_launches_total"] = {"pack_ms": pack_total, "conv_ms": 0.0, "bytes": 0, "bmac": 0,
-                                                     "n_per_step": len(packs) // reps}
+                for i in range(per_step_c):
+                    name = names[i] if per_step_c == len(names) else f"conv{i}"
+                    per_layer[name] = {"pack_ms": 0.0, "conv_ms": med(convs, per_step_c, i)}
+                per_layer["_pack_launches_total"] = {"pack_ms": sum(med(packs, per_step_p, i) for i in range(per_step_p)),
+                                                     "conv_ms": 0.0, "bytes": 0, "bmac": 0, "n_per_step": per_step_p}
             for name, d in per_layer.items():
                 d.setdefault("bytes", 0); d.setdefault("bmac", 0)
                 if name in algo:
