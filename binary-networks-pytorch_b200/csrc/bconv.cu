@@ -39,7 +39,7 @@ struct Epi {                       // device view of bnn_epilogue
     float* out;
     long long on, oc, oh, ow;
     uint4* obits;
-    int act, res_after_act, ochunks;
+    int act, res_after_act, ochunks, nx_relu, bits_pre_res;
 };
 
 struct ConvArgs {
@@ -296,7 +296,9 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
         const bool has_res = (EPI == 1) && a.e.res != nullptr;
         const bool want_bits = (EPI == 1) && a.e.obits != nullptr;
         // ReLU output with no affine in front of the next sign(): "non-zero" and "positive" coincide
-        const bool relu_bits = a.e.act == BNN_ACT_RELU && a.e.nx_scale == nullptr && !(has_res && a.e.res_after_act);
+        const bool bits_pre = has_res && a.e.res_after_act && a.e.bits_pre_res;
+        const bool relu_bits = a.e.nx_relu || (a.e.act == BNN_ACT_RELU && a.e.nx_scale == nullptr &&
+                                               !(has_res && a.e.res_after_act && !bits_pre));
         const bool full = (wo_first + P <= a.Wo) && ((blk0 + C) * 32 <= a.Cout);
         uint32_t sbits[C], mbits[C];     // lane p keeps the packed words of pixel p
 #pragma unroll
@@ -358,7 +360,7 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
 #pragma unroll
                     for (int p = 0; p < P; ++p) v[p] = (v[p] > 0.0f) ? v[p] : __fmul_rn(k2, v[p]);
                 }
-                if (has_res && a.e.res_after_act) {
+                if (has_res && a.e.res_after_act && !bits_pre) {
 #pragma unroll
                     for (int p = 0; p < P; ++p) v[p] = __fadd_rn(v[p], res[p]);
                 }
@@ -386,6 +388,10 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
                             if (lane == p) { sbits[j] = sw; mbits[j] = mw; }
                         }
                     }
+                }
+                if (bits_pre) {            // the planes were taken before the shortcut is added
+#pragma unroll
+                    for (int p = 0; p < P; ++p) v[p] = __fadd_rn(v[p], res[p]);
                 }
             }
             if (a.e.out != nullptr) {
@@ -654,6 +660,7 @@ static int launch_bconv(const void* abits, const void* wbits, const bnn_conv_geo
     a.e.res = ep.residual; a.e.rn = ep.rstride_n; a.e.rc = ep.rstride_c; a.e.rh = ep.rstride_h; a.e.rw = ep.rstride_w;
     a.e.out = ep.out; a.e.on = ep.ostride_n; a.e.oc = ep.ostride_c; a.e.oh = ep.ostride_h; a.e.ow = ep.ostride_w;
     a.e.obits = (uint4*)ep.out_bits; a.e.act = ep.act; a.e.res_after_act = ep.residual_after_act;
+    a.e.nx_relu = ep.nx_relu; a.e.bits_pre_res = ep.bits_before_residual;
     a.e.ochunks = ceil_div(g.c_out, 64);
     a.N = g.n; a.Cin = g.c_in; a.H = g.h; a.W = g.w; a.Cout = g.c_out; a.KH = g.kh; a.KW = g.kw;
     a.SH = g.stride_h; a.SW = g.stride_w; a.PH = g.pad_h; a.PW = g.pad_w; a.DH = g.dil_h; a.DW = g.dil_w;

@@ -31,7 +31,7 @@ __device__ __forceinline__ float load_pooled(const float* p, long long sh, long 
 __global__ void __launch_bounds__(256)
 pack_act_kernel(const float* __restrict__ x, long long sn, long long sc, long long sh, long long sw,
                 int N, int C, int H, int W, int nch, int pool, int Hin, int Win,
-                const float* __restrict__ pre_scale, const float* __restrict__ pre_shift,
+                const float* __restrict__ pre_scale, const float* __restrict__ pre_shift, int pre_relu,
                 uint4* __restrict__ abits) {
     const long long total = (long long)N * nch * H * W;       // H, W: OUTPUT (pooled) plane size
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -48,7 +48,7 @@ pack_act_kernel(const float* __restrict__ x, long long sn, long long sc, long lo
     const int hmax = Hin - h * k, wmax = Win - w * k;
     const int cmax = min(64, C - ch * 64);
     uint32_t s[2] = {0u, 0u}, m[2] = {0u, 0u};
-    if (cmax == 64 && pool <= 1 && pre_scale == nullptr) {
+    if (cmax == 64 && pool <= 1 && pre_scale == nullptr && !pre_relu) {
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
 #pragma unroll
@@ -72,7 +72,7 @@ pack_act_kernel(const float* __restrict__ x, long long sn, long long sc, long lo
                 const int c = ch * 64 + b;
                 v = __fadd_rn(__fmul_rn(v, __ldg(pre_scale + c)), __ldg(pre_shift + c));
             }
-            const uint32_t pos = v > 0.0f, neg = v < 0.0f;
+            const uint32_t pos = v > 0.0f, neg = (v < 0.0f) && !pre_relu;     // relu(v) < 0 never happens
             s[b >> 5] |= pos << (b & 31);
             m[b >> 5] |= (pos | neg) << (b & 31);
         }
@@ -88,7 +88,7 @@ pack_act_kernel(const float* __restrict__ x, long long sn, long long sc, long lo
 __global__ void __launch_bounds__(256)
 pack_act_cl_kernel(const float* __restrict__ x, long long sn, long long sh, long long sw,
                    int N, int C, int H, int W, int nch, int pool, int Hin, int Win,
-                   const float* __restrict__ pre_scale, const float* __restrict__ pre_shift,
+                   const float* __restrict__ pre_scale, const float* __restrict__ pre_shift, int pre_relu,
                    uint32_t* __restrict__ abits) {
     const long long pixels = (long long)N * H * W;
     const long long pix = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -130,7 +130,7 @@ pack_act_cl_kernel(const float* __restrict__ x, long long sn, long long sh, long
         for (int b = 0; b < 2; ++b) {
             const bool ok = ch * 64 + b * 32 + lane < C;
             s_[b] = __ballot_sync(0xffffffffu, ok && v[b] > 0.0f);
-            m_[b] = __ballot_sync(0xffffffffu, ok && (v[b] > 0.0f || v[b] < 0.0f));
+            m_[b] = __ballot_sync(0xffffffffu, ok && (v[b] > 0.0f || (v[b] < 0.0f && !pre_relu)));
         }
         if (lane == 0)
             reinterpret_cast<uint4*>(abits)[(((size_t)n * nch + ch) * H + h) * W + w] = make_uint4(s_[0], s_[1], m_[0], m_[1]);
@@ -225,7 +225,7 @@ extern "C" size_t bnn_weight_bits_bytes(int32_t c_out, int32_t c_in, int32_t kh,
 
 static int launch_pack(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw, int32_t n, int32_t c,
                        int32_t h, int32_t w, int32_t pool, int32_t ceil_mode, const float* pre_scale,
-                       const float* pre_shift, void* abits, void* stream_) {
+                       const float* pre_shift, int32_t pre_relu, void* abits, void* stream_) {
     if (!x || !abits) return BNN_E_NULL;
     if ((pre_scale == nullptr) != (pre_shift == nullptr)) return BNN_E_NULL;
     if (n <= 0 || c <= 0 || h <= 0 || w <= 0 || pool < 0) return BNN_E_SHAPE;
@@ -245,7 +245,7 @@ static int launch_pack(const float* x, int64_t sn, int64_t sc, int64_t sh, int64
         const long long blocks = (pixels + 7) / 8;
         if (blocks > 0x7fffffffLL) return BNN_E_UNSUPPORTED;
         pack_act_cl_kernel<<<(unsigned)blocks, threads, 0, stream>>>(x, sn, sh, sw, n, c, ho, wo, nch, pool, h, w,
-                                                                    pre_scale, pre_shift, (uint32_t*)abits);
+                                                                    pre_scale, pre_shift, pre_relu, (uint32_t*)abits);
         count_launch(1);
         return (int)cudaGetLastError();
     }
@@ -253,22 +253,23 @@ static int launch_pack(const float* x, int64_t sn, int64_t sc, int64_t sh, int64
     const long long blocks = (total + threads - 1) / threads;
     if (blocks > 0x7fffffffLL) return BNN_E_UNSUPPORTED;
     pack_act_kernel<<<(unsigned)blocks, threads, 0, stream>>>(x, sn, sc, sh, sw, n, c, ho, wo, nch, pool, h, w,
-                                                            pre_scale, pre_shift, (uint4*)abits);
+                                                            pre_scale, pre_shift, pre_relu, (uint4*)abits);
     count_launch(1);
     return (int)cudaGetLastError();
 }
 
 extern "C" int bnn_pack_act_f32(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw,
                                 int32_t n, int32_t c, int32_t h, int32_t w, const float* pre_scale,
-                                const float* pre_shift, void* abits, void* stream) {
-    return launch_pack(x, sn, sc, sh, sw, n, c, h, w, 0, 0, pre_scale, pre_shift, abits, stream);
+                                const float* pre_shift, int32_t pre_relu, void* abits, void* stream) {
+    return launch_pack(x, sn, sc, sh, sw, n, c, h, w, 0, 0, pre_scale, pre_shift, pre_relu, abits, stream);
 }
 
 extern "C" int bnn_avgpool_pack_f32(const float* x, int64_t sn, int64_t sc, int64_t sh, int64_t sw,
                                     int32_t n, int32_t c, int32_t h, int32_t w, int32_t k, int32_t ceil_mode,
-                                    const float* pre_scale, const float* pre_shift, void* abits, void* stream) {
+                                    const float* pre_scale, const float* pre_shift, int32_t pre_relu, void* abits,
+                                    void* stream) {
     if (k < 1) return BNN_E_SHAPE;
-    return launch_pack(x, sn, sc, sh, sw, n, c, h, w, k, ceil_mode, pre_scale, pre_shift, abits, stream);
+    return launch_pack(x, sn, sc, sh, sw, n, c, h, w, k, ceil_mode, pre_scale, pre_shift, pre_relu, abits, stream);
 }
 
 extern "C" int bnn_pack_weight_f32(const float* w, int32_t c_out, int32_t c_in, int32_t kh, int32_t kw,

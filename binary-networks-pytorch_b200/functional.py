@@ -46,13 +46,13 @@ class PackedWeights:
 
 
 def pack_activations(x: torch.Tensor, linear_rows: bool = False, pre: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
-                     pool: int = 0, ceil_mode: bool = True) -> PackedActivations:
+                     pool: int = 0, ceil_mode: bool = True, pre_relu: bool = False) -> PackedActivations:
     """``BasicInputBinarizer`` (reference bnn/ops.py:151-152) as a bit-pack.
 
     ``x`` is [n,c,h,w] (any strides) or, with ``linear_rows``, [rows, features] which is packed
     as n=1, h=1, w=rows so that ``blinear`` can treat rows as pixels.  ``pre=(scale, shift)`` folds a
-    per-channel affine (eval BatchNorm) in front of the sign; ``pool=k`` first applies
-    AvgPool2d(k, k, ceil_mode, count_include_pad=False)."""
+    per-channel affine (eval BatchNorm) in front of the sign, ``pre_relu`` a ReLU between the two; ``pool=k``
+    first applies AvgPool2d(k, k, ceil_mode, count_include_pad=False)."""
     _require_cuda_f32(x, "input")
     if linear_rows:
         rows, feat = x.shape
@@ -71,10 +71,10 @@ def pack_activations(x: torch.Tensor, linear_rows: bool = False, pre: Optional[T
         bits = torch.empty((n, nch, ho, wo, 4), dtype=torch.int32, device=x.device)
         if pool > 1:
             rc = native.lib().bnn_avgpool_pack_f32(x.data_ptr(), sn, sc, sh, sw, n, c, h, w, pool, int(ceil_mode),
-                                                   ps, ph, bits.data_ptr(), _stream_ptr(x.device))
+                                                   ps, ph, int(pre_relu), bits.data_ptr(), _stream_ptr(x.device))
         else:
-            rc = native.lib().bnn_pack_act_f32(x.data_ptr(), sn, sc, sh, sw, n, c, h, w, ps, ph, bits.data_ptr(),
-                                               _stream_ptr(x.device))
+            rc = native.lib().bnn_pack_act_f32(x.data_ptr(), sn, sc, sh, sw, n, c, h, w, ps, ph, int(pre_relu),
+                                               bits.data_ptr(), _stream_ptr(x.device))
     native.check(rc, "bnn_pack_act_f32")
     return PackedActivations(bits, n, c, ho, wo)
 
@@ -164,7 +164,8 @@ def bconv2d(act: PackedActivations, wts: PackedWeights, bias: Optional[torch.Ten
 def bconv2d_fused(act: PackedActivations, wts: PackedWeights, *, bias=None, post=None, bn=None, residual=None,
                   residual_after_act: bool = False, activation: int = native.ACT_NONE, act_slope=None,
                   want_out: bool = True, want_bits: bool = False, nx=None, stride=(1, 1), padding=(0, 0),
-                  dilation=(1, 1), use_alpha: bool = True, flags: int = 0, channels_last: bool = False):
+                  dilation=(1, 1), use_alpha: bool = True, flags: int = 0, channels_last: bool = False,
+                  out: Optional[torch.Tensor] = None, nx_relu: bool = False, bits_before_residual: bool = False):
     """Binary convolution with the cross-module epilogue of ``struct bnn_epilogue``:
     ``y=(alpha*dot+bias)*post; z=y*bn[0]+bn[1]; (+residual); act; (+residual)`` -> fp32 ``out`` and/or the
     packed planes of ``sign(v*nx[0]+nx[1])`` for the next binarized layer.  Returns (out, PackedActivations).
@@ -190,11 +191,17 @@ def bconv2d_fused(act: PackedActivations, wts: PackedWeights, *, bias=None, post
     ep.residual_after_act, ep.act, ep.act_slope = int(residual_after_act), int(activation), _opt_ptr(act_slope)
     if nx is not None:
         ep.nx_scale, ep.nx_shift = nx[0].data_ptr(), nx[1].data_ptr()
-    out = bits = None
+    ep.nx_relu, ep.bits_before_residual = int(nx_relu), int(bits_before_residual)
+    bits = None
     with torch.cuda.device(dev):
-        if want_out:
+        if out is not None:                     # caller-provided view (e.g. a channel slice of a block output)
+            if tuple(out.shape) != (act.n, wts.c_out, ho, wo) or out.dtype != torch.float32 or not out.is_cuda:
+                raise native.NativeError(f"out must be a float32 CUDA tensor of shape {(act.n, wts.c_out, ho, wo)}")
+            want_out = True
+        elif want_out:
             out = torch.empty((act.n, wts.c_out, ho, wo), dtype=torch.float32, device=dev,
                               memory_format=torch.channels_last if channels_last else torch.contiguous_format)
+        if want_out:
             ep.out = out.data_ptr()
             ep.ostride_n, ep.ostride_c, ep.ostride_h, ep.ostride_w = out.stride()
         if want_bits:

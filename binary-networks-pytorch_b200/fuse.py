@@ -269,11 +269,94 @@ class FusedResNet(nn.Module):
             return m.fc(x)
 
 
+class _HBlockPlan:
+    """Hierarchical block (reference bnn/models/layers/hierarchical_block.py:8-60): three bn-ReLU-conv stages whose
+    outputs are concatenated, plus the shortcut.  Every conv input is relu(bn(.)), i.e. its planes are ``bn(.) > 0``."""
+
+    def __init__(self, block: nn.Module) -> None:
+        self.block, self.ok = block, False
+        names = ("bn1", "conv1", "act1", "bn2", "conv2", "act2", "bn3", "conv3", "act3")
+        if type(block).__name__ != "HBlock" or not all(hasattr(block, k) for k in names):
+            return
+        convs = [block.conv1, block.conv2, block.conv3]
+        bns = [block.bn1, block.bn2, block.bn3]
+        ok = all(_fusable_conv(c) for c in convs) and all(isinstance(b, nn.BatchNorm2d) and b.track_running_stats for b in bns)
+        ok = ok and all(isinstance(a, nn.ReLU) for a in (block.act1, block.act2, block.act3))
+        ok = ok and all(b.num_features == c.in_channels for b, c in zip(bns, convs))
+        ds = getattr(block, "downsample", None)
+        self.shortcut = None
+        if ok and ds is not None:
+            # the harness shortcut: BatchNorm -> ReLU -> binarized conv1x1 (SURVEY.md A.1.4)
+            good = (isinstance(ds, nn.Sequential) and len(ds) == 3 and isinstance(ds[0], nn.BatchNorm2d)
+                    and isinstance(ds[1], nn.ReLU) and _fusable_conv(ds[2]) and ds[0].track_running_stats)
+            ok = good
+            if good:
+                self.shortcut = (_FoldedBN(ds[0]), ds[2])
+        if ok:
+            self.ok = True
+            self.convs, self.bns = convs, [_FoldedBN(b) for b in bns]
+
+
+def run_hblock(plan: _HBlockPlan, x: torch.Tensor, bits=None) -> torch.Tensor:
+    """One fused HBlock on a channels_last fp32 tensor: 3 (+2 with a shortcut conv) launches after the input pack."""
+    if bits is None:
+        bits = BF.pack_activations(x, pre=plan.bns[0].get(), pre_relu=True)
+    if plan.shortcut is not None:
+        bn_d, conv_d = plan.shortcut
+        kw, wts = _conv_args(conv_d)
+        res, _ = BF.bconv2d_fused(BF.pack_activations(x, pre=bn_d.get(), pre_relu=True), wts, channels_last=True, **kw)
+    else:
+        res = x
+    n, _, h, w = x.shape
+    planes = sum(c.out_channels for c in plan.convs)
+    y = torch.empty((n, planes, h, w), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+    c0 = 0
+    for i, conv in enumerate(plan.convs):
+        kw, wts = _conv_args(conv)
+        sl = slice(c0, c0 + conv.out_channels)
+        nxt = plan.bns[i + 1].get() if i + 1 < len(plan.convs) else None
+        # block output slice = conv + shortcut slice; the next stage sees relu(bn(conv)) -> planes before the add
+        _, bits = BF.bconv2d_fused(bits, wts, residual=res[:, sl], residual_after_act=True, out=y[:, sl],
+                                   want_bits=nxt is not None, nx=nxt, nx_relu=True, bits_before_residual=True, **kw)
+        c0 += conv.out_channels
+    return y
+
+
+class FusedHBlockNet(nn.Module):
+    """Engine for the Hierarchical-Block harness of BASELINE configs[3] (``workloads.HBlockNet`` layout:
+    conv1/bn1/relu, block0, pool, blocks, avgpool, fc): fp32 stem and pooling stay torch ops, every HBlock is fused."""
+
+    def __init__(self, model: nn.Module) -> None:
+        super().__init__()
+        self.model = model
+        self.plans = [_HBlockPlan(model.block0)] + [_HBlockPlan(b) for b in model.blocks]
+
+    @property
+    def fused_blocks(self) -> int:
+        return sum(p.ok for p in self.plans)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        m = self.model
+        if m.training:
+            raise native.NativeError("FusedHBlockNet is an inference engine: call model.eval()")
+        with torch.no_grad():
+            x = m.relu(m.bn1(m.conv1(x))).contiguous(memory_format=torch.channels_last)
+            x = run_hblock(self.plans[0], x) if self.plans[0].ok else m.block0(x)
+            x = m.pool(x)
+            for plan in self.plans[1:]:
+                x = run_hblock(plan, x) if plan.ok else plan.block(x)
+            return m.fc(torch.flatten(m.avgpool(x), 1))
+
+
 def optimize(model: nn.Module, fuse_stem: bool = True) -> nn.Module:
     """Return the fused inference engine for ``model`` if its layout is recognised, else ``model``."""
     needed = ("conv1", "layer1", "layer2", "layer3", "layer4", "avgpool", "fc")
     if all(hasattr(model, k) for k in needed):
         engine = FusedResNet(model, fuse_stem=fuse_stem)
+        if engine.fused_blocks:
+            return engine
+    if all(hasattr(model, k) for k in ("conv1", "bn1", "relu", "block0", "pool", "blocks", "avgpool", "fc")):
+        engine = FusedHBlockNet(model)
         if engine.fused_blocks:
             return engine
     return model

@@ -31,7 +31,7 @@ class Epilogue(ctypes.Structure):
                 ("rstride_h", c_int64), ("rstride_w", c_int64), ("residual_after_act", c_int32), ("act", c_int32),
                 ("act_slope", c_void_p), ("out", c_void_p), ("ostride_n", c_int64), ("ostride_c", c_int64),
                 ("ostride_h", c_int64), ("ostride_w", c_int64), ("out_bits", c_void_p), ("nx_scale", c_void_p),
-                ("nx_shift", c_void_p)]
+                ("nx_shift", c_void_p), ("nx_relu", c_int32), ("bits_before_residual", c_int32)]
 
 
 ACT_NONE, ACT_RELU, ACT_PRELU = 0, 1, 2
@@ -42,9 +42,9 @@ _SIGNATURES = {
     "bnn_act_bits_bytes": (c_size_t, [c_int32] * 4),
     "bnn_weight_bits_bytes": (c_size_t, [c_int32] * 4),
     "bnn_pack_act_f32": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32,
-                                 c_void_p, c_void_p, c_void_p, c_void_p]),
+                                 c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
     "bnn_avgpool_pack_f32": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32,
-                                     c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                     c_int32, c_int32, c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
     "bnn_pack_weight_f32": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                                     c_void_p, c_void_p, c_void_p, c_void_p]),
     "bnn_bconv2d_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

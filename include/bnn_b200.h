@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define BNN_B200_ABI_VERSION 2
+#define BNN_B200_ABI_VERSION 3
 
 /* argument errors (negative); positive codes are cudaError_t */
 #define BNN_E_NULL        (-1)  /* required pointer is NULL                         */
@@ -81,11 +81,14 @@ size_t bnn_weight_bits_bytes(int32_t c_out, int32_t c_in, int32_t kh, int32_t kw
  * bit-pack: fp32 activations, addressed with ELEMENT strides (so NCHW,
  * channels_last and Linear's [rows,in] viewed as n=1,h=1,w=rows all fit),
  * -> abits (16-byte aligned).  pre_scale/pre_shift ([c], both or neither) fold an
- * eval-mode BatchNorm that sits in front of the layer: sign(x*pre_scale + pre_shift).
+ * eval-mode BatchNorm that sits in front of the layer: sign(x*pre_scale + pre_shift);
+ * pre_relu != 0 additionally puts a ReLU between that BatchNorm and the sign (bn -> relu -> conv,
+ * bnn/models/layers/hierarchical_block.py:41-43): negative values become 0, i.e. m = s.
  */
 int bnn_pack_act_f32(const float *x, int64_t stride_n, int64_t stride_c, int64_t stride_h,
                      int64_t stride_w, int32_t n, int32_t c, int32_t h, int32_t w,
-                     const float *pre_scale, const float *pre_shift, void *abits, void *stream);
+                     const float *pre_scale, const float *pre_shift, int32_t pre_relu,
+                     void *abits, void *stream);
 
 /*
  * AvgPool2d(kernel = stride = k, ceil_mode, count_include_pad = False) followed by the
@@ -96,7 +99,7 @@ int bnn_pack_act_f32(const float *x, int64_t stride_n, int64_t stride_c, int64_t
 int bnn_avgpool_pack_f32(const float *x, int64_t stride_n, int64_t stride_c, int64_t stride_h,
                          int64_t stride_w, int32_t n, int32_t c, int32_t h, int32_t w,
                          int32_t k, int32_t ceil_mode, const float *pre_scale,
-                         const float *pre_shift, void *abits, void *stream);
+                         const float *pre_shift, int32_t pre_relu, void *abits, void *stream);
 
 /*
  * XNORWeightBinarizer.forward (bnn/ops.py:129-140) as a prepare-time pack:
@@ -134,6 +137,9 @@ int bnn_bconv2d_fwd(const void *abits, const void *wbits,
  *     out      <- v                 fp32, element strides; skipped if out == NULL
  *     out_bits <- planes of sign(v * nx_scale[co] + nx_shift[co])   (next layer's input, in the
  *                 abits layout for [n, c_out, ho, wo]; nx_* NULL = identity; skipped if NULL)
+ *                 nx_relu: a ReLU sits between that BatchNorm and the sign (m = s);
+ *                 bits_before_residual: take v before the after-activation residual add (HBlock:
+ *                 the next conv sees the conv output, the block output adds the shortcut)
  * In this fused mode the per-channel constants are folded once per launch --
  *     k0 = scale*post*bn_scale,  k1 = (bias*post)*bn_scale + bn_shift,  z = fma(k0, dot, k1)
  * -- the next-layer affine is one fma, and ReLU is fmaxf(z, 0); oracle/bnn_oracle.c restates it
@@ -151,6 +157,8 @@ typedef struct bnn_epilogue {
     int64_t ostride_n, ostride_c, ostride_h, ostride_w;
     void *out_bits;
     const float *nx_scale, *nx_shift;
+    int32_t nx_relu;
+    int32_t bits_before_residual;
 } bnn_epilogue;
 
 #define BNN_ACT_NONE  0

@@ -173,12 +173,13 @@ int64_t orc_weight_words(int c_out, int c_in, int kh, int kw) {
  * pool > 1: v is first the AvgPool2d(kernel=stride=pool, ceil_mode, count_include_pad=False)
  * of x (bnn/models/resnet.py:129-133), summed row-major and divided by the in-bounds count;
  * pre_scale/pre_shift (may be NULL): v = v*pre_scale[c] + pre_shift[c] (an eval BatchNorm in
- * front of the binarized layer, e.g. PreBasicBlock.bn1, res_block.py:152-154).
+ * front of the binarized layer, e.g. PreBasicBlock.bn1, res_block.py:152-154); pre_relu: a ReLU
+ * between that BatchNorm and the sign (HBlock, hierarchical_block.py:41-43).
  * h, w are the INPUT plane size; the output plane is ho x wo.
  */
 void orc_pack_act(const float *x, int64_t sn, int64_t sc, int64_t sh, int64_t sw,
                   int n, int c, int h, int w, int pool, int ceil_mode,
-                  const float *pre_scale, const float *pre_shift, uint32_t *abits) {
+                  const float *pre_scale, const float *pre_shift, int pre_relu, uint32_t *abits) {
     const int nch = (c + 63) / 64;
     const int k = pool > 1 ? pool : 1;
     const int ho = pool > 1 ? (ceil_mode ? (h + k - 1) / k : h / k) : h;
@@ -205,7 +206,7 @@ void orc_pack_act(const float *x, int64_t sn, int64_t sc, int64_t sh, int64_t sw
                             v = sum / (float)cnt;
                         }
                         if (pre_scale) v = v * pre_scale[ci] + pre_shift[ci];
-                        const uint32_t pos = v > 0.0f, neg = v < 0.0f;
+                        const uint32_t pos = v > 0.0f, neg = (v < 0.0f) && !pre_relu;   /* bn -> relu -> sign */
                         u[b >> 5] |= pos << (b & 31);
                         u[2 + (b >> 5)] |= (pos | neg) << (b & 31);
                     }
@@ -266,6 +267,7 @@ typedef struct {
     int64_t on, oc, oh, ow;
     uint32_t *out_bits;
     const float *nx_scale, *nx_shift;
+    int32_t nx_relu, bits_before_residual;
 } orc_epilogue;
 
 void orc_bconv2d_fused(const uint32_t *abits, const uint32_t *wbits, const orc_geom *g, const orc_epilogue *e) {
@@ -291,7 +293,7 @@ void orc_bconv2d_fused(const uint32_t *abits, const uint32_t *wbits, const orc_g
                                 dis += popc32(u[2] & (u[0] ^ t[0])) + popc32(u[3] & (u[1] ^ t[1]));
                             }
                     const int fused = e->bn_scale || e->residual || e->act != 0 || e->out_bits || e->nx_scale;
-                    float y;
+                    float y, ybits = 0.0f;
                     if (!fused) {
                         /* reference order, conv.py:92-97 + ops.py:136,202 */
                         y = (e->scale ? e->scale[co] : 1.0f) * (float)(msum - 2 * dis);
@@ -312,12 +314,15 @@ void orc_bconv2d_fused(const uint32_t *abits, const uint32_t *wbits, const orc_g
                         y = y + (e->residual_after_act ? 0.0f : r);
                         if (e->act == 1) y = fmaxf(y, 0.0f);
                         else if (e->act == 2) y = (y > 0.0f) ? y : e->act_slope[co] * y;
+                        ybits = y;            /* value before the after-activation shortcut add */
                         y = y + (e->residual_after_act ? r : 0.0f);
+                        if (!(e->residual && e->residual_after_act && e->bits_before_residual)) ybits = y;
                     }
                     if (e->out) e->out[n * e->on + co * e->oc + ho * e->oh + wo * e->ow] = y;
                     if (e->out_bits) {
-                        float b = y;
+                        float b = fused ? ybits : y;
                         if (e->nx_scale) b = fmaf(e->nx_scale[co], b, e->nx_shift[co]);
+                        if (e->nx_relu && b < 0.0f) b = 0.0f;
                         uint32_t *u = e->out_bits + ((((int64_t)n * ochunks + co / 64) * ho_n + ho) * wo_n + wo) * 4;
                         const int bit = co % 64;
                         if (b > 0.0f) u[bit >> 5] |= 1u << (bit & 31);

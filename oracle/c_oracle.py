@@ -60,7 +60,7 @@ def floatsim_linear(x, w, bias, post, center: bool, compute_alpha: bool):
     return out
 
 
-def pack_act(x, pool=0, ceil_mode=True, pre_scale=None, pre_shift=None):
+def pack_act(x, pool=0, ceil_mode=True, pre_scale=None, pre_shift=None, pre_relu=False):
     """x: float32 [n,c,h,w] (any numpy strides) -> abits uint32 [n,chunks,ho,wo,4]."""
     x = np.asarray(x, dtype=np.float32)
     n, c, h, w = x.shape
@@ -72,7 +72,7 @@ def pack_act(x, pool=0, ceil_mode=True, pre_scale=None, pre_shift=None):
     abits = np.zeros((n, nch, ho, wo, 4), np.uint32)
     pre_scale, pre_shift = _f32(pre_scale), _f32(pre_shift)
     lib().orc_pack_act(_p(x), c_int64(sn), c_int64(sc), c_int64(sh), c_int64(sw), n, c, h, w, int(pool),
-                       int(ceil_mode), _p(pre_scale), _p(pre_shift), _p(abits))
+                       int(ceil_mode), _p(pre_scale), _p(pre_shift), int(pre_relu), _p(abits))
     return abits
 
 
@@ -118,11 +118,13 @@ class Epilogue(ctypes.Structure):
                 ("bn_shift", c_void_p), ("residual", c_void_p), ("rn", c_int64), ("rc", c_int64), ("rh", c_int64),
                 ("rw", c_int64), ("residual_after_act", c_int32), ("act", c_int32), ("act_slope", c_void_p),
                 ("out", c_void_p), ("on", c_int64), ("oc", c_int64), ("oh", c_int64), ("ow", c_int64),
-                ("out_bits", c_void_p), ("nx_scale", c_void_p), ("nx_shift", c_void_p)]
+                ("out_bits", c_void_p), ("nx_scale", c_void_p), ("nx_shift", c_void_p), ("nx_relu", c_int32),
+                ("bits_before_residual", c_int32)]
 
 
 def bconv2d_fused(abits, wbits, g: Geom, scale=None, bias=None, post=None, bn=None, residual=None,
-                  residual_after_act=False, act=0, act_slope=None, want_out=True, want_bits=False, nx=None):
+                  residual_after_act=False, act=0, act_slope=None, want_out=True, want_bits=False, nx=None,
+                  nx_relu=False, bits_before_residual=False):
     """Fused epilogue (struct bnn_epilogue). bn / nx: (scale, shift) pairs. Returns (out or None, bits or None)."""
     ho, wo = out_hw(g)
     keep = [_f32(a) for a in (scale, bias, post, None if bn is None else bn[0], None if bn is None else bn[1],
@@ -140,6 +142,7 @@ def bconv2d_fused(abits, wbits, g: Geom, scale=None, bias=None, post=None, bn=No
         e.out = _v(out)
         e.on, e.oc, e.oh, e.ow = (s // 4 for s in out.strides)
     e.out_bits, e.nx_scale, e.nx_shift = _v(bits), _v(nxs), _v(nxh)
+    e.nx_relu, e.bits_before_residual = int(nx_relu), int(bits_before_residual)
     lib().orc_bconv2d_fused(_p(abits), _p(wbits), ctypes.byref(g), ctypes.byref(e))
     return out, bits
 

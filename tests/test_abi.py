@@ -36,11 +36,11 @@ def test_size_helpers_and_errors_without_gpu():
     assert lib.bnn_act_bits_bytes(1, 65, 1, 1) == 2 * 16
     assert lib.bnn_weight_bits_bytes(33, 64, 3, 3) == 2 * 9 * 32 * 8
     assert lib.bnn_act_bits_bytes(0, 1, 1, 1) == 0
-    assert native.query(native.Q_ABI_VERSION) == 2
+    assert native.query(native.Q_ABI_VERSION) == 3
     assert native.query(native.Q_SM_ARCH) == 100
     assert b"NULL" in lib.bnn_strerror(-1)
     # argument errors are reported before any CUDA call
-    assert lib.bnn_pack_act_f32(None, 0, 0, 0, 0, 1, 1, 1, 1, None, None, None, None) == -1
+    assert lib.bnn_pack_act_f32(None, 0, 0, 0, 0, 1, 1, 1, 1, None, None, 0, None, None) == -1
     assert lib.bnn_pack_weight_f32(None, 1, 1, 1, 1, 0, 1, None, None, None, None) == -1
     assert lib.bnn_bconv2d_fwd(None, None, None, None, None, None, 0, 0, 0, 0, None, 0, None) == -1
     g = native.ConvGeom(1, 64, 4, 4, 64, 3, 3, 0, 1, 1, 1, 1, 1)   # stride 0

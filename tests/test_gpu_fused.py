@@ -40,19 +40,22 @@ def test_fused_epilogue_bit_exact_vs_oracle(fc, flags):
     alpha_dev = wts.alpha.cpu().numpy()
     want_out, want_bits = co.bconv2d_fused(ab, wb, g, scale=alpha_dev, bias=d["bias"], post=d["post"], bn=d["bn"],
                                            residual=d["residual"], residual_after_act=d["res_after"], act=d["act"],
-                                           act_slope=d["slope"], want_out=True, want_bits=True, nx=d["nx"])
+                                           act_slope=d["slope"], want_out=True, want_bits=True, nx=d["nx"], nx_relu=d["nx_relu"],
+                                           bits_before_residual=d["bits_pre"])
     pair = lambda p: None if p is None else (_d(p[0]), _d(p[1]))
     out, bits = BF.bconv2d_fused(act, wts, bias=_d(d["bias"]), post=_d(d["post"]), bn=pair(d["bn"]),
                                  residual=_d(d["residual"]), residual_after_act=d["res_after"], activation=d["act"],
                                  act_slope=_d(d["slope"]), want_out=True, want_bits=True, nx=pair(d["nx"]),
-                                 stride=(g.stride_h, g.stride_w), padding=(g.pad_h, g.pad_w), flags=flags)
+                                 stride=(g.stride_h, g.stride_w), padding=(g.pad_h, g.pad_w), flags=flags,
+                                 nx_relu=d["nx_relu"], bits_before_residual=d["bits_pre"])
     assert np.array_equal(out.cpu().numpy(), want_out)
     assert np.array_equal(bits.bits.cpu().numpy().view(np.uint32), want_bits)
     # bits only (no fp32 store) and out only give the same planes / values
     _, bits2 = BF.bconv2d_fused(act, wts, bias=_d(d["bias"]), post=_d(d["post"]), bn=pair(d["bn"]),
                                 residual=_d(d["residual"]), residual_after_act=d["res_after"], activation=d["act"],
                                 act_slope=_d(d["slope"]), want_out=False, want_bits=True, nx=pair(d["nx"]),
-                                stride=(g.stride_h, g.stride_w), padding=(g.pad_h, g.pad_w), flags=flags)
+                                stride=(g.stride_h, g.stride_w), padding=(g.pad_h, g.pad_w), flags=flags,
+                                nx_relu=d["nx_relu"], bits_before_residual=d["bits_pre"])
     assert torch.equal(bits2.bits, bits.bits)
 
 
@@ -177,11 +180,41 @@ def test_fused_engine_resnet50_blocks(pre):
     assert rel_err(eager, want) <= 1e-3
 
 
-def test_unrecognised_models_are_returned_unchanged():
+def test_fused_hblock_net_matches_twin_and_unfused():
+    """BASELINE configs[3] through the fused engine: HBlock stages write channel slices of the block output,
+    add the shortcut slice, and hand relu(bn(conv)) planes (taken before the add) to the next stage."""
     torch.manual_seed(0)
-    m = workloads.HBlockNet(depth=1)
-    m = bnn.prepare_binary_model(m, xnor_cfg(), ignore_layers_name=["_first_", "_last_"]).eval().to(DEV)
+    m = workloads.HBlockNet(depth=2)
+    m = bnn.prepare_binary_model(m, xnor_cfg(), ignore_layers_name=["_first_", "_last_"])
+    workloads.randomize_batchnorm(m, seed=1)
+    m = m.eval()
+    twin = fs.mirror_model(m)
+    engine = fuse.optimize(m.to(DEV))
+    assert isinstance(engine, fuse.FusedHBlockNet) and engine.fused_blocks == 3
+    x = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(4))
+    with torch.no_grad():
+        want = twin(x).numpy()
+        got = engine(x.to(DEV)).cpu().numpy()
+        eager = m(x.to(DEV)).cpu().numpy()
+    print("hblock fused vs twin", rel_err(got, want), "unfused vs twin", rel_err(eager, want))
+    assert rel_err(got, want) <= 1e-3 and rel_err(eager, want) <= 1e-3
+
+
+def test_unrecognised_models_are_returned_unchanged():
+    m = nn.Sequential(nn.Conv2d(3, 64, 3), nn.ReLU(), nn.Conv2d(64, 64, 3))
+    m = bnn.prepare_binary_model(m, xnor_cfg(), ignore_layers_name=["_first_"]).eval().to(DEV)
     assert fuse.optimize(m) is m
+
+
+def test_pack_with_relu_in_front_of_the_sign():
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal((2, 96, 6, 7)).astype(np.float32)
+    s_, h_ = (0.5 + rng.random(96)).astype(np.float32), rng.standard_normal(96).astype(np.float32)
+    want = co.pack_act(x, pre_scale=s_, pre_shift=h_, pre_relu=True)
+    assert np.array_equal(want[..., :2], want[..., 2:])                      # relu-fed: mask == sign plane
+    for t in (_d(x), _d(x).contiguous(memory_format=torch.channels_last)):
+        got = BF.pack_activations(t, pre=(_d(s_), _d(h_)), pre_relu=True)
+        assert np.array_equal(got.bits.cpu().numpy().view(np.uint32), want)
 
 
 def test_host_pipeline_returns_the_same_logits_in_order():

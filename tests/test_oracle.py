@@ -184,6 +184,7 @@ FUSED_CASES = [
     dict(name="shortcut", cin=64, cout=128, hw=(8, 8), k=1, pad=0, bn=True, out=True, bits=False),
     dict(name="ragged_c1", cin=70, cout=24, hw=(6, 5), bn=True, act=1, res="pre", bits=True, out=True, bias=True, post=True),
     dict(name="c96_s2", cin=64, cout=96, hw=(10, 10), stride=2, bn=True, act=2, bits=True, out=True, nx=True),
+    dict(name="hblock_stage", cin=128, cout=64, hw=(8, 8), res="post", bits=True, out=True, nx=True, nx_relu=True, bits_pre=True),
 ]
 
 
@@ -205,7 +206,8 @@ def make_fused_inputs(fc):
              res_after=fc.get("res") == "post", act=fc.get("act", 0),
              slope=(rng.random(co_) * 0.5).astype(np.float32) if fc.get("act", 0) == 2 else None,
              nx=((0.5 + rng.random(co_)).astype(np.float32), (rng.standard_normal(co_) * 0.2).astype(np.float32)) if fc.get("nx") else None,
-             want_out=fc.get("out", True), want_bits=fc.get("bits", False))
+             want_out=fc.get("out", True), want_bits=fc.get("bits", False), nx_relu=bool(fc.get("nx_relu")),
+             bits_pre=bool(fc.get("bits_pre")))
     return d
 
 
@@ -220,7 +222,7 @@ def test_fused_epilogue_oracle_against_torch_composition(fc):
     assert nz == 0
     out, bits = co.bconv2d_fused(ab, wb, g, scale=alpha, bias=d["bias"], post=d["post"], bn=d["bn"], residual=d["residual"],
                                  residual_after_act=d["res_after"], act=d["act"], act_slope=d["slope"], want_out=True,
-                                 want_bits=True, nx=d["nx"])
+                                 want_bits=True, nx=d["nx"], nx_relu=d["nx_relu"], bits_before_residual=d["bits_pre"])
     y = fs.conv2d(_t(d["x"]), _t(d["w"]), _t(d["bias"]), _t(d["post"]), (g.stride_h, g.stride_w), (g.pad_h, g.pad_w),
                   (1, 1), True, True)
     v = lambda a: _t(a).view(1, -1, 1, 1)
@@ -232,9 +234,15 @@ def test_fused_epilogue_oracle_against_torch_composition(fc):
         y = torch.relu(y)
     elif d["act"] == 2:
         y = torch.nn.functional.prelu(y, _t(d["slope"]))
+    y_before = y
     if d["residual"] is not None and d["res_after"]:
         y = y + _t(d["residual"])
     assert rel_err(out, y.numpy()) <= 1e-5
+    if d["bits_pre"]:
+        # HBlock stage: the next conv sees relu(bn(conv)); the block output is conv + shortcut
+        nb = torch.relu(y_before * v(d["nx"][0]) + v(d["nx"][1])).numpy()
+        assert (bits != co.pack_act(nb)).sum() <= 2          # fma vs mul+add at the knife edge
+        return
     # emitted planes are the bit-pack of the oracle's own fp32 result (with the next layer's affine, which the
     # epilogue applies as one fma while the stand-alone pack rounds the product first: identical except when
     # the affine lands within an ulp of zero)
