@@ -237,6 +237,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA graph")
     ap.add_argument("--no-fuse", action="store_true", help="per-layer kernels + torch glue (no cross-module fusion)")
+    ap.add_argument("--stem", default="mma", choices=["mma", "fma"],
+                    help="fused engine's stem kernel: mma.sync split-fp16 (default) or the fp32 fma chain")
     ap.add_argument("--layers-out", default=None, help="write the per-layer table to this JSON file")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -269,7 +271,7 @@ def main():
     algo = layer_algorithmics(model_cpu, args.batch, RES)
     model = model_cpu.to(dev)
     from bnn_b200 import fuse
-    engine = model if args.no_fuse else fuse.optimize(model)       # public API: bnn_b200.fuse.optimize(model)
+    engine = model if args.no_fuse else fuse.optimize(model, stem=args.stem)   # public API: bnn_b200.fuse.optimize
     B = args.batch
     x_dev = torch.randn(B, 3, RES, RES, device=dev)       # 154 MB at bs256 > 126 MB L2
     x_host = torch.randn(B, 3, RES, RES).pin_memory()
@@ -458,7 +460,8 @@ def main():
                    "launch": "cuda_graph" if graph is not None else "eager",
                    "fusion": "per-layer" if args.no_fuse else "bnn_b200.fuse.optimize (BN/act/residual/sign in conv epilogues)",
                    "glue": ("torch fp32 (TF32 off): stem conv7x7+BN+ReLU+maxpool, BN/act/add per layer, avgpool, fc"
-                            if args.no_fuse else "stem = bnn_stem_fwd; torch fp32 only for global avgpool + fc")},
+                            if args.no_fuse else f"stem = {'bnn_stem_mma_fwd' if args.stem == 'mma' else 'bnn_stem_fwd'}; "
+                                              "torch fp32 only for global avgpool + fc")},
         "clocks": clocks,
         "e2e": {"value": images / (ms_e2e / args.steps * 1e-3), "unit": "images/s",
                 "h2d_bytes_per_step": B * 3 * RES * RES * 4 * world, "d2h_bytes_per_step": images * 1000 * 4 * world,

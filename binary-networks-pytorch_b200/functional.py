@@ -3,6 +3,7 @@ current CUDA stream.  torch is plumbing here (device memory + streams); all arit
 binarized path happens in the kernels of csrc/.
 """
 import ctypes
+import math
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -256,6 +257,53 @@ def stem(x: torch.Tensor, w_t: torch.Tensor, bn: Tuple[torch.Tensor, torch.Tenso
                                        None if nx is None else nx[1].data_ptr(), out.data_ptr(),
                                        None if bits is None else bits.data_ptr(), flags, _stream_ptr(dev))
     native.check(rc, "bnn_stem_fwd")
+    return out, (None if bits is None else PackedActivations(bits, n, 64, hp, wp))
+
+
+STEM_X_LOG2_SCALE = 7          # inputs up to |x| < 511 stay inside the fp16 range (raw 0..255 pixels included)
+
+
+def stem_mma_weights(w: torch.Tensor):
+    """[64,3,7,7] fp32 conv weight -> (fragment buffer, w_log2_scale) for ``stem_mma`` (bnn_stem_mma_pack_weight).
+    The scale puts max|w| just below 2^14, well inside the fp16 range.  One host sync (prepare time only)."""
+    _require_cuda_f32(w, "stem weight")
+    if tuple(w.shape) != (64, 3, 7, 7):
+        raise native.NativeError(f"stem weight must be [64,3,7,7], got {tuple(w.shape)}")
+    w = w.detach().contiguous()
+    wmax = float(w.abs().max())
+    if not math.isfinite(wmax):
+        raise native.NativeError("stem weight has non-finite values")
+    log2_scale = 0 if wmax == 0.0 else max(-60, min(60, 13 - math.frexp(wmax)[1]))
+    dev = w.device
+    with torch.cuda.device(dev):
+        frag = torch.empty(native.lib().bnn_stem_mma_weight_bytes() // 4, dtype=torch.int32, device=dev)
+        rc = native.lib().bnn_stem_mma_pack_weight(w.data_ptr(), log2_scale, frag.data_ptr(), _stream_ptr(dev))
+    native.check(rc, "bnn_stem_mma_pack_weight")
+    return frag, log2_scale
+
+
+def stem_mma(x: torch.Tensor, wfrag, bn: Tuple[torch.Tensor, torch.Tensor], nx=None, want_bits: bool = True,
+             x_log2_scale: int = STEM_X_LOG2_SCALE, flags: int = 0):
+    """``stem`` on the mma.sync path (split-fp16 operands, fp32-level accuracy; see include/bnn_b200.h).
+    ``wfrag`` = ``stem_mma_weights(conv.weight)``.  Same outputs as ``stem``."""
+    _require_cuda_f32(x, "input")
+    if x.dim() != 4 or x.shape[1] != 3 or not x.is_contiguous():
+        raise native.NativeError(f"stem expects a contiguous [n,3,h,w] tensor, got {tuple(x.shape)}")
+    frag, w_log2_scale = wfrag
+    n, _, h, w = x.shape
+    hp, wp = ctypes.c_int32(0), ctypes.c_int32(0)
+    native.check(native.lib().bnn_stem_out_hw(h, w, ctypes.byref(hp), ctypes.byref(wp)), "bnn_stem_out_hw")
+    hp, wp = hp.value, wp.value
+    dev = x.device
+    with torch.cuda.device(dev):
+        out = torch.empty((n, 64, hp, wp), dtype=torch.float32, device=dev, memory_format=torch.channels_last)
+        bits = torch.empty((n, 1, hp, wp, 4), dtype=torch.int32, device=dev) if want_bits else None
+        rc = native.lib().bnn_stem_mma_fwd(x.data_ptr(), n, h, w, frag.data_ptr(), x_log2_scale, w_log2_scale,
+                                           bn[0].data_ptr(), bn[1].data_ptr(),
+                                           None if nx is None else nx[0].data_ptr(),
+                                           None if nx is None else nx[1].data_ptr(), out.data_ptr(),
+                                           None if bits is None else bits.data_ptr(), flags, _stream_ptr(dev))
+    native.check(rc, "bnn_stem_mma_fwd")
     return out, (None if bits is None else PackedActivations(bits, n, 64, hp, wp))
 
 

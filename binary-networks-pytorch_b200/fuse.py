@@ -162,6 +162,7 @@ class _StemPlan:
         if good:
             self.ok, self.conv, self.bn = True, conv, _FoldedBN(bn)
             self.key, self.w_t = None, None
+            self.mma_key, self.mma_w = None, None
 
     def weight(self) -> torch.Tensor:
         w = self.conv.weight
@@ -172,13 +173,25 @@ class _StemPlan:
             self.key = key
         return self.w_t
 
+    def mma_weight(self):
+        """(fragment buffer, log2 scale) for the mma.sync stem kernel, cached per weight version."""
+        w = self.conv.weight
+        key = (w.data_ptr(), w._version)
+        if key != self.mma_key:
+            self.mma_w = BF.stem_mma_weights(w)
+            self.mma_key = key
+        return self.mma_w
+
 
 class FusedResNet(nn.Module):
     """Inference engine over a prepared ResNet; same call signature as the wrapped model."""
 
-    def __init__(self, model: nn.Module, fuse_stem: bool = True) -> None:
+    def __init__(self, model: nn.Module, fuse_stem: bool = True, stem: str = "mma") -> None:
         super().__init__()
+        if stem not in ("mma", "fma"):
+            raise ValueError(f"stem must be 'mma' (mma.sync, split fp16) or 'fma' (fp32 fma chain), got {stem!r}")
         self.model = model
+        self.stem_kernel = stem
         blocks: List[nn.Module] = []
         for name in ("layer1", "layer2", "layer3", "layer4"):
             blocks += list(getattr(model, name))
@@ -252,8 +265,12 @@ class FusedResNet(nn.Module):
             if (self.stem is not None and self.stem.ok and first is not None and first.fused and x.is_cuda
                     and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == 3 and min(x.shape[2:]) >= 7):
                 # fp32 stem in one kernel: NHWC residual stream + the first binarized conv's planes
-                x, bits = BF.stem(x.contiguous(), self.stem.weight(), self.stem.bn.get(), nx=self._entry_affine(first),
-                                  flags=runtime.kernel_flags())
+                if self.stem_kernel == "mma":
+                    x, bits = BF.stem_mma(x.contiguous(), self.stem.mma_weight(), self.stem.bn.get(),
+                                          nx=self._entry_affine(first))
+                else:
+                    x, bits = BF.stem(x.contiguous(), self.stem.weight(), self.stem.bn.get(),
+                                      nx=self._entry_affine(first), flags=runtime.kernel_flags())
             else:
                 x = m.conv1(x)
                 if getattr(m, "stem_type", "basic") == "basic" and hasattr(m, "bn1"):
@@ -348,11 +365,13 @@ class FusedHBlockNet(nn.Module):
             return m.fc(torch.flatten(m.avgpool(x), 1))
 
 
-def optimize(model: nn.Module, fuse_stem: bool = True) -> nn.Module:
-    """Return the fused inference engine for ``model`` if its layout is recognised, else ``model``."""
+def optimize(model: nn.Module, fuse_stem: bool = True, stem: str = "mma") -> nn.Module:
+    """Return the fused inference engine for ``model`` if its layout is recognised, else ``model``.
+    ``stem``: "mma" = the stem kernel on mma.sync with split-fp16 operands (fp32-level accuracy, default),
+    "fma" = the fp32 fma-chain stem kernel (bit-identical to the oracle's summation order)."""
     needed = ("conv1", "layer1", "layer2", "layer3", "layer4", "avgpool", "fc")
     if all(hasattr(model, k) for k in needed):
-        engine = FusedResNet(model, fuse_stem=fuse_stem)
+        engine = FusedResNet(model, fuse_stem=fuse_stem, stem=stem)
         if engine.fused_blocks:
             return engine
     if all(hasattr(model, k) for k in ("conv1", "bn1", "relu", "block0", "pool", "blocks", "avgpool", "fc")):

@@ -213,12 +213,32 @@ int bnn_stem_fwd(const float *x, int32_t n, int32_t h, int32_t w, const float *w
                  const float *nx_shift, float *out, void *out_bits, uint32_t flags, void *stream);
 
 /*
+ * The same stem on the legacy tensor path (mma.sync m16n8k16 f16, fp32 accumulate) with fp32-level accuracy:
+ * both operands are split into (hi, lo) fp16 pairs of x*2^x_log2_scale and w*2^w_log2_scale (22 significand bits
+ * each), the products hi*hi + hi*lo + lo*hi are exact in fp32, and each 16-tap partial sum is added to the running
+ * sum with a round-to-nearest fp32 add -- total error at the level of an fp32 fma chain over the 147 taps, but NOT
+ * bit-identical to bnn_stem_fwd (different summation order).  Operands must stay inside the fp16 range:
+ * |x| * 2^x_log2_scale < 65504 and |w| * 2^w_log2_scale < 65504 (choose w_log2_scale from max|w|).
+ * w_frag: bnn_stem_mma_weight_bytes() bytes, 16-byte aligned, written by bnn_stem_mma_pack_weight from the plain
+ * [64,3,7,7] fp32 conv weight (mma B fragments in k-step / n-tile / lane order).  bn_scale / bn_shift 8-byte aligned.
+ * Everything else as bnn_stem_fwd.
+ */
+size_t bnn_stem_mma_weight_bytes(void);
+int bnn_stem_mma_pack_weight(const float *w, int32_t w_log2_scale, void *w_frag, void *stream);
+int bnn_stem_mma_fwd(const float *x, int32_t n, int32_t h, int32_t w, const void *w_frag,
+                     int32_t x_log2_scale, int32_t w_log2_scale, const float *bn_scale, const float *bn_shift,
+                     const float *nx_scale, const float *nx_shift, float *out, void *out_bits, uint32_t flags,
+                     void *stream);
+
+/*
  * Integer-pipe micro-benchmarks used for the popcount roofline denominator
  * (bench.py): runs `which` on every SM and returns achieved giga-operations/s
  * (warp-lane operations) in *gops.  Synchronises the device.  which:
  *   0 POPC only   1 LOP3 only   2 LOP3+POPC+IADD (one word per POPC)
  *   3 3:2 carry-save (5 LOP3 + 2 POPC per 3 words)   4 7:3 carry-save
  * For 2..4 the figure is 32-bit XNOR-popcount WORDS per second.
+ * Floating-point rates behind the stem kernels, in giga multiply-adds / s:
+ *   5 mma.sync m16n8k8 tf32   6 mma.sync m16n8k16 f16   7 mma.sync m16n8k16 bf16   8 fma.rn.f32x2   9 fma.rn.f32
  */
 int bnn_ubench(int32_t which, int32_t iters, double *gops);
 

@@ -93,6 +93,52 @@ def test_stem_kernel_bit_exact_vs_oracle(hw, flags):
         assert np.array_equal(bits.bits.cpu().numpy().view(np.uint32), want_bits)
 
 
+def _stem_f64(x, w, g, h):
+    """float64 conv7x7/2/3 -> folded BN -> ReLU -> maxpool3/2/1, NHWC (the yardstick for both stem kernels)."""
+    y = torch.nn.functional.conv2d(torch.from_numpy(x).double(), torch.from_numpy(w).double(), stride=2, padding=3)
+    y = torch.relu(y * torch.from_numpy(g).double().view(1, -1, 1, 1) + torch.from_numpy(h).double().view(1, -1, 1, 1))
+    return torch.nn.functional.max_pool2d(y, 3, 2, 1).permute(0, 2, 3, 1).numpy()
+
+
+@pytest.mark.parametrize("hw,xscale", [((64, 64), 1.0), ((224, 224), 1.0), ((37, 52), 1.0), ((30, 30), 1.0),
+                                       ((64, 64), 100.0), ((64, 64), 1e-3)])
+def test_stem_mma_kernel_fp32_accuracy(hw, xscale):
+    """The mma.sync stem (split-fp16 operands) is as accurate as the fp32 fma-chain stem against a float64
+    convolution, and its planes are exactly the planes of the fp32 tensor it returns."""
+    rng = np.random.default_rng(6)
+    x = (rng.standard_normal((2, 3) + hw) * xscale).astype(np.float32)
+    w = (rng.standard_normal((64, 3, 7, 7)) * 0.1).astype(np.float32)
+    g, h = ((0.5 + rng.random(64)) / xscale).astype(np.float32), (rng.standard_normal(64) * 0.3).astype(np.float32)
+    nx = ((0.5 + rng.random(64)).astype(np.float32), (rng.standard_normal(64) * 0.2).astype(np.float32))
+    exact = _stem_f64(x, w, g, h)
+    scale = np.abs(exact).max()
+    fma, _ = BF.stem(_d(x), BF.stem_weight_layout(_d(w)), (_d(g), _d(h)))
+    err_fma = np.abs(fma.permute(0, 2, 3, 1).cpu().numpy() - exact).max() / scale
+    wfrag = BF.stem_mma_weights(_d(w))
+    for nxa in (None, nx):
+        out, bits = BF.stem_mma(_d(x), wfrag, (_d(g), _d(h)), nx=None if nxa is None else (_d(nxa[0]), _d(nxa[1])))
+        assert out.shape == (2, 64) + exact.shape[1:3] and out.is_contiguous(memory_format=torch.channels_last)
+        got = out.permute(0, 2, 3, 1).cpu().numpy()
+        err_mma = np.abs(got - exact).max() / scale
+        print(f"stem {hw} x{xscale}: max err / max|y| vs float64: mma {err_mma:.2e}  fma chain {err_fma:.2e}")
+        assert err_mma <= max(3.0 * err_fma, 3e-7)
+        nchw = np.ascontiguousarray(got.transpose(0, 3, 1, 2))
+        want_bits = co.pack_act(nchw) if nxa is None else co.pack_act(nchw, pre_scale=nxa[0], pre_shift=nxa[1])
+        assert np.array_equal(bits.bits.cpu().numpy().view(np.uint32), want_bits)
+
+
+def test_stem_mma_rejects_bad_arguments():
+    w = torch.randn(64, 3, 7, 7, device=DEV) * 0.1
+    wfrag = BF.stem_mma_weights(w)
+    g, h = torch.ones(64, device=DEV), torch.zeros(64, device=DEV)
+    with pytest.raises(native.NativeError):
+        BF.stem_mma(torch.randn(1, 3, 5, 5, device=DEV), wfrag, (g, h))            # smaller than the kernel
+    with pytest.raises(native.NativeError):
+        BF.stem_mma(torch.randn(1, 4, 32, 32, device=DEV), wfrag, (g, h))          # not 3 channels
+    with pytest.raises(native.NativeError):
+        BF.stem_mma_weights(torch.randn(32, 3, 7, 7, device=DEV))
+
+
 @pytest.fixture(autouse=True)
 def _fp32_glue():
     prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
@@ -117,8 +163,10 @@ def test_fused_engine_matches_reference_and_unfused(variant, golden_models):
     assert launches == 1 + 16 + 3 * 2              # stem + 2 per block + (pool-pack, conv) per shortcut
     with torch.no_grad():
         no_stem = fuse.optimize(m, fuse_stem=False)(x).cpu().numpy()
-    print(variant, "stem kernel vs torch stem", rel_err(fused, no_stem))
-    assert rel_err(fused, no_stem) <= 1e-3
+        fma_stem = fuse.optimize(m, stem="fma")(x).cpu().numpy()
+    print(variant, "stem kernel (mma) vs torch stem", rel_err(fused, no_stem), "fma-chain stem kernel vs torch stem",
+          rel_err(fma_stem, no_stem))
+    assert rel_err(fused, no_stem) <= 1e-3 and rel_err(fma_stem, no_stem) <= 1e-3
     ref = golden_models[variant + "_logits"]
     print(variant, "fused vs reference", rel_err(fused, ref), "fused vs unfused", rel_err(fused, eager))
     assert rel_err(fused, ref) <= 1e-3
