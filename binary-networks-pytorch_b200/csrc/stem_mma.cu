@@ -56,7 +56,8 @@ struct StemMmaArgs {
 };
 
 __device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, const float (&c)[4]) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
+    // not volatile: a pure function of its operands, so ptxas may interleave independent accumulator chains
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
                  : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(c[0]), "f"(c[1]), "f"(c[2]), "f"(c[3]));
 }
@@ -96,19 +97,28 @@ stem_mma_kernel(const __grid_constant__ StemMmaArgs a) {
     }
     // input window: fp32 -> scaled (hi, lo) fp16 pairs; zero fill = the convolution's padding.  Column 35 of a
     // row is the zero-weight eighth tap of the last pixel: it must be finite, so it is zero as well.
-    for (int i = threadIdx.x; i < SM_IN_WORDS; i += SM_WARPS * 32) {
-        const int pc = i % SM_IPW, r = (i / SM_IPW) % SM_IR, ci = i / (SM_IPW * SM_IR);
-        const int hi = hi0 + r, wi = wi0 + 2 * pc;
-        float v0 = 0.0f, v1 = 0.0f;
-        if ((unsigned)hi < (unsigned)a.H) {
-            const float* row = a.x + (((size_t)n * 3 + ci) * a.H + hi) * a.W;
-            if ((unsigned)wi < (unsigned)a.W) v0 = __ldg(row + wi) * a.x_scale;
-            if (2 * pc + 1 < SM_IC && (unsigned)(wi + 1) < (unsigned)a.W) v1 = __ldg(row + wi + 1) * a.x_scale;
+    {
+        constexpr int ITERS = (SM_IN_WORDS + SM_WARPS * 32 - 1) / (SM_WARPS * 32);      // 9
+        float v0[ITERS], v1[ITERS];
+#pragma unroll
+        for (int k = 0; k < ITERS; ++k) {                      // all loads in flight before the first conversion
+            const int i = threadIdx.x + k * SM_WARPS * 32;
+            const int pc = i % SM_IPW, r = (i / SM_IPW) % SM_IR, ci = i / (SM_IPW * SM_IR);
+            const int hi = hi0 + r, wi = wi0 + 2 * pc;
+            v0[k] = 0.0f; v1[k] = 0.0f;
+            if (i < SM_IN_WORDS && (unsigned)hi < (unsigned)a.H) {
+                const float* row = a.x + (((size_t)n * 3 + ci) * a.H + hi) * a.W;
+                if ((unsigned)wi < (unsigned)a.W) v0[k] = __ldg(row + wi);
+                if (2 * pc + 1 < SM_IC && (unsigned)(wi + 1) < (unsigned)a.W) v1[k] = __ldg(row + wi + 1);
+            }
         }
-        uint32_t h, l;
-        split2(v0, v1, h, l);
-        in_hi[i] = h;
-        in_lo[i] = l;
+#pragma unroll
+        for (int k = 0; k < ITERS; ++k) {
+            const int i = threadIdx.x + k * SM_WARPS * 32;
+            uint32_t h, l;
+            split2(v0[k] * a.x_scale, v1[k] * a.x_scale, h, l);
+            if (i < SM_IN_WORDS) { in_hi[i] = h; in_lo[i] = l; }
+        }
     }
     __syncthreads();
     mbar_wait(bar, 0);
@@ -145,17 +155,29 @@ stem_mma_kernel(const __grid_constant__ StemMmaArgs a) {
             al[mt][2] = in_lo[offB + pb[mt][0]]; al[mt][3] = in_lo[offB + pb[mt][1]];
         }
 #pragma unroll
-        for (int j = 0; j < SM_NT; ++j) {
-            const uint4 b = w_s[(s * SM_NT + j) * 32 + lane];      // {b0_hi, b1_hi, b0_lo, b1_lo}
+        for (int jp = 0; jp < SM_NT; jp += 2) {                // two n tiles x two m tiles = four independent chains
+            uint4 b[2];
 #pragma unroll
-            for (int mt = 0; mt < SM_MT; ++mt) {
-                float d[4];
-                mma_f16(d, al[mt], b.x, b.y, zero);            // xl * wh
-                mma_f16(d, ah[mt], b.z, b.w, d);               // xh * wl
-                mma_f16(d, ah[mt], b.x, b.y, d);               // xh * wh
+            for (int jj = 0; jj < 2; ++jj) b[jj] = w_s[(s * SM_NT + jp + jj) * 32 + lane];    // {b0_hi, b1_hi, b0_lo, b1_lo}
+            float d[2][SM_MT][4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) acc[mt][j][i] += d[i];
-            }
+            for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                for (int mt = 0; mt < SM_MT; ++mt) mma_f16(d[jj][mt], al[mt], b[jj].x, b[jj].y, zero);          // xl * wh
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                for (int mt = 0; mt < SM_MT; ++mt) mma_f16(d[jj][mt], ah[mt], b[jj].z, b[jj].w, d[jj][mt]);     // xh * wl
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                for (int mt = 0; mt < SM_MT; ++mt) mma_f16(d[jj][mt], ah[mt], b[jj].x, b[jj].y, d[jj][mt]);     // xh * wh
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                for (int mt = 0; mt < SM_MT; ++mt)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[mt][jp + jj][i] += d[jj][mt][i];
         }
     }
     __syncthreads();                                           // every warp is done with the operand buffers
