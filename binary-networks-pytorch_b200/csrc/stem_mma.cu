@@ -43,7 +43,7 @@ constexpr size_t SM_CONV_BYTES = (size_t)(SM_NPIX + 1) * SM_CPITCH * 4;     // 7
 constexpr size_t SM_OPER_BYTES = SM_W_BYTES + 2 * (size_t)SM_IN_WORDS_PAD * 4;
 constexpr size_t SM_SMEM = 128 + (SM_CONV_BYTES > SM_OPER_BYTES ? SM_CONV_BYTES : SM_OPER_BYTES);
 static_assert(SM_WARPS * SM_MT * 16 >= SM_NPIX, "m tiles must cover the conv tile");
-static_assert(SM_PH * SM_PW % SM_WARPS == 0, "pooled pixels split evenly over the warps");
+static_assert(SM_PH == SM_WARPS, "one warp per pooled row of the tile");
 
 struct StemMmaArgs {
     const float* x;           // [n,3,h,w] contiguous
@@ -64,10 +64,11 @@ __device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], u
 
 // (hi, lo) fp16 split of two adjacent scaled inputs, packed as the two halves of a word each
 __device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
-    const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
-    const __half l0 = __float2half_rn(v0 - __half2float(h0)), l1 = __float2half_rn(v1 - __half2float(h1));
-    hi = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-    lo = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    const __half2 h = __floats2half2_rn(v0, v1);               // low half = v0 (the even column / lower k index)
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 __global__ void __launch_bounds__(SM_WARPS * 32, 2)
@@ -98,26 +99,31 @@ stem_mma_kernel(const __grid_constant__ StemMmaArgs a) {
     // input window: fp32 -> scaled (hi, lo) fp16 pairs; zero fill = the convolution's padding.  Column 35 of a
     // row is the zero-weight eighth tap of the last pixel: it must be finite, so it is zero as well.
     {
+        // thread -> word i = tid + 256 k of the window, (rf, pc) = divmod(i, 18) kept incrementally (256 = 14 * 18 + 4);
+        // rf = c_in * 39 + window row.  32-bit offsets inside the image (3 * H * W < 2^31, checked by the caller).
         constexpr int ITERS = (SM_IN_WORDS + SM_WARPS * 32 - 1) / (SM_WARPS * 32);      // 9
+        const float* xn = a.x + (size_t)n * 3 * a.H * a.W;
+        int rf = threadIdx.x / SM_IPW, pc = threadIdx.x - rf * SM_IPW;
         float v0[ITERS], v1[ITERS];
 #pragma unroll
         for (int k = 0; k < ITERS; ++k) {                      // all loads in flight before the first conversion
-            const int i = threadIdx.x + k * SM_WARPS * 32;
-            const int pc = i % SM_IPW, r = (i / SM_IPW) % SM_IR, ci = i / (SM_IPW * SM_IR);
-            const int hi = hi0 + r, wi = wi0 + 2 * pc;
-            v0[k] = 0.0f; v1[k] = 0.0f;
-            if (i < SM_IN_WORDS && (unsigned)hi < (unsigned)a.H) {
-                const float* row = a.x + (((size_t)n * 3 + ci) * a.H + hi) * a.W;
-                if ((unsigned)wi < (unsigned)a.W) v0[k] = __ldg(row + wi);
-                if (2 * pc + 1 < SM_IC && (unsigned)(wi + 1) < (unsigned)a.W) v1[k] = __ldg(row + wi + 1);
-            }
+            const int ci = (rf >= SM_IR) + (rf >= 2 * SM_IR);
+            const int hi = hi0 + rf - ci * SM_IR, wi = wi0 + 2 * pc;
+            const bool rowok = (unsigned)hi < (unsigned)a.H && (k + 1 < ITERS || rf < 3 * SM_IR);
+            const int off = (ci * a.H + hi) * a.W + wi;
+            const bool ok0 = rowok && (unsigned)wi < (unsigned)a.W;
+            const bool ok1 = rowok && pc < SM_IPW - 1 && (unsigned)(wi + 1) < (unsigned)a.W;
+            v0[k] = ok0 ? __ldg(xn + off) : 0.0f;
+            v1[k] = ok1 ? __ldg(xn + off + 1) : 0.0f;
+            rf += (SM_WARPS * 32) / SM_IPW; pc += (SM_WARPS * 32) % SM_IPW;
+            if (pc >= SM_IPW) { pc -= SM_IPW; rf += 1; }
         }
 #pragma unroll
         for (int k = 0; k < ITERS; ++k) {
             const int i = threadIdx.x + k * SM_WARPS * 32;
             uint32_t h, l;
             split2(v0[k] * a.x_scale, v1[k] * a.x_scale, h, l);
-            if (i < SM_IN_WORDS) { in_hi[i] = h; in_lo[i] = l; }
+            if (k + 1 < ITERS || i < SM_IN_WORDS) { in_hi[i] = h; in_lo[i] = l; }
         }
     }
     __syncthreads();
@@ -205,25 +211,37 @@ stem_mma_kernel(const __grid_constant__ StemMmaArgs a) {
     __syncthreads();
 
     // ---------------- 3x3 / stride 2 max, NHWC store, planes for the first binarized conv ----------------
-    for (int task = warp; task < SM_PH * SM_PW; task += SM_WARPS) {
-        const int pr = task / SM_PW, pc = task - pr * SM_PW;
-        const int ph = ph0 + pr, pw = pw0 + pc;
-        if (ph >= a.Hp || pw >= a.Wp) continue;              // warp-uniform
-        uint32_t sw[2], mw[2];
-#pragma unroll
-        for (int cb = 0; cb < 2; ++cb) {
-            const int ch = cb * 32 + lane;
-            float m = 0.0f;
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int j = 0; j < 3; ++j) m = fmaxf(m, conv_s[((2 * pr + i) * SM_CC + 2 * pc + j) * SM_CPITCH + ch]);
-            a.out[(((size_t)n * a.Hp + ph) * a.Wp + pw) * 64 + ch] = m;
-            const float b = a.nx_scale ? __fmaf_rn(__ldg(a.nx_scale + ch), m, __ldg(a.nx_shift + ch)) : m;
-            sw[cb] = __ballot_sync(0xffffffffu, b > 0.0f);
-            mw[cb] = __ballot_sync(0xffffffffu, b > 0.0f || b < 0.0f);
+    // warp = pooled row of the tile, its 7 pooled pixels unrolled (constant shared-memory offsets), lanes <-> channels
+    const int ph = ph0 + warp;
+    if (ph < a.Hp) {
+        const bool has_nx = a.nx_scale != nullptr;
+        float nxs[2] = {1.0f, 1.0f}, nxh[2] = {0.0f, 0.0f};
+        if (has_nx) {
+            nxs[0] = __ldg(a.nx_scale + lane); nxs[1] = __ldg(a.nx_scale + 32 + lane);
+            nxh[0] = __ldg(a.nx_shift + lane); nxh[1] = __ldg(a.nx_shift + 32 + lane);
         }
-        if (lane == 0 && a.obits) a.obits[((size_t)n * a.Hp + ph) * a.Wp + pw] = make_uint4(sw[0], sw[1], mw[0], mw[1]);
+        const size_t pix0 = ((size_t)n * a.Hp + ph) * a.Wp + pw0;
+        float* orow = a.out + pix0 * 64 + lane;
+        const float* cbase = conv_s + (2 * warp * SM_CC) * SM_CPITCH + lane;
+#pragma unroll
+        for (int pc = 0; pc < SM_PW; ++pc) {
+            if (pw0 + pc < a.Wp) {                             // warp-uniform
+                uint32_t sw[2], mw[2];
+#pragma unroll
+                for (int cb = 0; cb < 2; ++cb) {
+                    float m = 0.0f;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) m = fmaxf(m, cbase[(i * SM_CC + 2 * pc + j) * SM_CPITCH + cb * 32]);
+                    orow[pc * 64 + cb * 32] = m;
+                    const float b = has_nx ? __fmaf_rn(nxs[cb], m, nxh[cb]) : m;
+                    sw[cb] = __ballot_sync(0xffffffffu, b > 0.0f);
+                    mw[cb] = __ballot_sync(0xffffffffu, b > 0.0f || b < 0.0f);
+                }
+                if (lane == 0 && a.obits) a.obits[pix0 + pc] = make_uint4(sw[0], sw[1], mw[0], mw[1]);
+            }
+        }
     }
 }
 
@@ -272,6 +290,7 @@ extern "C" int bnn_stem_mma_fwd(const float* x, int32_t n, int32_t h, int32_t w,
     if (!x || !w_frag || !bn_scale || !bn_shift || !out) return BNN_E_NULL;
     if ((nx_scale == nullptr) != (nx_shift == nullptr)) return BNN_E_NULL;
     if (n <= 0 || h < 7 || w < 7) return BNN_E_SHAPE;
+    if ((long long)h * w * 3 >= 0x7fffffffLL) return BNN_E_UNSUPPORTED;
     if (x_log2_scale < -60 || x_log2_scale > 60 || w_log2_scale < -60 || w_log2_scale > 60) return BNN_E_SHAPE;
     if (((uintptr_t)w_frag & 15) || ((uintptr_t)out_bits & 15) || ((uintptr_t)bn_scale & 7) || ((uintptr_t)bn_shift & 7))
         return BNN_E_ALIGN;
