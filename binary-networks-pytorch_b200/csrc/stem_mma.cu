@@ -71,6 +71,7 @@ __device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+template <bool CHAIN>
 __global__ void __launch_bounds__(SM_WARPS * 32, 2)
 stem_mma_kernel(const __grid_constant__ StemMmaArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -165,6 +166,21 @@ stem_mma_kernel(const __grid_constant__ StemMmaArgs a) {
             uint4 b[2];
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) b[jj] = w_s[(s * SM_NT + jp + jj) * 32 + lane];    // {b0_hi, b1_hi, b0_lo, b1_lo}
+            if (CHAIN) {
+                // experiment: every product accumulates inside the tensor core (no fp32 adds outside)
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                    for (int mt = 0; mt < SM_MT; ++mt) mma_f16(acc[mt][jp + jj], al[mt], b[jj].x, b[jj].y, acc[mt][jp + jj]);
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                    for (int mt = 0; mt < SM_MT; ++mt) mma_f16(acc[mt][jp + jj], ah[mt], b[jj].z, b[jj].w, acc[mt][jp + jj]);
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                    for (int mt = 0; mt < SM_MT; ++mt) mma_f16(acc[mt][jp + jj], ah[mt], b[jj].x, b[jj].y, acc[mt][jp + jj]);
+            } else {
             float d[2][SM_MT][4];
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj)
@@ -184,6 +200,7 @@ stem_mma_kernel(const __grid_constant__ StemMmaArgs a) {
                 for (int mt = 0; mt < SM_MT; ++mt)
 #pragma unroll
                     for (int i = 0; i < 4; ++i) acc[mt][jp + jj][i] += d[jj][mt][i];
+            }
         }
     }
     __syncthreads();                                           // every warp is done with the operand buffers
@@ -286,7 +303,6 @@ extern "C" int bnn_stem_mma_fwd(const float* x, int32_t n, int32_t h, int32_t w,
                                 int32_t x_log2_scale, int32_t w_log2_scale, const float* bn_scale,
                                 const float* bn_shift, const float* nx_scale, const float* nx_shift, float* out,
                                 void* out_bits, uint32_t flags, void* stream_) {
-    (void)flags;
     if (!x || !w_frag || !bn_scale || !bn_shift || !out) return BNN_E_NULL;
     if ((nx_scale == nullptr) != (nx_shift == nullptr)) return BNN_E_NULL;
     if (n <= 0 || h < 7 || w < 7) return BNN_E_SHAPE;
@@ -303,11 +319,14 @@ extern "C" int bnn_stem_mma_fwd(const float* x, int32_t n, int32_t h, int32_t w,
     a.Hc = (h + 6 - 7) / 2 + 1; a.Wc = (w + 6 - 7) / 2 + 1;
     a.Hp = (a.Hc + 2 - 3) / 2 + 1; a.Wp = (a.Wc + 2 - 3) / 2 + 1;
     a.tiles_h = (a.Hp + SM_PH - 1) / SM_PH; a.tiles_w = (a.Wp + SM_PW - 1) / SM_PW;
-    cudaError_t ce = cudaFuncSetAttribute((const void*)stem_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_SMEM);
+    const bool chain = (flags & BNN_F_STEM_MMA_CHAIN) != 0;
+    const void* fn = chain ? (const void*)stem_mma_kernel<true> : (const void*)stem_mma_kernel<false>;
+    cudaError_t ce = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_SMEM);
     if (ce != cudaSuccess) return (int)ce;
     const long long ctas = (long long)n * a.tiles_h * a.tiles_w;
     if (ctas > 0x7fffffffLL) return BNN_E_UNSUPPORTED;
-    stem_mma_kernel<<<(unsigned)ctas, SM_WARPS * 32, SM_SMEM, (cudaStream_t)stream_>>>(a);
+    if (chain) stem_mma_kernel<true><<<(unsigned)ctas, SM_WARPS * 32, SM_SMEM, (cudaStream_t)stream_>>>(a);
+    else stem_mma_kernel<false><<<(unsigned)ctas, SM_WARPS * 32, SM_SMEM, (cudaStream_t)stream_>>>(a);
     count_launch(1);
     return (int)cudaGetLastError();
 }

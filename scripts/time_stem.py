@@ -31,13 +31,17 @@ def timed(fn, reps=20):
     return float(np.median(ts))
 
 
-res = {"bs": bs, "fma_ms": timed(lambda: BF.stem(x, w_t, (g, h))), "mma_ms": timed(lambda: BF.stem_mma(x, wfrag, (g, h)))}
+res = {"bs": bs, "fma_ms": timed(lambda: BF.stem(x, w_t, (g, h))), "mma_ms": timed(lambda: BF.stem_mma(x, wfrag, (g, h))),
+       "mma_chain_ms": timed(lambda: BF.stem_mma(x, wfrag, (g, h), flags=16))}
 xs = x[:4]
 y64 = torch.nn.functional.conv2d(xs.double(), w.double(), stride=2, padding=3)
 y64 = torch.nn.functional.max_pool2d(torch.relu(y64 * g.double().view(1, -1, 1, 1) + h.double().view(1, -1, 1, 1)), 3, 2, 1)
 a, abits = BF.stem(xs, w_t, (g, h))
 b, bbits = BF.stem_mma(xs, wfrag, (g, h))
 sc = float(y64.abs().max())
+c, _ = BF.stem_mma(xs, wfrag, (g, h), flags=16)
+res["mma_chain_err"] = float((c.double() - y64).abs().max()) / sc
+res["mma_chain_rms"] = float((c.double() - y64).pow(2).mean().sqrt()) / sc
 res["fma_err"] = float((a.double() - y64).abs().max()) / sc
 res["mma_err"] = float((b.double() - y64).abs().max()) / sc
 res["fma_rms"] = float((a.double() - y64).pow(2).mean().sqrt()) / sc
