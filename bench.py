@@ -156,6 +156,15 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback"
 
 
+def measured_traffic():
+    """DRAM bytes of the binarized-path launches of one step, from the committed ncu capture (profiles/traffic.json)."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f)
+    return None
+
+
 def pick_cpu_threads(twin):
     """The float simulation is many small torch ops; on a many-core host the default (all cores) is not always
     the fastest setting.  Give the CPU arm its best case: try a few intra-op thread counts on a tiny batch."""
@@ -437,6 +446,8 @@ def main():
         return
 
     peaks, peak_kind = measured_peaks()
+    traffic = measured_traffic()
+    n_conv = sum(1 for k, d in per_layer.items() if d.get("conv_ms", 0) > 0)
     total_bytes = sum(d["bytes"] for d in per_layer.values())
     total_bmac = sum(d["bmac"] for d in per_layer.values())
     path_ms = sum(d["pack_ms"] + d["conv_ms"] for d in per_layer.values())
@@ -470,7 +481,14 @@ def main():
                        "double-buffered (upload of step i+1 overlaps the forward of step i)"},
         "gpu_launches": int(launches_per_step * args.steps) if launches_per_step else 0,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind,
+                     "frac": achieved / peaks["hbm_gbs"],
+                     "traffic": (traffic["binarized_path_dram_bytes_per_step"] / max(1, n_conv)
+                                 if traffic and not args.no_fuse and B == BATCH_PER_GPU else None),
+                     "traffic_what": "ncu dram__bytes_read+write of the same launches, per conv launch "
+                                     "(profiles/traffic.json; fused engine at bs 256): below the algorithmic bytes "
+                                     "because fused layers exchange bit planes instead of fp32 NCHW tensors",
+                     "launches": n_conv, "algorithmic_bytes_per_launch": total_bytes / max(1, n_conv),
+                     "avg_launch_ms": path_ms / max(1, n_conv), "peak_kind": peak_kind,
                      "what": "bit-pack + XNOR-popcount launches of the 19 binarized layers, algorithmic bytes "
                              f"{total_bytes / 1e9:.3f} GB/step over {path_ms:.3f} ms/step; these layers are "
                              "POPC-bound, see 'popc'"},
