@@ -260,6 +260,34 @@ def stem(x: torch.Tensor, w_t: torch.Tensor, bn: Tuple[torch.Tensor, torch.Tenso
     return out, (None if bits is None else PackedActivations(bits, n, 64, hp, wp))
 
 
+def shortcut(x: torch.Tensor, wts: PackedWeights, pool: int, ceil_mode: bool, *, bias=None, post=None, bn=None,
+             use_alpha: bool = True, flags: int = 0) -> torch.Tensor:
+    """AvgPool(pool) -> sign -> binarized conv1x1 -> BatchNorm of the reference's down-sampling shortcut
+    (bnn/models/resnet.py:129-133) in one kernel (bnn_shortcut_fwd).  ``x``: channels_last fp32 [n,c,h,w];
+    returns [n,c_out,ho,wo] channels_last.  Bit-identical to ``pack_activations(x, pool=...)`` +
+    ``bconv2d_fused(..., bn=bn)``."""
+    _require_cuda_f32(x, "input")
+    if x.dim() != 4 or x.stride(1) != 1:
+        raise native.NativeError("shortcut expects a channels_last [n,c,h,w] tensor (channel stride 1)")
+    if wts.kh != 1 or wts.kw != 1 or wts.c_in != x.shape[1]:
+        raise native.NativeError(f"shortcut expects a 1x1 conv over {x.shape[1]} channels, got "
+                                 f"{wts.kh}x{wts.kw} over {wts.c_in}")
+    n, c, h, w = x.shape
+    k = max(1, int(pool))
+    ho, wo = (-(-h // k), -(-w // k)) if ceil_mode else (h // k, w // k)
+    dev = x.device
+    with torch.cuda.device(dev):
+        out = torch.empty((n, wts.c_out, ho, wo), dtype=torch.float32, device=dev, memory_format=torch.channels_last)
+        rc = native.lib().bnn_shortcut_fwd(x.data_ptr(), x.stride(0), x.stride(2), x.stride(3), n, c, h, w, k,
+                                           int(bool(ceil_mode)), wts.bits.data_ptr(), wts.c_out,
+                                           wts.alpha.data_ptr() if use_alpha else None, _opt_ptr(bias), _opt_ptr(post),
+                                           None if bn is None else bn[0].data_ptr(),
+                                           None if bn is None else bn[1].data_ptr(), out.data_ptr(), flags,
+                                           _stream_ptr(dev))
+    native.check(rc, "bnn_shortcut_fwd")
+    return out
+
+
 STEM_X_LOG2_SCALE = 7          # inputs up to |x| < 511 stay inside the fp16 range (raw 0..255 pixels included)
 
 

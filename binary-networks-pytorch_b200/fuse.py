@@ -223,8 +223,15 @@ class FusedResNet(nn.Module):
         if plan.shortcut is not None:
             pool, conv_d, bn_d = plan.shortcut
             kw, wts = _conv_args(conv_d)
-            pooled = BF.pack_activations(x, pool=_pair(pool.kernel_size)[0], ceil_mode=pool.ceil_mode)
-            shortcut, _ = BF.bconv2d_fused(pooled, wts, bn=bn_d.get(), channels_last=True, **kw)
+            one_kernel = (wts.kh == 1 and wts.kw == 1 and kw["stride"] == (1, 1) and kw["padding"] == (0, 0)
+                          and conv_d.groups == 1 and x.stride(1) == 1 and wts.c_in <= 1024 and wts.c_out <= 4096)
+            if one_kernel:
+                # pool + sign + conv1x1 + BN without the planes ever reaching HBM
+                shortcut = BF.shortcut(x, wts, _pair(pool.kernel_size)[0], pool.ceil_mode, bias=kw["bias"],
+                                       post=kw["post"], bn=bn_d.get(), use_alpha=kw["use_alpha"])
+            else:
+                pooled = BF.pack_activations(x, pool=_pair(pool.kernel_size)[0], ceil_mode=pool.ceil_mode)
+                shortcut, _ = BF.bconv2d_fused(pooled, wts, bn=bn_d.get(), channels_last=True, **kw)
         else:
             shortcut = x
         dev = x.device

@@ -60,6 +60,9 @@ _SIGNATURES = {
     "bnn_stem_mma_pack_weight": (c_int, [c_void_p, c_int32, c_void_p, c_void_p]),
     "bnn_stem_mma_fwd": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p]),
+    "bnn_shortcut_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                 c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_uint32,
+                                 c_void_p]),
     "bnn_bconv2d_tune": (c_int, [c_void_p, c_void_p, POINTER(ConvGeom), POINTER(Epilogue), c_uint32, c_int32, c_void_p]),
     "bnn_conv_plan": (c_int, [POINTER(ConvGeom), c_uint32, c_int32, POINTER(c_int32)]),
 }

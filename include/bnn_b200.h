@@ -232,6 +232,20 @@ int bnn_stem_mma_fwd(const float *x, int32_t n, int32_t h, int32_t w, const void
                      void *stream);
 
 /*
+ * The down-sampling shortcut of bnn.models.resnet (bnn/models/resnet.py:129-133) as one kernel:
+ *   AvgPool2d(pool, stride pool, ceil_mode, count_include_pad=False) -> sign() -> binarized conv 1x1 -> eval BatchNorm,
+ * i.e. bnn_avgpool_pack_f32 followed by bnn_bconv2d_fused_fwd (1x1, stride 1, no padding, epilogue with scale / bias /
+ * post / bn_* only), bit-identical to that pair but without the round trip of the planes through HBM.
+ * x: channels-last fp32, element (n, c, h, w) at n*xs_n + h*xs_h + w*xs_w + c (channel stride 1).
+ * wbits: bnn_pack_weight_f32 output for the [c_out, c_in, 1, 1] weight.  scale (= alpha), bias, post, bn_* may be NULL.
+ * out: [n, ho, wo, c_out] contiguous fp32 (torch channels_last), ho = ceil or floor of h / pool.
+ */
+int bnn_shortcut_fwd(const float *x, int64_t xs_n, int64_t xs_h, int64_t xs_w, int32_t n, int32_t c_in,
+                     int32_t h, int32_t w, int32_t pool, int32_t ceil_mode, const void *wbits, int32_t c_out,
+                     const float *scale, const float *bias, const float *post, const float *bn_scale,
+                     const float *bn_shift, float *out, uint32_t flags, void *stream);
+
+/*
  * Integer-pipe micro-benchmarks used for the popcount roofline denominator
  * (bench.py): runs `which` on every SM and returns achieved giga-operations/s
  * (warp-lane operations) in *gops.  Synchronises the device.  which:

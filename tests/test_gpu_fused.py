@@ -93,6 +93,45 @@ def test_stem_kernel_bit_exact_vs_oracle(hw, flags):
         assert np.array_equal(bits.bits.cpu().numpy().view(np.uint32), want_bits)
 
 
+@pytest.mark.parametrize("shape,c_out,k,ceil,extras", [
+    ((2, 64, 8, 8), 128, 2, True, "bn"), ((1, 70, 7, 9), 40, 2, True, "bn"), ((1, 64, 7, 9), 96, 2, False, "bn"),
+    ((2, 128, 6, 6), 256, 1, True, "bn"), ((1, 64, 9, 7), 64, 3, True, "bn"), ((3, 256, 5, 5), 512, 2, True, "all"),
+    ((2, 64, 8, 8), 128, 2, True, "none"), ((67, 64, 4, 4), 32, 2, True, "bn")])
+def test_shortcut_kernel_bit_exact_vs_two_launch_form_and_oracle(shape, c_out, k, ceil, extras):
+    """AvgPool -> sign -> conv1x1 -> BN in one kernel == pack(pool) + fused conv (oracle and the two-launch CUDA path)."""
+    rng = np.random.default_rng(11)
+    n, c, h, w = shape
+    x = rng.standard_normal(shape).astype(np.float32)
+    x[rng.random(shape) < 0.2] = 0.0
+    wt = rng.standard_normal((c_out, c, 1, 1)).astype(np.float32)
+    bn = ((0.5 + rng.random(c_out)).astype(np.float32), rng.standard_normal(c_out).astype(np.float32)) if extras != "none" else None
+    bias = rng.standard_normal(c_out).astype(np.float32) if extras == "all" else None
+    post = (0.5 + rng.random(c_out)).astype(np.float32) if extras == "all" else None
+    xcl = _d(x).contiguous(memory_format=torch.channels_last)
+    wts = BF.pack_weights(_d(wt), True, True)
+    pair = None if bn is None else (_d(bn[0]), _d(bn[1]))
+    got = BF.shortcut(xcl, wts, k, ceil, bias=_d(bias), post=_d(post), bn=pair)
+    pooled = BF.pack_activations(xcl, pool=k, ceil_mode=ceil)
+    two, _ = BF.bconv2d_fused(pooled, wts, bias=_d(bias), post=_d(post), bn=pair, channels_last=True)
+    assert got.shape == two.shape and got.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(got, two)
+    ab = co.pack_act(x, pool=k, ceil_mode=ceil)
+    wb, _, _ = co.pack_weight(wt, True, True)
+    g = co.geom(n, c, ab.shape[2], ab.shape[3], c_out, 1, 1, (1, 1), (0, 0), (1, 1))
+    want, _ = co.bconv2d_fused(ab, wb, g, scale=wts.alpha.cpu().numpy(), bias=bias, post=post, bn=bn)
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_shortcut_kernel_rejects_bad_arguments():
+    wts = BF.pack_weights(torch.randn(32, 64, 3, 3, device=DEV), True, True)
+    x = torch.randn(1, 64, 8, 8, device=DEV).contiguous(memory_format=torch.channels_last)
+    with pytest.raises(native.NativeError):
+        BF.shortcut(x, wts, 2, True)                                   # not a 1x1 conv
+    wts1 = BF.pack_weights(torch.randn(32, 64, 1, 1, device=DEV), True, True)
+    with pytest.raises(native.NativeError):
+        BF.shortcut(torch.randn(1, 64, 8, 8, device=DEV), wts1, 2, True)  # NCHW input
+
+
 def _stem_f64(x, w, g, h):
     """float64 conv7x7/2/3 -> folded BN -> ReLU -> maxpool3/2/1, NHWC (the yardstick for both stem kernels)."""
     y = torch.nn.functional.conv2d(torch.from_numpy(x).double(), torch.from_numpy(w).double(), stride=2, padding=3)
@@ -160,7 +199,7 @@ def test_fused_engine_matches_reference_and_unfused(variant, golden_models):
         before = native.launch_count()
         fused = engine(x).cpu().numpy()
     launches = native.launch_count() - before
-    assert launches == 1 + 16 + 3 * 2              # stem + 2 per block + (pool-pack, conv) per shortcut
+    assert launches == 1 + 16 + 3                  # stem + 2 per block + one kernel per down-sampling shortcut
     with torch.no_grad():
         no_stem = fuse.optimize(m, fuse_stem=False)(x).cpu().numpy()
         fma_stem = fuse.optimize(m, stem="fma")(x).cpu().numpy()
