@@ -382,7 +382,7 @@ def main():
         per_layer = {}
         if rank == 0:
             records = []
-            orig_pack, orig_conv, orig_fused = BF.pack_activations, BF.bconv2d, BF.bconv2d_fused
+            orig_pack, orig_conv, orig_fused, orig_short = BF.pack_activations, BF.bconv2d, BF.bconv2d_fused, BF.shortcut
 
             def ev():
                 e = torch.cuda.Event(enable_timing=True)
@@ -400,7 +400,10 @@ def main():
                 records.append(("conv", e0, ev(), (wts.c_in, wts.c_out, wts.kh, act.h, act.w)))
                 return r
 
-            BF.pack_activations, BF.bconv2d, BF.bconv2d_fused = pack_t, conv_t, fused_t
+            def short_t(x, wts, *a, **k):        # pool + sign + conv1x1 + BN of a down-sampling shortcut: one launch
+                e0 = ev(); r = orig_short(x, wts, *a, **k); records.append(("conv", e0, ev())); return r
+
+            BF.pack_activations, BF.bconv2d, BF.bconv2d_fused, BF.shortcut = pack_t, conv_t, fused_t, short_t
             order = []
             hooks = [m.register_forward_hook(lambda mod, i, o, n=n: order.append(n))
                      for n, m in model.named_modules() if isinstance(m, bnn.layers.Conv2d)]
@@ -408,7 +411,7 @@ def main():
             for _ in range(reps):
                 engine(x_dev)                      # rank-local: no collective in this pass
             torch.cuda.synchronize()
-            BF.pack_activations, BF.bconv2d, BF.bconv2d_fused = orig_pack, orig_conv, orig_fused
+            BF.pack_activations, BF.bconv2d, BF.bconv2d_fused, BF.shortcut = orig_pack, orig_conv, orig_fused, orig_short
             for h in hooks:
                 h.remove()
             packs = [r for r in records if r[0] == "pack"]
@@ -429,7 +432,9 @@ def main():
             else:                                       # fused engine: conv launches in execution order
                 names = fused_layer_order(model)
                 for i in range(per_step_c):
-                    name = names[i] if per_step_c == len(names) else f"conv{i}"
+                    if per_step_c != len(names):
+                        raise SystemExit(f"bench.py: {per_step_c} binarized-layer launches per step, expected {len(names)}")
+                    name = names[i]
                     per_layer[name] = {"pack_ms": 0.0, "conv_ms": med(convs, per_step_c, i)}
                 per_layer["_pack_launches_total"] = {"pack_ms": sum(med(packs, per_step_p, i) for i in range(per_step_p)),
                                                      "conv_ms": 0.0, "bytes": 0, "bmac": 0, "n_per_step": per_step_p}

@@ -3,7 +3,7 @@
 ``optimize(model)`` wraps a prepared ResNet-style model (``bnn.models.resnet`` layout: ``conv1,
 bn1, relu, maxpool, layer1..4, avgpool, fc``; blocks of the reference's ``BasicBlock`` /
 ``PreBasicBlock`` / ``Bottleneck`` / ``PreBottleneck`` shape, bnn/models/layers/res_block.py:8-229) in an
-engine that runs each residual block as one kernel launch per binarized conv (plus two for a shortcut):
+engine that runs each residual block as one kernel launch per binarized conv (plus one for a shortcut):
 
 * the eval-mode BatchNorm after (or before) a binarized conv, the ReLU / PReLU, the residual add
   and the *next* layer's sign() are folded into the conv kernel's epilogue (``bnn_bconv2d_fused_fwd``);
@@ -11,14 +11,16 @@ engine that runs each residual block as one kernel launch per binarized conv (pl
   next layer's sign/mask planes directly (lanes <-> channels makes that one ``ballot`` per word);
 * the residual stream stays fp32 and is read once / written once per block; between fused blocks it is
   kept in torch's channels_last (NHWC) memory format, which matches the kernel's lanes <-> channels mapping;
-* the shortcut's AvgPool2d + sign is one pass (``bnn_avgpool_pack_f32``).
+* the shortcut (AvgPool2d -> sign -> conv1x1 -> BatchNorm) is one kernel (``bnn_shortcut_fwd``): the pooled
+  planes never leave shared memory (other shortcut shapes: ``bnn_avgpool_pack_f32`` + the fused conv).
 
 Per-channel BatchNorm constants are folded once (``g = weight / sqrt(var + eps)``, ``h = bias -
 mean * g``) and re-folded when any of the BatchNorm tensors changes (version counters).
 Blocks the engine does not recognise run through their own ``forward`` (per-layer kernels), so
 the engine is always a drop-in for ``model`` in eval mode.  Results agree with the unfused path
 to fp32 rounding of the BatchNorm fold (tests/test_gpu_fused.py).  The fp32 stem (conv7x7/2 + BN + ReLU +
-max-pool, reference resnet.py:85-92) is one kernel too (``bnn_stem_fwd``) when it has the reference's shape;
+max-pool, reference resnet.py:85-92) is one kernel too (``bnn_stem_mma_fwd`` by default, ``bnn_stem_fwd`` with
+``stem="fma"``) when it has the reference's shape;
 global pooling and the classifier stay torch ops.
 """
 from typing import List, Optional, Tuple
