@@ -70,6 +70,9 @@ template <int P, int C, int KWT, int SWT, int MODE, int EPI>
 __global__ void __launch_bounds__(256, 2)
 bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ConvArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
+    // EPI 0: reference epilogue.  EPI 1: fused epilogue, any strides.  EPI 2: fused epilogue with channel-contiguous
+    // (NHWC) residual and output -- what the fused engine always uses: the pixel-contiguous transposes are compiled out
+    constexpr bool FUSED = EPI >= 1, CL = EPI == 2;
     constexpr int PITCH = P | 1;      // odd pitch: conflict-free transposes
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
     uint4* act = reinterpret_cast<uint4*>(smem + 128);
@@ -176,10 +179,11 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
 
     // ---------------- pixel groups ----------------
     // per-image bases (the image is fixed for the CTA); inside an image 32-bit element offsets suffice (host-checked)
-    const float* res_n = (EPI == 1 && a.e.res) ? a.e.res + (long long)n * a.e.rn : nullptr;
+    const float* res_n = (FUSED && a.e.res) ? a.e.res + (long long)n * a.e.rn : nullptr;
     float* out_n = a.e.out ? a.e.out + (long long)n * a.e.on : nullptr;
-    const int e_rc = (int)a.e.rc, e_rh = (int)a.e.rh, e_rw = (int)a.e.rw;
-    const int e_oc = (int)a.e.oc, e_oh = (int)a.e.oh, e_ow = (int)a.e.ow;
+    const int e_rc = CL ? 1 : (int)a.e.rc, e_rh = (int)a.e.rh, e_rw = (int)a.e.rw;
+    const int e_oc = CL ? 1 : (int)a.e.oc, e_oh = (int)a.e.oh, e_ow = (int)a.e.ow;
+    const int a_chstep = a.BH * a.BW, a_khstep = a.DH * a.BW;     // activation rows: per chunk, per kernel row
     int g_row = warp / a.gpr, g_col = warp - g_row * a.gpr;      // one division per warp, then incremental
     const int step_row = nwarps / a.gpr, step_col = nwarps - step_row * a.gpr;
     for (int g = warp; g < a.G; g += nwarps) {
@@ -191,12 +195,12 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
         const int wo_first = wo0 + wq;
         if (ho >= a.Ho || wo_first >= a.Wo) continue;   // warp-uniform
 
-        if constexpr (EPI == 1) {
+        if constexpr (FUSED) {
             // the residual tile is needed only after the K loop: start pulling its lines toward the SM now so the
             // epilogue does not sit on DRAM latency
             if (a.e.res != nullptr) {
                 const float* rb = res_n + ho * e_rh;
-                if (e_rw == 1) {              // NCHW: one 32-byte pixel run per channel row
+                if (!CL && e_rw == 1) {       // NCHW: one 32-byte pixel run per channel row
 #pragma unroll
                     for (int j = 0; j < C; ++j) {
                         const int c = (blk0 + j) * 32 + lane;
@@ -216,10 +220,14 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
 #pragma unroll
             for (int j = 0; j < C; ++j) acc[p][j] = 0;
 
-        for (int ch = 0; ch < a.nch; ++ch) {
+        // row pointers advance by additions: (chunk, kernel row) is a running k-step for the weights
+        const uint4* arow_c = act + (r * a.SH) * a.BW + wq * SW;
+        const uint2* wrow = wsm + lane - KW * 32;
+        for (int ch = 0; ch < a.nch; ++ch, arow_c += a_chstep) {
+            const uint4* arow = arow_c - a_khstep;
             for (int kh = 0; kh < a.KH; ++kh) {
-                const uint4* arow = act + (size_t)(ch * a.BH + r * a.SH + kh * a.DH) * a.BW + wq * SW;
-                const uint2* wrow = wsm + (size_t)((ch * a.KH + kh) * KW) * 32 + lane;
+                arow += a_khstep;
+                wrow += KW * 32;
                 if constexpr (KWT > 0) {
                     constexpr int U = (P - 1) * SWT + KWT;
                     constexpr bool WINDOW = (U <= 12);
@@ -292,9 +300,9 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
         int ms[P];
 #pragma unroll
         for (int p = 0; p < P; ++p) ms[p] = ms_s[r * a.TW + wq + p];      // broadcast loads
-        const bool transposed = (a.e.ow == 1) || (a.e.out == nullptr);
-        const bool has_res = (EPI == 1) && a.e.res != nullptr;
-        const bool want_bits = (EPI == 1) && a.e.obits != nullptr;
+        const bool transposed = CL ? false : ((a.e.ow == 1) || (a.e.out == nullptr));
+        const bool has_res = FUSED && a.e.res != nullptr;
+        const bool want_bits = FUSED && a.e.obits != nullptr;
         // ReLU output with no affine in front of the next sign(): "non-zero" and "positive" coincide
         const bool bits_pre = has_res && a.e.res_after_act && a.e.bits_pre_res;
         const bool relu_bits = a.e.nx_relu || (a.e.act == BNN_ACT_RELU && a.e.nx_scale == nullptr &&
@@ -320,7 +328,7 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
                 // ---- fused epilogue.  `full` groups (all P pixels and all 32 channels valid) take the
                 //      predicate-free path; strides are 32-bit here (the host checked the tensors fit)
                 float res[P];
-                const bool res_direct = has_res && a.e.rw != 1;
+                const bool res_direct = CL ? has_res : (has_res && a.e.rw != 1);
                 if (has_res && !res_direct) {
                     // NCHW residual: tile [32 ch][P px] through shared memory, coalesced along pixels
                     const float* rbase = res_n + ho * e_rh;
@@ -490,7 +498,7 @@ static KernelFn pick_pc(int P, int C) {
     return nullptr;
 }
 
-// EPI 0 = reference epilogue (both inner-loop modes, for A/B runs); EPI 1 = fused epilogue (carry-save only)
+// EPI 0 = reference epilogue (both inner-loop modes, for A/B runs); EPI 1 / 2 = fused epilogue (carry-save only)
 static KernelFn pick_kernel(const Plan& p, int epi) {
     if (epi == 0) {
         if (p.kwt == 3 && p.swt == 1) return p.mode ? pick_pc<3, 1, 1, 0>(p.P, p.C) : pick_pc<3, 1, 0, 0>(p.P, p.C);
@@ -498,10 +506,24 @@ static KernelFn pick_kernel(const Plan& p, int epi) {
         if (p.kwt == 1 && p.swt == 1) return pick_pc<1, 1, 0, 0>(p.P, p.C);
         return pick_pc<0, 0, 0, 0>(p.P, p.C);
     }
+    if (epi == 2) {
+        if (p.kwt == 3 && p.swt == 1) return pick_pc<3, 1, 1, 2>(p.P, p.C);
+        if (p.kwt == 3 && p.swt == 2) return pick_pc<3, 2, 1, 2>(p.P, p.C);
+        if (p.kwt == 1 && p.swt == 1) return pick_pc<1, 1, 0, 2>(p.P, p.C);
+        return pick_pc<0, 0, 0, 2>(p.P, p.C);
+    }
     if (p.kwt == 3 && p.swt == 1) return pick_pc<3, 1, 1, 1>(p.P, p.C);
     if (p.kwt == 3 && p.swt == 2) return pick_pc<3, 2, 1, 1>(p.P, p.C);
     if (p.kwt == 1 && p.swt == 1) return pick_pc<1, 1, 0, 1>(p.P, p.C);
     return pick_pc<0, 0, 0, 1>(p.P, p.C);
+}
+
+// 0 = reference epilogue, 1 = fused, 2 = fused with channel-contiguous residual / output (or neither)
+static int epilogue_kind(const bnn_epilogue& ep) {
+    const bool fused = ep.bn_scale || ep.residual || ep.act != BNN_ACT_NONE || ep.out_bits || ep.nx_scale;
+    if (!fused) return 0;
+    const bool cl = (!ep.out || ep.ostride_c == 1) && (!ep.residual || ep.rstride_c == 1);
+    return cl ? 2 : 1;
 }
 
 static int ceil_div(int a, int b) { return (a + b - 1) / b; }
@@ -632,7 +654,7 @@ static int launch_bconv(const void* abits, const void* wbits, const bnn_conv_geo
         if (dev < 64) cached_sms[dev] = sms;
     }
 
-    const int epi = (ep.bn_scale || ep.residual || ep.act != BNN_ACT_NONE || ep.out_bits || ep.nx_scale) ? 1 : 0;
+    const int epi = epilogue_kind(ep);
     {   // the kernel indexes inside one image row with 32-bit element offsets
         const long long lim = 0x7fffffffLL;
         auto ab = [](int64_t v) { return (long long)(v < 0 ? -v : v); };
@@ -714,7 +736,7 @@ extern "C" int bnn_bconv2d_tune(const void* abits, const void* wbits, const bnn_
     const int Ho = out_dim(g.h, g.kh, g.stride_h, g.pad_h, g.dil_h);
     const int Wo = out_dim(g.w, g.kw, g.stride_w, g.pad_w, g.dil_w);
     if (Ho <= 0 || Wo <= 0) return BNN_E_SHAPE;
-    const int epi = (ep.bn_scale || ep.residual || ep.act != BNN_ACT_NONE || ep.out_bits || ep.nx_scale) ? 1 : 0;
+    const int epi = epilogue_kind(ep);
     if (epi) flags &= ~BNN_F_NO_CSA;
     const PlanKey key = plan_key(g, epi, flags);
     {

@@ -57,6 +57,16 @@ def test_fused_epilogue_bit_exact_vs_oracle(fc, flags):
                                 stride=(g.stride_h, g.stride_w), padding=(g.pad_h, g.pad_w), flags=flags,
                                 nx_relu=d["nx_relu"], bits_before_residual=d["bits_pre"])
     assert torch.equal(bits2.bits, bits.bits)
+    # channels_last residual and output: the NHWC-specialised instances (EPI 2) of the same kernel
+    res_cl = None if d["residual"] is None else _d(d["residual"]).contiguous(memory_format=torch.channels_last)
+    out3, bits3 = BF.bconv2d_fused(act, wts, bias=_d(d["bias"]), post=_d(d["post"]), bn=pair(d["bn"]),
+                                   residual=res_cl, residual_after_act=d["res_after"], activation=d["act"],
+                                   act_slope=_d(d["slope"]), want_out=True, want_bits=True, nx=pair(d["nx"]),
+                                   stride=(g.stride_h, g.stride_w), padding=(g.pad_h, g.pad_w), flags=flags,
+                                   nx_relu=d["nx_relu"], bits_before_residual=d["bits_pre"], channels_last=True)
+    assert out3.is_contiguous(memory_format=torch.channels_last) or out3.shape[1] == 1
+    assert np.array_equal(out3.cpu().numpy(), want_out)
+    assert torch.equal(bits3.bits, bits.bits)
 
 
 @pytest.mark.parametrize("shape,k,ceil", [((2, 64, 8, 8), 2, True), ((1, 70, 7, 9), 2, True), ((1, 64, 7, 9), 2, False),
