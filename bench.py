@@ -369,7 +369,7 @@ def main():
         e0.record(pipe.compute_stream)
         for _ in range(args.steps):
             pipe.submit(x_host)
-        e1.record(pipe.compute_stream)
+        e1.record(pipe.d2h_stream)            # behind the last logits download (which waits for the last forward)
         last_logits = pipe.drain()
         sync_all()
         ms_e2e_t = torch.tensor([e0.elapsed_time(e1)], device=dev)

@@ -21,9 +21,11 @@ class HostPipeline:
         self.post = post                                   # e.g. the logits all-gather of sharded inference
         self.copy_stream = torch.cuda.Stream(self.device)
         self.compute_stream = torch.cuda.Stream(self.device)
+        self.d2h_stream = torch.cuda.Stream(self.device)       # logits download off the compute stream
         self.bufs = [torch.empty(example.shape, dtype=example.dtype, device=self.device) for _ in range(2)]
         self.ready = [torch.cuda.Event() for _ in range(2)]
         self.done = [torch.cuda.Event() for _ in range(2)]
+        self.read = [torch.cuda.Event() for _ in range(2)]     # slot k's logits have left the device
         self.graphs = [None, None]
         self.outs = [None, None]
         self.host_out = [None, None, None]      # three pinned result buffers: a retired view survives one more submit
@@ -48,6 +50,7 @@ class HostPipeline:
                 if k == 1:
                     self.host_out[2] = torch.empty(final.shape, dtype=final.dtype).pin_memory()
                 self.done[k].record(self.compute_stream)
+                self.read[k].record(self.compute_stream)
         torch.cuda.synchronize(self.device)
 
     @property
@@ -77,16 +80,22 @@ class HostPipeline:
             self.bufs[k].copy_(host_batch, non_blocking=True)
             self.ready[k].record(self.copy_stream)
         self.compute_stream.wait_event(self.ready[k])
+        self.compute_stream.wait_event(self.read[k])        # the previous logits of this slot have been downloaded
         with torch.cuda.stream(self.compute_stream), torch.no_grad():
             if self.graphs[k] is not None:
                 self.graphs[k].replay()
             else:
                 self.outs[k] = self.engine(self.bufs[k])
             final = self.post(self.outs[k]) if self.post is not None else self.outs[k]
-            self.host_out[hk].copy_(final, non_blocking=True)
             self.done[k].record(self.compute_stream)
+        # the download runs on its own stream: the next forward does not queue behind a PCIe round trip
+        self.d2h_stream.wait_event(self.done[k])
         fin = torch.cuda.Event()
-        fin.record(self.compute_stream)
+        with torch.cuda.stream(self.d2h_stream):
+            final.record_stream(self.d2h_stream)
+            self.host_out[hk].copy_(final, non_blocking=True)
+            self.read[k].record(self.d2h_stream)
+            fin.record(self.d2h_stream)
         self.pending.append((hk, fin))
         return retired
 
