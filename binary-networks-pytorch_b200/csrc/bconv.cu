@@ -72,7 +72,10 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
     extern __shared__ __align__(1024) unsigned char smem[];
     // EPI 0: reference epilogue.  EPI 1: fused epilogue, any strides.  EPI 2: fused epilogue with channel-contiguous
     // (NHWC) residual and output -- what the fused engine always uses: the pixel-contiguous transposes are compiled out
-    constexpr bool FUSED = EPI >= 1, CL = EPI == 2;
+    // EPI 3: the lean NHWC epilogue of post-activation ReLU blocks (BatchNorm, optional shortcut add BEFORE the ReLU,
+    // optional fp32 store, optional planes where "non-zero" == "positive"), launched only when every pixel group and
+    // every channel block is complete -- no bounds predicates, no stride arithmetic beyond one multiply per access.
+    constexpr bool FUSED = EPI >= 1, CL = EPI >= 2, LEAN = EPI == 3;
     constexpr int PITCH = P | 1;      // odd pitch: conflict-free transposes
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
     uint4* act = reinterpret_cast<uint4*>(smem + 128);
@@ -300,6 +303,53 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
         int ms[P];
 #pragma unroll
         for (int p = 0; p < P; ++p) ms[p] = ms_s[r * a.TW + wq + p];      // broadcast loads
+        if constexpr (LEAN) {
+            const bool has_res = a.e.res != nullptr, has_out = a.e.out != nullptr;
+            const int cch = blk0 * 32 + lane;
+            const float* rp = res_n + (ho * e_rh + wo_first * e_rw + cch);      // dereferenced only if has_res
+            float* op = out_n + (ho * e_oh + wo_first * e_ow + cch);            // dereferenced only if has_out
+            uint32_t sw[P][C];                   // ballots are warp-uniform: every lane holds every word
+#pragma unroll
+            for (int j = 0; j < C; ++j) {
+                const float k0 = epc[j * 32 + lane], k1 = epc[32 * C + j * 32 + lane];
+                float res[P];
+                if (has_res) {
+#pragma unroll
+                    for (int p = 0; p < P; ++p) res[p] = __ldg(rp + p * e_rw + j * 32);
+                }
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    float v = __fmaf_rn(k0, (float)(ms[p] - 2 * acc[p][j]), k1);
+                    if (has_res) v = __fadd_rn(v, res[p]);
+                    v = fmaxf(v, 0.0f);
+                    if (has_out) op[p * e_ow + j * 32] = v;
+                    sw[p][j] = __ballot_sync(0xffffffffu, v > 0.0f);
+                }
+            }
+            if (a.e.obits != nullptr) {
+                // lane 0 parks the words in the warp's staging area; lane p then writes pixel p's 16-byte units
+                // {s_lo, s_hi, m_lo, m_hi} with m == s (ReLU output), consecutive lanes -> consecutive units
+                uint32_t* sb = reinterpret_cast<uint32_t*>(stg);
+                __syncwarp();
+                if (lane == 0) {
+#pragma unroll
+                    for (int p = 0; p < P; ++p)
+#pragma unroll
+                        for (int j = 0; j < C; ++j) sb[p * C + j] = sw[p][j];
+                }
+                __syncwarp();
+                if (lane < P) {
+#pragma unroll
+                    for (int j = 0; j < C; j += 2) {
+                        const uint32_t s0 = sb[lane * C + j], s1 = sb[lane * C + (C >= 2 ? j + 1 : j)];
+                        const size_t unit_idx = (((size_t)n * a.e.ochunks + ((blk0 + j) >> 1)) * a.Ho + ho) * a.Wo + wo_first + lane;
+                        a.e.obits[unit_idx] = make_uint4(s0, s1, s0, s1);
+                    }
+                }
+                __syncwarp();
+            }
+            continue;
+        }
         const bool transposed = CL ? false : ((a.e.ow == 1) || (a.e.out == nullptr));
         const bool has_res = FUSED && a.e.res != nullptr;
         const bool want_bits = FUSED && a.e.obits != nullptr;
@@ -491,9 +541,12 @@ typedef void (*KernelFn)(const CUtensorMap, const ConvArgs);
 template <int KWT, int SWT, int MODE, int EPI>
 static KernelFn pick_pc(int P, int C) {
 #define BNN_PC(p, c) if (P == p && C == c) return bconv_kernel<p, c, KWT, SWT, MODE, EPI>;
-    BNN_PC(8, 4) BNN_PC(8, 2) BNN_PC(8, 1)
-    BNN_PC(7, 4) BNN_PC(7, 2) BNN_PC(7, 1)
-    BNN_PC(4, 4) BNN_PC(4, 2) BNN_PC(4, 1)
+    BNN_PC(8, 4) BNN_PC(8, 2)
+    BNN_PC(7, 4) BNN_PC(7, 2)
+    BNN_PC(4, 4) BNN_PC(4, 2)
+    if constexpr (EPI != 3) {          // the lean epilogue writes whole 64-channel units: C >= 2 only
+        BNN_PC(8, 1) BNN_PC(7, 1) BNN_PC(4, 1)
+    }
 #undef BNN_PC
     return nullptr;
 }
@@ -505,6 +558,12 @@ static KernelFn pick_kernel(const Plan& p, int epi) {
         if (p.kwt == 3 && p.swt == 2) return p.mode ? pick_pc<3, 2, 1, 0>(p.P, p.C) : pick_pc<3, 2, 0, 0>(p.P, p.C);
         if (p.kwt == 1 && p.swt == 1) return pick_pc<1, 1, 0, 0>(p.P, p.C);
         return pick_pc<0, 0, 0, 0>(p.P, p.C);
+    }
+    if (epi == 3) {
+        if (p.kwt == 3 && p.swt == 1) return pick_pc<3, 1, 1, 3>(p.P, p.C);
+        if (p.kwt == 3 && p.swt == 2) return pick_pc<3, 2, 1, 3>(p.P, p.C);
+        if (p.kwt == 1 && p.swt == 1) return pick_pc<1, 1, 0, 3>(p.P, p.C);
+        return pick_pc<0, 0, 0, 3>(p.P, p.C);
     }
     if (epi == 2) {
         if (p.kwt == 3 && p.swt == 1) return pick_pc<3, 1, 1, 2>(p.P, p.C);
@@ -523,7 +582,17 @@ static int epilogue_kind(const bnn_epilogue& ep) {
     const bool fused = ep.bn_scale || ep.residual || ep.act != BNN_ACT_NONE || ep.out_bits || ep.nx_scale;
     if (!fused) return 0;
     const bool cl = (!ep.out || ep.ostride_c == 1) && (!ep.residual || ep.rstride_c == 1);
-    return cl ? 2 : 1;
+    if (!cl) return 1;
+    // 3: post-activation ReLU block (BatchNorm folded, shortcut added before the ReLU, planes of the ReLU output);
+    // whether the lean instance can actually run also depends on the tile plan, see lean_plan_ok()
+    const bool lean = ep.act == BNN_ACT_RELU && !ep.nx_scale && !ep.nx_relu && !ep.residual_after_act &&
+                      !ep.bits_before_residual;
+    return lean ? 3 : 2;
+}
+
+// the lean epilogue has no bounds predicates: every pixel group and every channel block must be complete
+static bool lean_plan_ok(const Plan& pl, const bnn_conv_geom& g, int Wo) {
+    return pl.C >= 2 && Wo % pl.P == 0 && g.c_out % (32 * pl.C) == 0;
 }
 
 static int ceil_div(int a, int b) { return (a + b - 1) / b; }
@@ -671,7 +740,7 @@ static int launch_bconv(const void* abits, const void* wbits, const bnn_conv_geo
     if (forced) pl = *forced;
     else rc = make_plan(g, Ho, Wo, flags, sms, &pl, epi);
     if (rc) return rc;
-    KernelFn fn = pick_kernel(pl, epi);
+    KernelFn fn = pick_kernel(pl, (epi == 3 && !lean_plan_ok(pl, g, Wo)) ? 2 : epi);
     if (!fn) return BNN_E_UNSUPPORTED;
 
     ConvArgs a{};

@@ -67,6 +67,16 @@ def test_fused_epilogue_bit_exact_vs_oracle(fc, flags):
     assert out3.is_contiguous(memory_format=torch.channels_last) or out3.shape[1] == 1
     assert np.array_equal(out3.cpu().numpy(), want_out)
     assert torch.equal(bits3.bits, bits.bits)
+    for wo_, wb_ in ((False, True), (True, False)):          # planes only / fp32 only through the NHWC instances
+        out4, bits4 = BF.bconv2d_fused(act, wts, bias=_d(d["bias"]), post=_d(d["post"]), bn=pair(d["bn"]),
+                                       residual=res_cl, residual_after_act=d["res_after"], activation=d["act"],
+                                       act_slope=_d(d["slope"]), want_out=wo_, want_bits=wb_, nx=pair(d["nx"]),
+                                       stride=(g.stride_h, g.stride_w), padding=(g.pad_h, g.pad_w), flags=flags,
+                                       nx_relu=d["nx_relu"], bits_before_residual=d["bits_pre"], channels_last=True)
+        if wo_:
+            assert np.array_equal(out4.cpu().numpy(), want_out)
+        if wb_:
+            assert torch.equal(bits4.bits, bits.bits)
 
 
 @pytest.mark.parametrize("shape,k,ceil", [((2, 64, 8, 8), 2, True), ((1, 70, 7, 9), 2, True), ((1, 64, 7, 9), 2, False),

@@ -185,6 +185,11 @@ FUSED_CASES = [
     dict(name="ragged_c1", cin=70, cout=24, hw=(6, 5), bn=True, act=1, res="pre", bits=True, out=True, bias=True, post=True),
     dict(name="c96_s2", cin=64, cout=96, hw=(10, 10), stride=2, bn=True, act=2, bits=True, out=True, nx=True),
     dict(name="hblock_stage", cin=128, cout=64, hw=(8, 8), res="post", bits=True, out=True, nx=True, nx_relu=True, bits_pre=True),
+    # complete pixel groups for every P in {8, 7, 4} and complete channel blocks: the lean NHWC epilogue (EPI 3) runs
+    dict(name="lean_mid", cin=64, cout=128, hw=(3, 56), bn=True, act=1, bits=True, out=False),
+    dict(name="lean_out", cin=64, cout=128, hw=(3, 56), bn=True, act=1, res="pre", bits=True, out=True),
+    dict(name="lean_s2", cin=128, cout=128, hw=(6, 112), stride=2, bn=True, act=1, bits=True, out=True),
+    dict(name="lean_out_only", cin=64, cout=256, hw=(2, 56), bn=True, act=1, res="pre", bits=False, out=True, bias=True, post=True),
 ]
 
 
