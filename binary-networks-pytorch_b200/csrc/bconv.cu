@@ -309,42 +309,42 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
             const float* rp = res_n + (ho * e_rh + wo_first * e_rw + cch);      // dereferenced only if has_res
             float* op = out_n + (ho * e_oh + wo_first * e_ow + cch);            // dereferenced only if has_out
             uint32_t sw[P][C];                   // ballots are warp-uniform: every lane holds every word
+            float res[C][P];
+            if (has_res) {                       // every shortcut line of the group in flight before the first use
+#pragma unroll
+                for (int j = 0; j < C; ++j)
+#pragma unroll
+                    for (int p = 0; p < P; ++p) res[j][p] = __ldg(rp + p * e_rw + j * 32);
+            }
 #pragma unroll
             for (int j = 0; j < C; ++j) {
                 const float k0 = epc[j * 32 + lane], k1 = epc[32 * C + j * 32 + lane];
-                float res[P];
-                if (has_res) {
-#pragma unroll
-                    for (int p = 0; p < P; ++p) res[p] = __ldg(rp + p * e_rw + j * 32);
-                }
 #pragma unroll
                 for (int p = 0; p < P; ++p) {
                     float v = __fmaf_rn(k0, (float)(ms[p] - 2 * acc[p][j]), k1);
-                    if (has_res) v = __fadd_rn(v, res[p]);
+                    if (has_res) v = __fadd_rn(v, res[j][p]);
                     v = fmaxf(v, 0.0f);
                     if (has_out) op[p * e_ow + j * 32] = v;
                     sw[p][j] = __ballot_sync(0xffffffffu, v > 0.0f);
                 }
             }
             if (a.e.obits != nullptr) {
-                // lane 0 parks the words in the warp's staging area; lane p then writes pixel p's 16-byte units
-                // {s_lo, s_hi, m_lo, m_hi} with m == s (ReLU output), consecutive lanes -> consecutive units
-                uint32_t* sb = reinterpret_cast<uint32_t*>(stg);
+                // lane 0 parks finished 16-byte units {s_lo, s_hi, m_lo, m_hi} (m == s: ReLU output) in the warp's
+                // staging area; lane p then stores pixel p's units: consecutive lanes -> consecutive units
+                uint4* sb = reinterpret_cast<uint4*>(stg);
                 __syncwarp();
                 if (lane == 0) {
 #pragma unroll
                     for (int p = 0; p < P; ++p)
 #pragma unroll
-                        for (int j = 0; j < C; ++j) sb[p * C + j] = sw[p][j];
+                        for (int j = 0; j < C; j += 2) sb[p * (C / 2) + j / 2] = make_uint4(sw[p][j], sw[p][j + 1], sw[p][j], sw[p][j + 1]);
                 }
                 __syncwarp();
                 if (lane < P) {
+                    const size_t unit0 = (((size_t)n * a.e.ochunks + (blk0 >> 1)) * a.Ho + ho) * a.Wo + wo_first + lane;
+                    const size_t ustep = (size_t)a.Ho * a.Wo;
 #pragma unroll
-                    for (int j = 0; j < C; j += 2) {
-                        const uint32_t s0 = sb[lane * C + j], s1 = sb[lane * C + (C >= 2 ? j + 1 : j)];
-                        const size_t unit_idx = (((size_t)n * a.e.ochunks + ((blk0 + j) >> 1)) * a.Ho + ho) * a.Wo + wo_first + lane;
-                        a.e.obits[unit_idx] = make_uint4(s0, s1, s0, s1);
-                    }
+                    for (int j = 0; j < C; j += 2) a.e.obits[unit0 + (j / 2) * ustep] = sb[lane * (C / 2) + j / 2];
                 }
                 __syncwarp();
             }
