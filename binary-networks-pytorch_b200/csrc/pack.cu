@@ -137,6 +137,64 @@ pack_act_cl_kernel(const float* __restrict__ x, long long sn, long long sh, long
     }
 }
 
+// Dense NHWC fast path (pixel p at x + p * C, C = 64 * NCH, no pooling): a warp packs PL_PPW consecutive pixels with
+// every load of all of them in flight (4 * 2 * NCH independent 128-byte lines per warp), the optional pre-sign affine
+// held in registers, pixel -> (image, position) by one division per warp.  HBM-streaming: 4 B/element in, 2 bits out.
+constexpr int PL_PPW = 4;
+
+template <int NCH>
+__global__ void __launch_bounds__(256)
+pack_act_cl_dense_kernel(const float* __restrict__ x, int pixels, int HW, const float* __restrict__ pre_scale,
+                         const float* __restrict__ pre_shift, int pre_relu, uint4* __restrict__ abits) {
+    constexpr int C = 64 * NCH, NB = 2 * NCH;
+    const int lane = threadIdx.x & 31;
+    const int pix0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * PL_PPW;
+    if (pix0 >= pixels) return;                              // warp-uniform
+    float v[PL_PPW][NB];
+#pragma unroll
+    for (int u = 0; u < PL_PPW; ++u) {
+        const float* px = x + (size_t)(pix0 + u) * C + lane;
+        const bool on = pix0 + u < pixels;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) v[u][b] = on ? __ldg(px + b * 32) : 0.0f;
+    }
+    const bool pre = pre_scale != nullptr;
+    float sc[NB], sf[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        sc[b] = pre ? __ldg(pre_scale + b * 32 + lane) : 1.0f;
+        sf[b] = pre ? __ldg(pre_shift + b * 32 + lane) : 0.0f;
+    }
+    int n = pix0 / HW, hw = pix0 - n * HW;
+#pragma unroll
+    for (int u = 0; u < PL_PPW; ++u) {
+        if (pix0 + u >= pixels) break;                       // warp-uniform
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+            uint32_t s_[2], m_[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float t = v[u][2 * ch + h];
+                if (pre) t = __fadd_rn(__fmul_rn(t, sc[2 * ch + h]), sf[2 * ch + h]);      // same two roundings as the generic kernels
+                s_[h] = __ballot_sync(0xffffffffu, t > 0.0f);
+                m_[h] = __ballot_sync(0xffffffffu, t > 0.0f || (t < 0.0f && !pre_relu));
+            }
+            if (lane == 0) abits[((size_t)n * NCH + ch) * HW + hw] = make_uint4(s_[0], s_[1], m_[0], m_[1]);
+        }
+        if (++hw == HW) { hw = 0; ++n; }
+    }
+}
+
+template <int NCH>
+static int launch_pack_dense(const float* x, long long pixels, int HW, const float* pre_scale, const float* pre_shift,
+                             int pre_relu, void* abits, cudaStream_t stream) {
+    const long long warps = (pixels + PL_PPW - 1) / PL_PPW, blocks = (warps + 7) / 8;
+    if (blocks > 0x7fffffffLL || pixels > 0x7fffffffLL - PL_PPW) return BNN_E_UNSUPPORTED;
+    pack_act_cl_dense_kernel<NCH><<<(unsigned)blocks, 256, 0, stream>>>(x, (int)pixels, HW, pre_scale, pre_shift, pre_relu, (uint4*)abits);
+    count_launch(1);
+    return (int)cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------
 // weights: one CTA per output channel.
 // ---------------------------------------------------------------------------
@@ -239,6 +297,17 @@ static int launch_pack(const float* x, int64_t sn, int64_t sc, int64_t sh, int64
         if (ho <= 0 || wo <= 0) return BNN_E_SHAPE;
     }
     const int threads = 256;
+    if (sc == 1 && pool <= 1 && c % 64 == 0 && sw == c && sh == (int64_t)w * c && sn == (int64_t)h * w * c) {
+        // dense NHWC: the streaming fast path
+        const long long pixels = (long long)n * h * w;
+        switch (c / 64) {
+            case 1: return launch_pack_dense<1>(x, pixels, h * w, pre_scale, pre_shift, pre_relu, abits, stream);
+            case 2: return launch_pack_dense<2>(x, pixels, h * w, pre_scale, pre_shift, pre_relu, abits, stream);
+            case 4: return launch_pack_dense<4>(x, pixels, h * w, pre_scale, pre_shift, pre_relu, abits, stream);
+            case 8: return launch_pack_dense<8>(x, pixels, h * w, pre_scale, pre_shift, pre_relu, abits, stream);
+            default: break;
+        }
+    }
     if (sc == 1 && c >= 32) {
         // channels are contiguous: warp-per-pixel ballot kernel
         const long long pixels = (long long)n * ho * wo;

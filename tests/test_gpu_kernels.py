@@ -52,6 +52,28 @@ def test_pack_activations_bit_exact(shape, layout):
     assert np.array_equal(_bits(packed.bits), ab)
 
 
+@pytest.mark.parametrize("shape", [(3, 128, 5, 7), (1, 256, 3, 3), (2, 512, 2, 3), (5, 64, 3, 3), (2, 256, 16, 16)])
+@pytest.mark.parametrize("pre,pre_relu", [(False, False), (True, False), (True, True)])
+def test_pack_dense_nhwc_fast_path_bit_exact(shape, pre, pre_relu):
+    """Dense channels_last tensors with C in {64,128,256,512} take the streaming kernel (4 pixels per warp): ragged pixel
+    counts, NaN / -0 / denormals, the pre-sign affine and the ReLU-in-front form, all against the oracle."""
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal(shape).astype(np.float32)
+    x[rng.random(shape) < 0.3] = 0.0
+    flat = x.reshape(-1)
+    flat[::13] = -0.0
+    flat[5::97] = np.nan
+    flat[7::101] = 1e-42
+    c = shape[1]
+    sc = (0.5 + rng.random(c)).astype(np.float32) if pre else None
+    sh = rng.standard_normal(c).astype(np.float32) if pre else None
+    xt = torch.from_numpy(x).to(DEV).contiguous(memory_format=torch.channels_last)
+    got = BF.pack_activations(xt, pre=None if not pre else (torch.from_numpy(sc).to(DEV), torch.from_numpy(sh).to(DEV)),
+                              pre_relu=pre_relu)
+    want = co.pack_act(x, pre_scale=sc, pre_shift=sh, pre_relu=pre_relu)
+    assert np.array_equal(_bits(got.bits), want)
+
+
 @pytest.mark.parametrize("wshape,center,alpha", [((64, 64, 3, 3), True, True), ((40, 70, 3, 3), True, True),
                                                  ((3, 3, 1, 1), False, True), ((128, 64, 1, 1), False, False),
                                                  ((1000, 512), True, True), ((8, 16, 5), False, True),
