@@ -42,9 +42,9 @@ __device__ __forceinline__ float pooled_value(const float* base, int sh, int sw,
     return __fdiv_rn(sum, (float)(hmax * wmax));
 }
 
-// NCH > 0: chunks known at compile time, and FAST = 2x2 windows that are always full over a multiple of 64 channels
-// (every ResNet shape): straight-line code, 32 loads in flight per lane.  NCH == 0: any geometry.
-template <int NCH, bool FAST>
+// NCH > 0: chunks known at compile time.  POOL = 1 / 2: no pooling / 2x2 windows that are always full, over a multiple
+// of 64 channels (every ResNet shape): straight-line code, 8 / 32 loads in flight per lane.  POOL == 0: any geometry.
+template <int NCH, int POOL>
 __global__ void __launch_bounds__(SC_WARPS * 32, 3)
 shortcut_kernel(const __grid_constant__ ShortcutArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -56,7 +56,8 @@ shortcut_kernel(const __grid_constant__ ShortcutArgs a) {
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int pix0 = blockIdx.x * SC_PIX;
-    const int k = FAST ? 2 : (a.pool > 1 ? a.pool : 1);
+    constexpr bool FAST = POOL > 0;
+    const int k = FAST ? POOL : (a.pool > 1 ? a.pool : 1);
     // in-image offsets fit 32 bits (host-checked); only the image base is a 64-bit product
     const int sh = (int)a.sh, sw = (int)a.sw;
 
@@ -82,7 +83,7 @@ shortcut_kernel(const __grid_constant__ ShortcutArgs a) {
 #pragma unroll 1
         for (int ch = 0; ch < nch; ++ch) {                     // one chunk = 32 loads per lane in flight
             float v[SC_PPW][2];
-            if constexpr (FAST) {
+            if constexpr (POOL == 2) {
                 float t[SC_PPW][2][4];
 #pragma unroll
                 for (int u = 0; u < SC_PPW; ++u)
@@ -98,6 +99,11 @@ shortcut_kernel(const __grid_constant__ ShortcutArgs a) {
 #pragma unroll
                     for (int b = 0; b < 2; ++b)
                         v[u][b] = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(t[u][b][0], t[u][b][1]), t[u][b][2]), t[u][b][3]), 4.0f);
+            } else if constexpr (POOL == 1) {
+#pragma unroll
+                for (int u = 0; u < SC_PPW; ++u)
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) v[u][b] = ok[u] ? __ldg(base[u] + ch * 64 + b * 32) : 0.0f;
             } else {
 #pragma unroll
                 for (int u = 0; u < SC_PPW; ++u)
@@ -182,11 +188,11 @@ shortcut_kernel(const __grid_constant__ ShortcutArgs a) {
     }
 }
 
-template <int NCH, bool FAST>
+template <int NCH, int POOL>
 static cudaError_t launch_shortcut(const ShortcutArgs& a, size_t smem, unsigned ctas, cudaStream_t stream) {
-    cudaError_t ce = cudaFuncSetAttribute((const void*)shortcut_kernel<NCH, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t ce = cudaFuncSetAttribute((const void*)shortcut_kernel<NCH, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (ce != cudaSuccess) return ce;
-    shortcut_kernel<NCH, FAST><<<ctas, SC_WARPS * 32, smem, stream>>>(a);
+    shortcut_kernel<NCH, POOL><<<ctas, SC_WARPS * 32, smem, stream>>>(a);
     return cudaGetLastError();
 }
 
@@ -222,12 +228,14 @@ extern "C" int bnn_shortcut_fwd(const float* x, int64_t xs_n, int64_t xs_h, int6
     if ((long long)SC_PIX * c_out >= 0x7fffffffLL) return BNN_E_UNSUPPORTED;
     const unsigned ctas = (unsigned)((pixels + SC_PIX - 1) / SC_PIX);
     cudaStream_t stream = (cudaStream_t)stream_;
-    const bool fast = pool == 2 && h % 2 == 0 && w % 2 == 0 && c_in % 64 == 0 && !(flags & BNN_F_STAGE_LDG);
+    const bool fast = !(flags & BNN_F_STAGE_LDG) && c_in % 64 == 0 &&
+                      ((pool == 2 && h % 2 == 0 && w % 2 == 0) || pool == 1);
     cudaError_t ce;
-    if (fast && a.nch == 1) ce = launch_shortcut<1, true>(a, smem, ctas, stream);
-    else if (fast && a.nch == 2) ce = launch_shortcut<2, true>(a, smem, ctas, stream);
-    else if (fast && a.nch == 4) ce = launch_shortcut<4, true>(a, smem, ctas, stream);
-    else ce = launch_shortcut<0, false>(a, smem, ctas, stream);
+#define BNN_SC(nch_, pool_) if (fast && a.nch == nch_ && pool == pool_) ce = launch_shortcut<nch_, pool_>(a, smem, ctas, stream); else
+    BNN_SC(1, 2) BNN_SC(2, 2) BNN_SC(4, 2) BNN_SC(8, 2) BNN_SC(16, 2)
+    BNN_SC(1, 1) BNN_SC(2, 1) BNN_SC(4, 1) BNN_SC(8, 1) BNN_SC(16, 1)
+    ce = launch_shortcut<0, 0>(a, smem, ctas, stream);
+#undef BNN_SC
     count_launch(1);
     return (int)ce;
 }
