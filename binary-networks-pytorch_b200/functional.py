@@ -260,8 +260,15 @@ def stem(x: torch.Tensor, w_t: torch.Tensor, bn: Tuple[torch.Tensor, torch.Tenso
     return out, (None if bits is None else PackedActivations(bits, n, 64, hp, wp))
 
 
+def shortcut_out_shape(x: torch.Tensor, wts: PackedWeights, pool: int, ceil_mode: bool):
+    n, _, h, w = x.shape
+    k = max(1, int(pool))
+    ho, wo = (-(-h // k), -(-w // k)) if ceil_mode else (h // k, w // k)
+    return (n, wts.c_out, ho, wo)
+
+
 def shortcut(x: torch.Tensor, wts: PackedWeights, pool: int, ceil_mode: bool, *, bias=None, post=None, bn=None,
-             use_alpha: bool = True, flags: int = 0) -> torch.Tensor:
+             use_alpha: bool = True, flags: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """AvgPool(pool) -> sign -> binarized conv1x1 -> BatchNorm of the reference's down-sampling shortcut
     (bnn/models/resnet.py:129-133) in one kernel (bnn_shortcut_fwd).  ``x``: channels_last fp32 [n,c,h,w];
     returns [n,c_out,ho,wo] channels_last.  Bit-identical to ``pack_activations(x, pool=...)`` +
@@ -277,7 +284,11 @@ def shortcut(x: torch.Tensor, wts: PackedWeights, pool: int, ceil_mode: bool, *,
     ho, wo = (-(-h // k), -(-w // k)) if ceil_mode else (h // k, w // k)
     dev = x.device
     with torch.cuda.device(dev):
-        out = torch.empty((n, wts.c_out, ho, wo), dtype=torch.float32, device=dev, memory_format=torch.channels_last)
+        if out is None:
+            out = torch.empty((n, wts.c_out, ho, wo), dtype=torch.float32, device=dev, memory_format=torch.channels_last)
+        elif (tuple(out.shape) != (n, wts.c_out, ho, wo) or out.dtype != torch.float32 or not out.is_cuda
+              or not out.is_contiguous(memory_format=torch.channels_last)):
+            raise native.NativeError(f"out must be a channels_last float32 CUDA tensor of shape {(n, wts.c_out, ho, wo)}")
         rc = native.lib().bnn_shortcut_fwd(x.data_ptr(), x.stride(0), x.stride(2), x.stride(3), n, c, h, w, k,
                                            int(bool(ceil_mode)), wts.bits.data_ptr(), wts.c_out,
                                            wts.alpha.data_ptr() if use_alpha else None, _opt_ptr(bias), _opt_ptr(post),
