@@ -516,7 +516,7 @@ def main():
                     "POPC rate); the POPC term is the larger one for every 3x3 layer, so roofline.frac (HBM) is low by "
                     "construction and this object is the one north_star's '>= 60 % of the tighter roofline' refers to"}
     if world == 1 and not args.no_cpu_baseline:
-        sample, iters = 64, 2
+        sample, iters = 64, 10          # ~6-20 s of host work depending on the box
         rate, threads = cpu_floatsim_rate(model_cpu, sample, iters, None)
         line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
                                 "sample": f"{iters} forwards of {sample} images (oracle/floatsim.py, torch CPU fp32, "
