@@ -40,8 +40,7 @@ constexpr int SM_IN_WORDS = 3 * SM_IR * SM_IPW;                // 2106
 constexpr int SM_IN_WORDS_PAD = (SM_IN_WORDS + 3) & ~3;        // 2108
 constexpr size_t SM_W_BYTES = (size_t)SM_KSTEPS * SM_NT * 32 * 16;          // 45056
 constexpr size_t SM_CONV_BYTES = (size_t)(SM_NPIX + 1) * SM_CPITCH * 4;     // 73728
-constexpr size_t SM_IN_BYTES = (size_t)SM_IN_WORDS_PAD * 8;                 // {hi, lo} word pairs: 16864
-constexpr size_t SM_OPER_BYTES = SM_W_BYTES + SM_IN_BYTES;
+constexpr size_t SM_OPER_BYTES = SM_W_BYTES + 2 * (size_t)SM_IN_WORDS_PAD * 4;
 constexpr size_t SM_SMEM = 128 + (SM_CONV_BYTES > SM_OPER_BYTES ? SM_CONV_BYTES : SM_OPER_BYTES);
 static_assert(SM_WARPS * SM_MT * 16 >= SM_NPIX, "m tiles must cover the conv tile");
 static_assert(SM_PH == SM_WARPS, "one warp per pooled row of the tile");
@@ -72,67 +71,74 @@ __device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
-constexpr int SM_STAGE_ITERS = (SM_IN_WORDS + SM_WARPS * 32 - 1) / (SM_WARPS * 32);      // 9
+template <bool CHAIN>
+__global__ void __launch_bounds__(SM_WARPS * 32, 2)
+stem_mma_kernel(const __grid_constant__ StemMmaArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+    const uint4* w_s = reinterpret_cast<const uint4*>(smem + 128);
+    uint32_t* in_hi = reinterpret_cast<uint32_t*>(smem + 128 + SM_W_BYTES);
+    uint32_t* in_lo = in_hi + SM_IN_WORDS_PAD;
+    float* conv_s = reinterpret_cast<float*>(smem + 128);        // aliases the operands after the MMA phase
 
-struct TilePos { int n, ph0, pw0, cr0, cc0, hi0, wi0; };
-
-__device__ __forceinline__ TilePos tile_pos(const StemMmaArgs& a, int tile) {
-    TilePos p;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    int tile = blockIdx.x;
     const int tw = tile % a.tiles_w; tile /= a.tiles_w;
     const int th = tile % a.tiles_h;
-    p.n = tile / a.tiles_h;
-    p.ph0 = th * SM_PH; p.pw0 = tw * SM_PW;
-    p.cr0 = 2 * p.ph0 - 1; p.cc0 = 2 * p.pw0 - 1;            // first conv row / col of the tile
-    p.hi0 = 2 * p.cr0 - 3; p.wi0 = 2 * p.cc0 - 3;            // first input row / col of the window
-    return p;
-}
+    const int n = tile / a.tiles_h;
+    const int ph0 = th * SM_PH, pw0 = tw * SM_PW;
+    const int cr0 = 2 * ph0 - 1, cc0 = 2 * pw0 - 1;            // first conv row / col of the tile
+    const int hi0 = 2 * cr0 - 3, wi0 = 2 * cc0 - 3;            // first input row / col of the window
 
-// Input window of one tile, 256 threads (tid 0..255): fp32 loads into registers (all in flight at once) ...
-// thread -> pair i = tid + 256 k of the window, (rf, pc) = divmod(i, 18) kept incrementally (256 = 14 * 18 + 4);
-// rf = c_in * 39 + window row.  32-bit offsets inside the image (3 * H * W < 2^31, checked by the caller).
-__device__ __forceinline__ void stage_load(const StemMmaArgs& a, const TilePos& p, int tid, float (&v0)[SM_STAGE_ITERS],
-                                           float (&v1)[SM_STAGE_ITERS]) {
-    const float* xn = a.x + (size_t)p.n * 3 * a.H * a.W;
-    int rf = tid / SM_IPW, pc = tid - rf * SM_IPW;
-#pragma unroll
-    for (int k = 0; k < SM_STAGE_ITERS; ++k) {
-        const int ci = (rf >= SM_IR) + (rf >= 2 * SM_IR);
-        const int hi = p.hi0 + rf - ci * SM_IR, wi = p.wi0 + 2 * pc;
-        const bool rowok = (unsigned)hi < (unsigned)a.H && (k + 1 < SM_STAGE_ITERS || rf < 3 * SM_IR);
-        const int off = (ci * a.H + hi) * a.W + wi;
-        const bool ok0 = rowok && (unsigned)wi < (unsigned)a.W;
-        const bool ok1 = rowok && pc < SM_IPW - 1 && (unsigned)(wi + 1) < (unsigned)a.W;
-        v0[k] = ok0 ? __ldg(xn + off) : 0.0f;
-        v1[k] = ok1 ? __ldg(xn + off + 1) : 0.0f;
-        rf += (SM_WARPS * 32) / SM_IPW; pc += (SM_WARPS * 32) % SM_IPW;
-        if (pc >= SM_IPW) { pc -= SM_IPW; rf += 1; }
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+        mbar_expect_tx(bar, (unsigned)SM_W_BYTES);
+        bulk_load_1d(const_cast<uint4*>(w_s), a.wfrag, (unsigned)SM_W_BYTES, bar);
     }
-}
-// ... and their conversion to scaled {hi, lo} fp16 word pairs in shared memory; zero fill = the convolution's padding.
-// Column 35 of a row is the zero-weight eighth tap of the last pixel: it must be finite, so it is zero as well.
-__device__ __forceinline__ void stage_store(const StemMmaArgs& a, int tid, const float (&v0)[SM_STAGE_ITERS],
-                                            const float (&v1)[SM_STAGE_ITERS], uint2* in_hl) {
+    // input window: fp32 -> scaled (hi, lo) fp16 pairs; zero fill = the convolution's padding.  Column 35 of a
+    // row is the zero-weight eighth tap of the last pixel: it must be finite, so it is zero as well.
+    {
+        // thread -> word i = tid + 256 k of the window, (rf, pc) = divmod(i, 18) kept incrementally (256 = 14 * 18 + 4);
+        // rf = c_in * 39 + window row.  32-bit offsets inside the image (3 * H * W < 2^31, checked by the caller).
+        constexpr int ITERS = (SM_IN_WORDS + SM_WARPS * 32 - 1) / (SM_WARPS * 32);      // 9
+        const float* xn = a.x + (size_t)n * 3 * a.H * a.W;
+        int rf = threadIdx.x / SM_IPW, pc = threadIdx.x - rf * SM_IPW;
+        float v0[ITERS], v1[ITERS];
 #pragma unroll
-    for (int k = 0; k < SM_STAGE_ITERS; ++k) {
-        const int i = tid + k * SM_WARPS * 32;
-        uint32_t h, l;
-        split2(v0[k] * a.x_scale, v1[k] * a.x_scale, h, l);
-        if (k + 1 < SM_STAGE_ITERS || i < SM_IN_WORDS) in_hl[i] = make_uint2(h, l);
+        for (int k = 0; k < ITERS; ++k) {                      // all loads in flight before the first conversion
+            const int ci = (rf >= SM_IR) + (rf >= 2 * SM_IR);
+            const int hi = hi0 + rf - ci * SM_IR, wi = wi0 + 2 * pc;
+            const bool rowok = (unsigned)hi < (unsigned)a.H && (k + 1 < ITERS || rf < 3 * SM_IR);
+            const int off = (ci * a.H + hi) * a.W + wi;
+            const bool ok0 = rowok && (unsigned)wi < (unsigned)a.W;
+            const bool ok1 = rowok && pc < SM_IPW - 1 && (unsigned)(wi + 1) < (unsigned)a.W;
+            v0[k] = ok0 ? __ldg(xn + off) : 0.0f;
+            v1[k] = ok1 ? __ldg(xn + off + 1) : 0.0f;
+            rf += (SM_WARPS * 32) / SM_IPW; pc += (SM_WARPS * 32) % SM_IPW;
+            if (pc >= SM_IPW) { pc -= SM_IPW; rf += 1; }
+        }
+#pragma unroll
+        for (int k = 0; k < ITERS; ++k) {
+            const int i = threadIdx.x + k * SM_WARPS * 32;
+            uint32_t h, l;
+            split2(v0[k] * a.x_scale, v1[k] * a.x_scale, h, l);
+            if (k + 1 < ITERS || i < SM_IN_WORDS) { in_hi[i] = h; in_lo[i] = l; }
+        }
     }
-}
+    __syncthreads();
+    mbar_wait(bar, 0);
 
-// implicit GEMM of one tile on mma.sync: 8 warps x 2 m16 tiles x 8 n8 tiles x 11 k16 steps
-template <bool CHAIN>
-__device__ __forceinline__ void mma_phase(const uint4* w_s, const uint2* in_hl, int warp, int lane,
-                                          float (&acc)[SM_MT][SM_NT][4]) {
-    const int g = lane >> 2, t = lane & 3;
+    // ---------------- implicit GEMM on mma.sync ----------------
+    float acc[SM_MT][SM_NT][4];
 #pragma unroll
     for (int mt = 0; mt < SM_MT; ++mt)
 #pragma unroll
         for (int j = 0; j < SM_NT; ++j)
 #pragma unroll
             for (int i = 0; i < 4; ++i) acc[mt][j][i] = 0.0f;
-    int pb[SM_MT][2];                                          // pair offset of (pixel, kw pair t) inside a kernel row
+    int pb[SM_MT][2];                                          // word offset of (pixel, kw pair t) inside a kernel row
 #pragma unroll
     for (int mt = 0; mt < SM_MT; ++mt)
 #pragma unroll
@@ -149,11 +155,11 @@ __device__ __forceinline__ void mma_phase(const uint4* w_s, const uint2* in_hl, 
         const int offA = ((rowA / 7) * SM_IR + rowA % 7) * SM_IPW, offB = ((rowB / 7) * SM_IR + rowB % 7) * SM_IPW;
         uint32_t ah[SM_MT][4], al[SM_MT][4];
 #pragma unroll
-        for (int mt = 0; mt < SM_MT; ++mt) {                   // one LDS.64 = the hi and the lo word of a fragment register
-            const uint2 q0 = in_hl[offA + pb[mt][0]], q1 = in_hl[offA + pb[mt][1]];
-            const uint2 q2 = in_hl[offB + pb[mt][0]], q3 = in_hl[offB + pb[mt][1]];
-            ah[mt][0] = q0.x; ah[mt][1] = q1.x; ah[mt][2] = q2.x; ah[mt][3] = q3.x;
-            al[mt][0] = q0.y; al[mt][1] = q1.y; al[mt][2] = q2.y; al[mt][3] = q3.y;
+        for (int mt = 0; mt < SM_MT; ++mt) {
+            ah[mt][0] = in_hi[offA + pb[mt][0]]; ah[mt][1] = in_hi[offA + pb[mt][1]];
+            ah[mt][2] = in_hi[offB + pb[mt][0]]; ah[mt][3] = in_hi[offB + pb[mt][1]];
+            al[mt][0] = in_lo[offA + pb[mt][0]]; al[mt][1] = in_lo[offA + pb[mt][1]];
+            al[mt][2] = in_lo[offB + pb[mt][0]]; al[mt][3] = in_lo[offB + pb[mt][1]];
         }
 #pragma unroll
         for (int jp = 0; jp < SM_NT; jp += 2) {                // two n tiles x two m tiles = four independent chains
@@ -175,34 +181,31 @@ __device__ __forceinline__ void mma_phase(const uint4* w_s, const uint2* in_hl, 
 #pragma unroll
                     for (int mt = 0; mt < SM_MT; ++mt) mma_f16(acc[mt][jp + jj], ah[mt], b[jj].x, b[jj].y, acc[mt][jp + jj]);
             } else {
-                float d[2][SM_MT][4];
+            float d[2][SM_MT][4];
 #pragma unroll
-                for (int jj = 0; jj < 2; ++jj)
+            for (int jj = 0; jj < 2; ++jj)
 #pragma unroll
-                    for (int mt = 0; mt < SM_MT; ++mt) mma_f16(d[jj][mt], al[mt], b[jj].x, b[jj].y, zero);          // xl * wh
+                for (int mt = 0; mt < SM_MT; ++mt) mma_f16(d[jj][mt], al[mt], b[jj].x, b[jj].y, zero);          // xl * wh
 #pragma unroll
-                for (int jj = 0; jj < 2; ++jj)
+            for (int jj = 0; jj < 2; ++jj)
 #pragma unroll
-                    for (int mt = 0; mt < SM_MT; ++mt) mma_f16(d[jj][mt], ah[mt], b[jj].z, b[jj].w, d[jj][mt]);     // xh * wl
+                for (int mt = 0; mt < SM_MT; ++mt) mma_f16(d[jj][mt], ah[mt], b[jj].z, b[jj].w, d[jj][mt]);     // xh * wl
 #pragma unroll
-                for (int jj = 0; jj < 2; ++jj)
+            for (int jj = 0; jj < 2; ++jj)
 #pragma unroll
-                    for (int mt = 0; mt < SM_MT; ++mt) mma_f16(d[jj][mt], ah[mt], b[jj].x, b[jj].y, d[jj][mt]);     // xh * wh
+                for (int mt = 0; mt < SM_MT; ++mt) mma_f16(d[jj][mt], ah[mt], b[jj].x, b[jj].y, d[jj][mt]);     // xh * wh
 #pragma unroll
-                for (int jj = 0; jj < 2; ++jj)
+            for (int jj = 0; jj < 2; ++jj)
 #pragma unroll
-                    for (int mt = 0; mt < SM_MT; ++mt)
+                for (int mt = 0; mt < SM_MT; ++mt)
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) acc[mt][jp + jj][i] += d[jj][mt][i];
+                    for (int i = 0; i < 4; ++i) acc[mt][jp + jj][i] += d[jj][mt][i];
             }
         }
     }
-}
+    __syncthreads();                                           // every warp is done with the operand buffers
 
-// BN + ReLU of the accumulators into the shared conv tile
-__device__ __forceinline__ void bn_relu_phase(const StemMmaArgs& a, const TilePos& p, const float (&acc)[SM_MT][SM_NT][4],
-                                              float* conv_s, int warp, int lane) {
-    const int g = lane >> 2, t = lane & 3;
+    // ---------------- BN + ReLU into the shared conv tile ----------------
 #pragma unroll
     for (int j = 0; j < SM_NT; ++j) {
         const int ch = 8 * j + 2 * t;
@@ -212,179 +215,50 @@ __device__ __forceinline__ void bn_relu_phase(const StemMmaArgs& a, const TilePo
         for (int mt = 0; mt < SM_MT; ++mt)
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
-                const int px = (warp * SM_MT + mt) * 16 + g + 8 * hh;
-                const int r = px / SM_CC, c = px - r * SM_CC;
+                const int p = (warp * SM_MT + mt) * 16 + g + 8 * hh;
+                const int r = p / SM_CC, c = p - r * SM_CC;
                 // positions outside the conv output are max-pool padding: 0 is neutral after the ReLU
-                const bool ok = (unsigned)(p.cr0 + r) < (unsigned)a.Hc && (unsigned)(p.cc0 + c) < (unsigned)a.Wc && px < SM_NPIX;
+                const bool ok = (unsigned)(cr0 + r) < (unsigned)a.Hc && (unsigned)(cc0 + c) < (unsigned)a.Wc && p < SM_NPIX;
                 float2 v;
                 v.x = ok ? fmaxf(__fmaf_rn(acc[mt][j][2 * hh] * a.inv_scale, gs.x, hs.x), 0.0f) : 0.0f;
                 v.y = ok ? fmaxf(__fmaf_rn(acc[mt][j][2 * hh + 1] * a.inv_scale, gs.y, hs.y), 0.0f) : 0.0f;
-                *reinterpret_cast<float2*>(conv_s + px * SM_CPITCH + ch) = v;
+                *reinterpret_cast<float2*>(conv_s + p * SM_CPITCH + ch) = v;
             }
     }
-}
+    __syncthreads();
 
-// 3x3 / stride 2 max, NHWC store, planes for the first binarized conv: warp = pooled row of the tile, its 7 pooled
-// pixels unrolled (constant shared-memory offsets), lanes <-> channels
-__device__ __forceinline__ void pool_phase(const StemMmaArgs& a, const TilePos& p, const float* conv_s, int warp, int lane) {
-    const int ph = p.ph0 + warp;
-    if (ph >= a.Hp) return;
-    const bool has_nx = a.nx_scale != nullptr;
-    float nxs[2] = {1.0f, 1.0f}, nxh[2] = {0.0f, 0.0f};
-    if (has_nx) {
-        nxs[0] = __ldg(a.nx_scale + lane); nxs[1] = __ldg(a.nx_scale + 32 + lane);
-        nxh[0] = __ldg(a.nx_shift + lane); nxh[1] = __ldg(a.nx_shift + 32 + lane);
-    }
-    const size_t pix0 = ((size_t)p.n * a.Hp + ph) * a.Wp + p.pw0;
-    float* orow = a.out + pix0 * 64 + lane;
-    const float* cbase = conv_s + (2 * warp * SM_CC) * SM_CPITCH + lane;
+    // ---------------- 3x3 / stride 2 max, NHWC store, planes for the first binarized conv ----------------
+    // warp = pooled row of the tile, its 7 pooled pixels unrolled (constant shared-memory offsets), lanes <-> channels
+    const int ph = ph0 + warp;
+    if (ph < a.Hp) {
+        const bool has_nx = a.nx_scale != nullptr;
+        float nxs[2] = {1.0f, 1.0f}, nxh[2] = {0.0f, 0.0f};
+        if (has_nx) {
+            nxs[0] = __ldg(a.nx_scale + lane); nxs[1] = __ldg(a.nx_scale + 32 + lane);
+            nxh[0] = __ldg(a.nx_shift + lane); nxh[1] = __ldg(a.nx_shift + 32 + lane);
+        }
+        const size_t pix0 = ((size_t)n * a.Hp + ph) * a.Wp + pw0;
+        float* orow = a.out + pix0 * 64 + lane;
+        const float* cbase = conv_s + (2 * warp * SM_CC) * SM_CPITCH + lane;
 #pragma unroll
-    for (int pc = 0; pc < SM_PW; ++pc) {
-        if (p.pw0 + pc < a.Wp) {                               // warp-uniform
-            uint32_t sw[2], mw[2];
+        for (int pc = 0; pc < SM_PW; ++pc) {
+            if (pw0 + pc < a.Wp) {                             // warp-uniform
+                uint32_t sw[2], mw[2];
 #pragma unroll
-            for (int cb = 0; cb < 2; ++cb) {
-                float m = 0.0f;
+                for (int cb = 0; cb < 2; ++cb) {
+                    float m = 0.0f;
 #pragma unroll
-                for (int i = 0; i < 3; ++i)
+                    for (int i = 0; i < 3; ++i)
 #pragma unroll
-                    for (int j = 0; j < 3; ++j) m = fmaxf(m, cbase[(i * SM_CC + 2 * pc + j) * SM_CPITCH + cb * 32]);
-                orow[pc * 64 + cb * 32] = m;
-                const float b = has_nx ? __fmaf_rn(nxs[cb], m, nxh[cb]) : m;
-                sw[cb] = __ballot_sync(0xffffffffu, b > 0.0f);
-                mw[cb] = __ballot_sync(0xffffffffu, b > 0.0f || b < 0.0f);
+                        for (int j = 0; j < 3; ++j) m = fmaxf(m, cbase[(i * SM_CC + 2 * pc + j) * SM_CPITCH + cb * 32]);
+                    orow[pc * 64 + cb * 32] = m;
+                    const float b = has_nx ? __fmaf_rn(nxs[cb], m, nxh[cb]) : m;
+                    sw[cb] = __ballot_sync(0xffffffffu, b > 0.0f);
+                    mw[cb] = __ballot_sync(0xffffffffu, b > 0.0f || b < 0.0f);
+                }
+                if (lane == 0 && a.obits) a.obits[pix0 + pc] = make_uint4(sw[0], sw[1], mw[0], mw[1]);
             }
-            if (lane == 0 && a.obits) a.obits[pix0 + pc] = make_uint4(sw[0], sw[1], mw[0], mw[1]);
         }
-    }
-}
-
-// One tile per CTA, two CTAs per SM; the conv tile aliases the operand buffers.
-template <bool CHAIN>
-__global__ void __launch_bounds__(SM_WARPS * 32, 2)
-stem_mma_kernel(const __grid_constant__ StemMmaArgs a) {
-    extern __shared__ __align__(1024) unsigned char smem[];
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
-    const uint4* w_s = reinterpret_cast<const uint4*>(smem + 128);
-    uint2* in_hl = reinterpret_cast<uint2*>(smem + 128 + SM_W_BYTES);
-    float* conv_s = reinterpret_cast<float*>(smem + 128);        // aliases the operands after the MMA phase
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const TilePos p = tile_pos(a, blockIdx.x);
-
-    if (threadIdx.x == 0) {
-        mbar_init(bar, 1);
-        fence_mbar_init();
-        mbar_expect_tx(bar, (unsigned)SM_W_BYTES);
-        bulk_load_1d(const_cast<uint4*>(w_s), a.wfrag, (unsigned)SM_W_BYTES, bar);
-    }
-    {
-        float v0[SM_STAGE_ITERS], v1[SM_STAGE_ITERS];
-        stage_load(a, p, threadIdx.x, v0, v1);
-        stage_store(a, threadIdx.x, v0, v1, in_hl);
-    }
-    __syncthreads();
-    mbar_wait(bar, 0);
-    float acc[SM_MT][SM_NT][4];
-    mma_phase<CHAIN>(w_s, in_hl, warp, lane, acc);
-    __syncthreads();                                           // every warp is done with the operand buffers
-    bn_relu_phase(a, p, acc, conv_s, warp, lane);
-    __syncthreads();
-    pool_phase(a, p, conv_s, warp, lane);
-}
-
-// Persistent form: one CTA per SM, two independent teams of 8 warps on named barriers, one resident copy of the
-// weights.  Each team loops over tiles.  The NEXT tile's raw fp32 window is fetched by cp.async (LDGSTS: no registers
-// held, so nothing to spill) into the team's operand buffer as soon as the MMA phase has released it, lands behind
-// the BN/ReLU and pooling phases, and is converted to {hi, lo} fp16 words IN PLACE (the two floats of a pair and
-// their two packed words are the same 8 bytes, and every thread converts the pairs it fetched itself).  While one
-// team pools and converts, the other keeps the tensor pipe busy.
-constexpr int SP_TEAMS = 2;
-constexpr size_t SP_TEAM_BYTES = SM_IN_BYTES + SM_CONV_BYTES;                                // 16864 + 73728
-constexpr size_t SP_SMEM = 128 + SM_W_BYTES + SP_TEAMS * SP_TEAM_BYTES;                      // 226368
-static_assert(SP_SMEM <= 227 * 1024, "persistent stem kernel must fit one SM");
-
-__device__ __forceinline__ void team_sync(int team) {
-    asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(SM_WARPS * 32) : "memory");
-}
-// 4-byte cp.async with zero fill (src_bytes = 0 reads nothing and writes zeros)
-__device__ __forceinline__ void cp_async4(void* dst, const void* src, bool valid) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(valid ? 4 : 0) : "memory");
-}
-
-// raw fp32 window of one tile -> the operand buffer (pair i = floats 2i, 2i+1), same thread <-> pair mapping as stage_load
-__device__ __forceinline__ void stage_async(const StemMmaArgs& a, const TilePos& p, int tid, float* raw) {
-    const float* xn = a.x + (size_t)p.n * 3 * a.H * a.W;
-    int rf = tid / SM_IPW, pc = tid - rf * SM_IPW;
-#pragma unroll
-    for (int k = 0; k < SM_STAGE_ITERS; ++k) {
-        const int i = tid + k * SM_WARPS * 32;
-        const int ci = (rf >= SM_IR) + (rf >= 2 * SM_IR);
-        const int hi = p.hi0 + rf - ci * SM_IR, wi = p.wi0 + 2 * pc;
-        const bool inb = k + 1 < SM_STAGE_ITERS || i < SM_IN_WORDS;
-        const bool rowok = (unsigned)hi < (unsigned)a.H && inb;
-        const int off = (ci * a.H + hi) * a.W + wi;
-        const bool ok0 = rowok && (unsigned)wi < (unsigned)a.W;
-        const bool ok1 = rowok && pc < SM_IPW - 1 && (unsigned)(wi + 1) < (unsigned)a.W;
-        if (inb) {
-            cp_async4(raw + 2 * i, ok0 ? xn + off : a.x, ok0);
-            cp_async4(raw + 2 * i + 1, ok1 ? xn + off + 1 : a.x, ok1);
-        }
-        rf += (SM_WARPS * 32) / SM_IPW; pc += (SM_WARPS * 32) % SM_IPW;
-        if (pc >= SM_IPW) { pc -= SM_IPW; rf += 1; }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void convert_in_place(const StemMmaArgs& a, int tid, uint2* in_hl) {
-    asm volatile("cp.async.wait_group 0;" ::: "memory");       // this thread's own copies have landed
-#pragma unroll
-    for (int k = 0; k < SM_STAGE_ITERS; ++k) {
-        const int i = tid + k * SM_WARPS * 32;
-        if (k + 1 < SM_STAGE_ITERS || i < SM_IN_WORDS) {
-            const float2 v = *reinterpret_cast<const float2*>(in_hl + i);
-            uint32_t h, l;
-            split2(v.x * a.x_scale, v.y * a.x_scale, h, l);
-            in_hl[i] = make_uint2(h, l);
-        }
-    }
-}
-
-__global__ void __launch_bounds__(SP_TEAMS * SM_WARPS * 32, 1)
-stem_mma_persist_kernel(const __grid_constant__ StemMmaArgs a, int total_tiles) {
-    extern __shared__ __align__(1024) unsigned char smem[];
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
-    const uint4* w_s = reinterpret_cast<const uint4*>(smem + 128);
-    const int team = threadIdx.x / (SM_WARPS * 32), tid = threadIdx.x - team * (SM_WARPS * 32);
-    unsigned char* mine = smem + 128 + SM_W_BYTES + (size_t)team * SP_TEAM_BYTES;
-    uint2* in_hl = reinterpret_cast<uint2*>(mine);
-    float* conv_s = reinterpret_cast<float*>(mine + SM_IN_BYTES);
-    const int lane = tid & 31, warp = tid >> 5;
-
-    if (threadIdx.x == 0) {
-        mbar_init(bar, 1);
-        fence_mbar_init();
-        mbar_expect_tx(bar, (unsigned)SM_W_BYTES);
-        bulk_load_1d(const_cast<uint4*>(w_s), a.wfrag, (unsigned)SM_W_BYTES, bar);
-    }
-    const int stride = gridDim.x * SP_TEAMS;
-    int tile = blockIdx.x * SP_TEAMS + team;
-    if (tile < total_tiles) {
-        stage_async(a, tile_pos(a, tile), tid, reinterpret_cast<float*>(in_hl));
-        convert_in_place(a, tid, in_hl);
-    }
-    __syncthreads();                                           // mbarrier initialised; first windows staged
-    mbar_wait(bar, 0);
-    for (; tile < total_tiles; tile += stride) {
-        const TilePos p = tile_pos(a, tile);
-        const int next = tile + stride;
-        float acc[SM_MT][SM_NT][4];
-        mma_phase<false>(w_s, in_hl, warp, lane, acc);
-        team_sync(team);                                       // the operand buffer is free: fetch the next window into it
-        if (next < total_tiles) stage_async(a, tile_pos(a, next), tid, reinterpret_cast<float*>(in_hl));
-        bn_relu_phase(a, p, acc, conv_s, warp, lane);
-        team_sync(team);                                       // conv tile complete
-        pool_phase(a, p, conv_s, warp, lane);
-        if (next < total_tiles) convert_in_place(a, tid, in_hl);
-        team_sync(team);                                       // next window converted, conv tile free again
     }
 }
 
@@ -446,25 +320,13 @@ extern "C" int bnn_stem_mma_fwd(const float* x, int32_t n, int32_t h, int32_t w,
     a.Hp = (a.Hc + 2 - 3) / 2 + 1; a.Wp = (a.Wc + 2 - 3) / 2 + 1;
     a.tiles_h = (a.Hp + SM_PH - 1) / SM_PH; a.tiles_w = (a.Wp + SM_PW - 1) / SM_PW;
     const bool chain = (flags & BNN_F_STEM_MMA_CHAIN) != 0;
+    const void* fn = chain ? (const void*)stem_mma_kernel<true> : (const void*)stem_mma_kernel<false>;
+    cudaError_t ce = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_SMEM);
+    if (ce != cudaSuccess) return (int)ce;
     const long long ctas = (long long)n * a.tiles_h * a.tiles_w;
     if (ctas > 0x7fffffffLL) return BNN_E_UNSUPPORTED;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    // persistent two-team form when there is enough work to keep every team busy for several tiles
-    const bool persist = !chain && !(flags & BNN_F_STEM_NO_PERSIST) && ctas >= 4LL * SP_TEAMS * sms;
-    cudaError_t ce;
-    if (persist) {
-        ce = cudaFuncSetAttribute((const void*)stem_mma_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_SMEM);
-        if (ce != cudaSuccess) return (int)ce;
-        stem_mma_persist_kernel<<<(unsigned)sms, SP_TEAMS * SM_WARPS * 32, SP_SMEM, (cudaStream_t)stream_>>>(a, (int)ctas);
-    } else {
-        const void* fn = chain ? (const void*)stem_mma_kernel<true> : (const void*)stem_mma_kernel<false>;
-        ce = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM_SMEM);
-        if (ce != cudaSuccess) return (int)ce;
-        if (chain) stem_mma_kernel<true><<<(unsigned)ctas, SM_WARPS * 32, SM_SMEM, (cudaStream_t)stream_>>>(a);
-        else stem_mma_kernel<false><<<(unsigned)ctas, SM_WARPS * 32, SM_SMEM, (cudaStream_t)stream_>>>(a);
-    }
+    if (chain) stem_mma_kernel<true><<<(unsigned)ctas, SM_WARPS * 32, SM_SMEM, (cudaStream_t)stream_>>>(a);
+    else stem_mma_kernel<false><<<(unsigned)ctas, SM_WARPS * 32, SM_SMEM, (cudaStream_t)stream_>>>(a);
     count_launch(1);
     return (int)cudaGetLastError();
 }

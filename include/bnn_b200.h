@@ -68,7 +68,6 @@ typedef struct bnn_conv_geom {
 #define BNN_F_NO_CSA      2u    /* force the one-POPC-per-word inner loop                     */
 #define BNN_F_STEM_TMA_IN 4u    /* bnn_stem_fwd: stage the input window with a 4-D TMA tensor load (experimental) */
 #define BNN_F_STEM_NO_BULK 8u   /* bnn_stem_fwd: stage the weights with plain loads instead of a TMA bulk copy   */
-#define BNN_F_STEM_NO_PERSIST 32u /* bnn_stem_mma_fwd: one tile per CTA instead of the persistent two-team kernel (A-B) */
 #define BNN_F_STEM_MMA_CHAIN 16u /* bnn_stem_mma_fwd: accumulate every product inside the tensor core (A-B experiment) */
 
 int         bnn_query(int what, int64_t *value);

@@ -32,8 +32,7 @@ def timed(fn, reps=20):
 
 
 res = {"bs": bs, "fma_ms": timed(lambda: BF.stem(x, w_t, (g, h))), "mma_ms": timed(lambda: BF.stem_mma(x, wfrag, (g, h))),
-       "mma_chain_ms": timed(lambda: BF.stem_mma(x, wfrag, (g, h), flags=16)),
-       "mma_one_tile_per_cta_ms": timed(lambda: BF.stem_mma(x, wfrag, (g, h), flags=32))}
+       "mma_chain_ms": timed(lambda: BF.stem_mma(x, wfrag, (g, h), flags=16))}
 xs = x[:4]
 y64 = torch.nn.functional.conv2d(xs.double(), w.double(), stride=2, padding=3)
 y64 = torch.nn.functional.max_pool2d(torch.relu(y64 * g.double().view(1, -1, 1, 1) + h.double().view(1, -1, 1, 1)), 3, 2, 1)
@@ -43,9 +42,6 @@ sc = float(y64.abs().max())
 c, _ = BF.stem_mma(xs, wfrag, (g, h), flags=16)
 res["mma_chain_err"] = float((c.double() - y64).abs().max()) / sc
 res["mma_chain_rms"] = float((c.double() - y64).pow(2).mean().sqrt()) / sc
-b1, b1bits = BF.stem_mma(x, wfrag, (g, h))
-b2, b2bits = BF.stem_mma(x, wfrag, (g, h), flags=32)
-res["persistent_equals_one_tile_per_cta"] = bool(torch.equal(b1, b2) and torch.equal(b1bits.bits, b2bits.bits))
 res["fma_err"] = float((a.double() - y64).abs().max()) / sc
 res["mma_err"] = float((b.double() - y64).abs().max()) / sc
 res["fma_rms"] = float((a.double() - y64).pow(2).mean().sqrt()) / sc
