@@ -72,9 +72,10 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
     extern __shared__ __align__(1024) unsigned char smem[];
     // EPI 0: reference epilogue.  EPI 1: fused epilogue, any strides.  EPI 2: fused epilogue with channel-contiguous
     // (NHWC) residual and output -- what the fused engine always uses: the pixel-contiguous transposes are compiled out
-    // EPI 3: the lean NHWC epilogue of post-activation ReLU blocks (BatchNorm, optional shortcut add BEFORE the ReLU,
-    // optional fp32 store, optional planes where "non-zero" == "positive"), launched only when every pixel group and
-    // every channel block is complete -- no bounds predicates, no stride arithmetic beyond one multiply per access.
+    // EPI 3: the lean NHWC epilogue of residual blocks, launched only when every pixel group and every channel block is
+    // complete -- no bounds predicates, no stride arithmetic beyond one multiply per access, planes through the warp's
+    // staging area.  Fast form: BatchNorm, optional shortcut add BEFORE a ReLU, planes where "non-zero" == "positive";
+    // general form: any activation, shortcut before or after it, optional affine in front of the next sign().
     constexpr bool FUSED = EPI >= 1, CL = EPI >= 2, LEAN = EPI == 3;
     constexpr int PITCH = P | 1;      // odd pitch: conflict-free transposes
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
@@ -308,7 +309,6 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
             const int cch = blk0 * 32 + lane;
             const float* rp = res_n + (ho * e_rh + wo_first * e_rw + cch);      // dereferenced only if has_res
             float* op = out_n + (ho * e_oh + wo_first * e_ow + cch);            // dereferenced only if has_out
-            uint32_t sw[P][C];                   // ballots are warp-uniform: every lane holds every word
             float res[C][P];
             if (has_res) {                       // every shortcut line of the group in flight before the first use
 #pragma unroll
@@ -316,6 +316,53 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
 #pragma unroll
                     for (int p = 0; p < P; ++p) res[j][p] = __ldg(rp + p * e_rw + j * 32);
             }
+            const bool res_after = a.e.res_after_act != 0, nx = a.e.nx_scale != nullptr;
+            if (a.e.act != BNN_ACT_RELU || nx || (has_res && res_after)) {
+                // general form (pre-activation blocks: PReLU, shortcut after the activation, the next layer's
+                // BatchNorm in front of its sign): same operations in the same order as the EPI 1 / 2 epilogue
+                const int act = a.e.act;
+                const bool want_bits = a.e.obits != nullptr;
+                uint4* sb = reinterpret_cast<uint4*>(stg);
+                if (want_bits) __syncwarp();
+#pragma unroll
+                for (int j = 0; j < C; j += 2) {
+                    uint32_t sw[2][P], mw[2][P];
+#pragma unroll
+                    for (int jj = 0; jj < 2; ++jj) {
+                        const int cl = (j + jj) * 32 + lane;
+                        const float k0 = epc[cl], k1 = epc[32 * C + cl], k2 = epc[2 * 32 * C + cl];
+                        const float k3 = epc[3 * 32 * C + cl], k4 = epc[4 * 32 * C + cl];
+#pragma unroll
+                        for (int p = 0; p < P; ++p) {
+                            float v = __fmaf_rn(k0, (float)(ms[p] - 2 * acc[p][j + jj]), k1);
+                            if (has_res && !res_after) v = __fadd_rn(v, res[j + jj][p]);
+                            if (act == BNN_ACT_RELU) v = fmaxf(v, 0.0f);
+                            else if (act == BNN_ACT_PRELU) v = (v > 0.0f) ? v : __fmul_rn(k2, v);
+                            if (has_res && res_after) v = __fadd_rn(v, res[j + jj][p]);
+                            if (has_out) op[p * e_ow + (j + jj) * 32] = v;
+                            const float b = nx ? __fmaf_rn(k3, v, k4) : v;
+                            sw[jj][p] = __ballot_sync(0xffffffffu, b > 0.0f);
+                            mw[jj][p] = __ballot_sync(0xffffffffu, b > 0.0f || b < 0.0f);
+                        }
+                    }
+                    if (want_bits && lane == 0) {
+#pragma unroll
+                        for (int p = 0; p < P; ++p) sb[p * (C / 2) + j / 2] = make_uint4(sw[0][p], sw[1][p], mw[0][p], mw[1][p]);
+                    }
+                }
+                if (want_bits) {
+                    __syncwarp();
+                    if (lane < P) {
+                        const size_t unit0 = (((size_t)n * a.e.ochunks + (blk0 >> 1)) * a.Ho + ho) * a.Wo + wo_first + lane;
+                        const size_t ustep = (size_t)a.Ho * a.Wo;
+#pragma unroll
+                        for (int j = 0; j < C; j += 2) a.e.obits[unit0 + (j / 2) * ustep] = sb[lane * (C / 2) + j / 2];
+                    }
+                    __syncwarp();
+                }
+                continue;
+            }
+            uint32_t sw[P][C];                   // ballots are warp-uniform: every lane holds every word
 #pragma unroll
             for (int j = 0; j < C; ++j) {
                 const float k0 = epc[j * 32 + lane], k1 = epc[32 * C + j * 32 + lane];
@@ -583,10 +630,10 @@ static int epilogue_kind(const bnn_epilogue& ep) {
     if (!fused) return 0;
     const bool cl = (!ep.out || ep.ostride_c == 1) && (!ep.residual || ep.rstride_c == 1);
     if (!cl) return 1;
-    // 3: post-activation ReLU block (BatchNorm folded, shortcut added before the ReLU, planes of the ReLU output);
+    // 3: residual blocks of either flavour (post-activation: BatchNorm folded, shortcut before the ReLU; pre-activation:
+    // PReLU, shortcut after it, the next BatchNorm in front of the sign) -- everything but the Hierarchical-Block forms;
     // whether the lean instance can actually run also depends on the tile plan, see lean_plan_ok()
-    const bool lean = ep.act == BNN_ACT_RELU && !ep.nx_scale && !ep.nx_relu && !ep.residual_after_act &&
-                      !ep.bits_before_residual;
+    const bool lean = !ep.nx_relu && !ep.bits_before_residual;
     return lean ? 3 : 2;
 }
 

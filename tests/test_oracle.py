@@ -190,6 +190,10 @@ FUSED_CASES = [
     dict(name="lean_out", cin=64, cout=128, hw=(3, 56), bn=True, act=1, res="pre", bits=True, out=True),
     dict(name="lean_s2", cin=128, cout=128, hw=(6, 112), stride=2, bn=True, act=1, bits=True, out=True),
     dict(name="lean_out_only", cin=64, cout=256, hw=(2, 56), bn=True, act=1, res="pre", bits=False, out=True, bias=True, post=True),
+    # ... and its general form: pre-activation blocks (PReLU, shortcut after the activation, next BatchNorm before the sign)
+    dict(name="lean_pre_mid", cin=64, cout=128, hw=(3, 56), act=2, bits=True, out=False, nx=True),
+    dict(name="lean_pre_out", cin=128, cout=128, hw=(3, 56), act=2, res="post", bits=True, out=True, nx=True),
+    dict(name="lean_res_after_noact", cin=64, cout=256, hw=(2, 56), bn=True, res="post", bits=True, out=True, nx=True, post=True),
 ]
 
 
