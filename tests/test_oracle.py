@@ -194,6 +194,10 @@ FUSED_CASES = [
     dict(name="lean_pre_mid", cin=64, cout=128, hw=(3, 56), act=2, bits=True, out=False, nx=True),
     dict(name="lean_pre_out", cin=128, cout=128, hw=(3, 56), act=2, res="post", bits=True, out=True, nx=True),
     dict(name="lean_res_after_noact", cin=64, cout=256, hw=(2, 56), bn=True, res="post", bits=True, out=True, nx=True, post=True),
+    # 1x1 kernels over several 64-channel chunks: the chunk-triple carry-save path (5 chunks = one triple + two singles)
+    dict(name="k1_c320", cin=320, cout=96, hw=(6, 10), k=1, pad=0, bn=True, act=1, bits=True, out=True),
+    dict(name="k1_c192_lean", cin=192, cout=128, hw=(2, 56), k=1, pad=0, bn=True, act=1, res="pre", bits=True, out=True),
+    dict(name="k1_c512_s2", cin=512, cout=64, hw=(8, 8), k=1, pad=0, stride=2, bn=True, act=2, bits=True, out=True, nx=True),
 ]
 
 
