@@ -48,6 +48,18 @@ def test_size_helpers_and_errors_without_gpu():
     assert lib.bnn_bconv2d_fwd(one, one, None, None, None, one, 0, 0, 0, 0, ctypes.byref(g), 0, None) == -2
     with pytest.raises(native.NativeError):
         native.check(-3, "x")
+    # the entry points added in ABI v3 validate the same way
+    assert lib.bnn_shortcut_fwd(None, 0, 0, 0, 1, 64, 8, 8, 2, 1, None, 64, None, None, None, None, None, None, 0, None) == -1
+    assert lib.bnn_shortcut_fwd(one, 0, 0, 0, 1, 64, 8, 8, 0, 1, one, 64, None, None, None, None, None, one, 0, None) == -2   # pool 0
+    assert lib.bnn_shortcut_fwd(one, 0, 0, 0, 1, 64, 8, 8, 2, 1, one, 64, None, None, None, one, None, one, 0, None) == -1   # bn_scale without bn_shift
+    assert lib.bnn_stem_mma_weight_bytes() == 11 * 8 * 32 * 16
+    assert lib.bnn_stem_mma_pack_weight(None, 0, None, None) == -1
+    assert lib.bnn_stem_mma_pack_weight(one, 99, one, None) == -2
+    assert lib.bnn_stem_mma_fwd(None, 1, 8, 8, None, 7, 0, None, None, None, None, None, None, 0, None) == -1
+    assert lib.bnn_stem_mma_fwd(one, 1, 5, 5, one, 7, 0, one, one, None, None, one, None, 0, None) == -2                    # smaller than the kernel
+    assert lib.bnn_stem_fwd(None, 1, 8, 8, None, None, None, None, None, None, None, 0, None) == -1
+    hp, wp = ctypes.c_int32(0), ctypes.c_int32(0)
+    assert lib.bnn_stem_out_hw(224, 224, ctypes.byref(hp), ctypes.byref(wp)) == 0 and (hp.value, wp.value) == (56, 56)
 
 
 def test_sass_contains_tma_and_popc():
@@ -60,5 +72,5 @@ def test_sass_contains_tma_and_popc():
         pytest.skip("no cuobjdump")
     sass = subprocess.run([cuobjdump, "-sass", native.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in sass
-    for mnemonic in ("UTMALDG", "UBLKCP", "POPC", "LOP3"):
+    for mnemonic in ("UTMALDG", "UBLKCP", "POPC", "LOP3", "HMMA.16816.F32", "FFMA2"):     # + the two stem kernels
         assert mnemonic in sass, mnemonic
