@@ -75,3 +75,65 @@ def test_pack_act_bits_are_the_sign_and_nonzero_planes(n, c, h, w, seed):
                 assert not np.any(last[..., 0] >> np.uint32(r)) and not np.any(last[..., 2] >> np.uint32(r))
         else:
             assert not np.any(last[..., 1] >> np.uint32(r - 32)) and not np.any(last[..., 3] >> np.uint32(r - 32))
+
+
+@st.composite
+def fused_configs(draw):
+    res = draw(st.sampled_from([None, "pre", "post"]))
+    nx = draw(st.booleans())
+    act = draw(st.sampled_from([0, 1, 2]))
+    # the Hierarchical-Block form: planes of relu(nx(.)) taken before a post-activation shortcut add
+    hblock = res == "post" and nx and act == 0 and draw(st.booleans())
+    return dict(cin=draw(st.sampled_from([3, 64, 70, 128])), cout=draw(st.sampled_from([8, 32, 64, 96])),
+                h=draw(st.integers(3, 7)), w=draw(st.integers(3, 9)), k=draw(st.sampled_from([1, 3])),
+                stride=draw(st.integers(1, 2)), bn=draw(st.booleans()), bias=draw(st.booleans()), post=draw(st.booleans()),
+                res=res, act=act, nx=nx, hblock=hblock, seed=draw(st.integers(0, 2 ** 20)))
+
+
+@settings(max_examples=60, deadline=None)
+@given(fused_configs())
+def test_fused_epilogue_oracle_equals_the_module_sequence(fc):
+    """The oracle's fused epilogue (struct bnn_epilogue) against the torch module sequence of the reference's blocks --
+    conv (float simulation) -> BatchNorm(eval, folded) -> (+shortcut) -> ReLU / PReLU -> (+shortcut) -- on random
+    configurations; the emitted planes are the bit-pack of the oracle's own fp32 result (knife-edge ulps aside)."""
+    rng = np.random.default_rng(fc["seed"])
+    k, pad = fc["k"], fc["k"] // 2
+    x = np.maximum(rng.standard_normal((2, fc["cin"], fc["h"], fc["w"])), 0).astype(np.float32)
+    w = (rng.standard_normal((fc["cout"], fc["cin"], k, k)) * 0.05).astype(np.float32)
+    g = co.geom(2, fc["cin"], fc["h"], fc["w"], fc["cout"], k, k, (fc["stride"],) * 2, (pad, pad), (1, 1))
+    ho, wo = co.out_hw(g)
+    c = fc["cout"]
+    bias = (rng.standard_normal(c) * 0.3).astype(np.float32) if fc["bias"] else None
+    post = (0.5 + rng.random(c)).astype(np.float32) if fc["post"] else None
+    bn = ((0.5 + rng.random(c)).astype(np.float32) * 3, (rng.standard_normal(c) * 0.3).astype(np.float32)) if fc["bn"] else None
+    residual = rng.standard_normal((2, c, ho, wo)).astype(np.float32) if fc["res"] else None
+    slope = (rng.random(c) * 0.5).astype(np.float32) if fc["act"] == 2 else None
+    nx = ((0.5 + rng.random(c)).astype(np.float32), (rng.standard_normal(c) * 0.2).astype(np.float32)) if fc["nx"] else None
+    wb, alpha, nz = co.pack_weight(w, True, True)
+    if nz:
+        return
+    out, bits = co.bconv2d_fused(co.pack_act(x), wb, g, scale=alpha, bias=bias, post=post, bn=bn, residual=residual,
+                                 residual_after_act=fc["res"] == "post", act=fc["act"], act_slope=slope, want_out=True,
+                                 want_bits=True, nx=nx, nx_relu=fc["hblock"], bits_before_residual=fc["hblock"])
+    t = lambda a: None if a is None else torch.from_numpy(a)
+    v = lambda a: t(a).view(1, -1, 1, 1)
+    y = fs.conv2d(t(x), t(w), t(bias), t(post), (fc["stride"],) * 2, (pad, pad), (1, 1), True, True)
+    if bn is not None:
+        y = y * v(bn[0]) + v(bn[1])
+    if fc["res"] == "pre":
+        y = y + t(residual)
+    if fc["act"] == 1:
+        y = torch.relu(y)
+    elif fc["act"] == 2:
+        y = torch.nn.functional.prelu(y, t(slope))
+    y_before = y
+    if fc["res"] == "post":
+        y = y + t(residual)
+    scale = max(1e-6, float(y.abs().max()))
+    assert np.abs(out - y.numpy()).max() <= 1e-5 * scale
+    if fc["hblock"]:
+        nb = torch.relu(y_before * v(nx[0]) + v(nx[1])).numpy()
+        assert (bits != co.pack_act(nb)).sum() <= 2
+        return
+    want_bits = co.pack_act(out, pre_scale=None if nx is None else nx[0], pre_shift=None if nx is None else nx[1])
+    assert (bits != want_bits).sum() <= (1 if nx is not None else 0)
