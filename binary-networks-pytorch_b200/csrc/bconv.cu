@@ -113,6 +113,10 @@ static int enumerate_plans(const bnn_conv_geom& g, int Ho, int Wo, uint32_t flag
     const int nblk32 = ceil_div(g.c_out, 32);
     const size_t smem_cap = 220 * 1024;
     const int candP[3] = {8, 7, 4}, candC[3] = {4, 2, 1};
+    // Tiles span the whole output row whenever that fits (shrink == 0).  Only if NO shape fits shared memory that way
+    // (many input chunks x a large kernel x a wide image) are narrower tiles tried: the row is cut into 2, 4, 8, ...
+    // pieces until something fits, so the plans of every geometry that already had one are unchanged.
+    for (int shrink = 0; shrink < 8 && out.empty(); ++shrink)
     for (int ci = 0; ci < 3; ++ci) {
         const int C = candC[ci];
         if (C > 1 && C / 2 >= nblk32) continue;                  // would only add idle channel blocks
@@ -123,7 +127,7 @@ static int enumerate_plans(const bnn_conv_geom& g, int Ho, int Wo, uint32_t flag
             const int P = candP[pi];
             const int usw = kwt ? swt : 1, ukw = kwt ? kwt : 1;
             const bool window = ((P - 1) * usw + ukw) <= 12;
-            int TW = ceil_div(Wo, P) * P;
+            int TW = ceil_div(ceil_div(Wo, 1 << shrink), P) * P;
             while ((TW - 1) * g.stride_w + (g.kw - 1) * g.dil_w + 1 > 256 && TW > P) TW -= P;
             const int BW = (TW - 1) * g.stride_w + (g.kw - 1) * g.dil_w + 1;
             if (BW > 256) continue;

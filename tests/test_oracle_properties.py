@@ -137,3 +137,43 @@ def test_fused_epilogue_oracle_equals_the_module_sequence(fc):
         return
     want_bits = co.pack_act(out, pre_scale=None if nx is None else nx[0], pre_shift=None if nx is None else nx[1])
     assert (bits != want_bits).sum() <= (1 if nx is not None else 0)
+
+
+@st.composite
+def conv_geoms(draw):
+    k = draw(st.sampled_from([1, 3, 5, 7]))
+    return dict(n=draw(st.integers(1, 300)), c_in=draw(st.integers(1, 2048)), c_out=draw(st.integers(1, 2048)),
+                h=draw(st.integers(k, 120)), w=draw(st.integers(k, 300)), k=k, stride=draw(st.integers(1, 2)),
+                pad=draw(st.integers(0, k // 2)), flags=draw(st.sampled_from([0, 2])))
+
+
+@settings(max_examples=150, deadline=None, derandomize=True)
+@given(conv_geoms())
+def test_tile_planner_invariants(gm):
+    """bnn_conv_plan (host only): whatever geometry comes in, the chosen plan covers every output pixel and channel,
+    fits shared memory, keeps whole pixel groups per tile row and uses an instance that exists."""
+    from bnn_b200 import native
+    g = native.ConvGeom(gm["n"], gm["c_in"], gm["h"], gm["w"], gm["c_out"], gm["k"], gm["k"], gm["stride"], gm["stride"],
+                        gm["pad"], gm["pad"], 1, 1)
+    ho = (gm["h"] + 2 * gm["pad"] - gm["k"]) // gm["stride"] + 1
+    wo = (gm["w"] + 2 * gm["pad"] - gm["k"]) // gm["stride"] + 1
+    try:
+        pl = native.conv_plan(g, gm["flags"], 148)
+    except native.NativeError:
+        # refusal is legitimate only if even the smallest tile (4 pixels x 32 channels, one row) exceeds shared memory:
+        # plan_smem() of bconv.cu for P = 4, C = 1, TH = 1, TW = 4, 7 warps
+        nch, k = (gm["c_in"] + 63) // 64, gm["k"]
+        act = nch * k * ((4 - 1) * gm["stride"] + k) * 16
+        smallest = 128 + ((act + 127) & ~127) + nch * k * k * 256 + 7 * 32 * 5 * 4 + 5 * 32 * 4 + 4 * 4
+        assert smallest > 220 * 1024 or nch * k * k * 256 + 16 * 1024 > 220 * 1024
+        return
+    assert pl["P"] in (8, 7, 4) and pl["C"] in (4, 2, 1) and pl["warps"] in (7, 8)
+    assert pl["TW"] % pl["P"] == 0 and pl["groups"] == pl["TH"] * (pl["TW"] // pl["P"])
+    assert pl["smem"] <= 220 * 1024
+    assert pl["kw_inst"] == (gm["k"] if gm["k"] in (1, 3) and not (gm["k"] == 1 and gm["stride"] == 2) else 0)
+    assert pl["csa"] == int(gm["flags"] == 0 and pl["kw_inst"] in (1, 3))
+    tiles_per_image = pl["units"] // gm["n"]
+    assert pl["units"] == tiles_per_image * gm["n"]
+    assert tiles_per_image * pl["TH"] * pl["TW"] >= ho * wo                       # every output pixel is in some tile
+    assert pl["channel_tiles"] * 32 * pl["C"] >= gm["c_out"]                        # every output channel in some block
+    assert (pl["channel_tiles"] - 1) * 32 * pl["C"] < gm["c_out"]                   # ... and no empty channel tile
