@@ -197,3 +197,22 @@ def test_exact_zero_weights_are_refused_not_approximated():
     m.weight.data[3, 7] = 0.0
     with torch.no_grad(), pytest.raises(native.NativeError, match="exactly zero"):
         m(torch.randn(1, 64, 4, 4, device=DEV))
+
+
+@pytest.mark.parametrize("cin,cout,k,s,pad,h,w", [(1153, 32, 5, 2, 2, 5, 57), (1153, 70, 5, 1, 2, 6, 300)])
+def test_narrow_tile_fallback_geometries(cin, cout, k, s, pad, h, w):
+    """19 input chunks x a 5x5 kernel: a tile spanning the whole output row does not fit shared memory, so the planner
+    cuts the row into pieces.  Integer dots bit-exact against the oracle."""
+    rng = np.random.default_rng(3)
+    x = np.maximum(rng.standard_normal((1, cin, h, w)), 0).astype(np.float32)
+    wt = (rng.standard_normal((cout, cin, k, k)) * 0.05).astype(np.float32)
+    g = co.geom(1, cin, h, w, cout, k, k, (s, s), (pad, pad), (1, 1))
+    wb, _, nz = co.pack_weight(wt, True, True)
+    assert nz == 0
+    want = co.bconv2d(co.pack_act(x), wb, None, None, None, g)
+    plan = native.conv_plan(native.ConvGeom(1, cin, h, w, cout, k, k, s, s, pad, pad, 1, 1), 0, 148)
+    assert plan["TW"] < want.shape[3]                       # the row really is cut
+    act = BF.pack_activations(torch.from_numpy(x).to(DEV))
+    wts = BF.pack_weights(torch.from_numpy(wt).to(DEV), True, True)
+    got = BF.bconv2d(act, wts, None, None, (s, s), (pad, pad), (1, 1), use_alpha=False).cpu().numpy()
+    assert np.array_equal(got, want)
