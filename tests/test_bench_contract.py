@@ -43,3 +43,26 @@ def test_b200_arm_refuses_to_run_without_cuda():
     r = _run("--steps", "1", "--warmup", "1", timeout=300)
     assert r.returncode != 0
     assert "no CUDA device" in (r.stderr + r.stdout) and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_product_package_never_touches_the_oracle():
+    """oracle/ is the checker: only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import it."""
+    import re
+    pkg = os.path.join(ROOT, "binary-networks-pytorch_b200")
+    offenders = []
+    for dirpath, _, files in os.walk(pkg):
+        for name in files:
+            if name.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, name), errors="replace").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b|oracle/|liboracle", text, flags=re.M):
+                    offenders.append(os.path.relpath(os.path.join(dirpath, name), ROOT))
+    assert offenders == []
+    shim = open(os.path.join(ROOT, "bnn_b200.py")).read()
+    assert "oracle" not in shim
+    # bench.py reaches the oracle only inside its CPU-baseline / reference-arm functions
+    bench = open(os.path.join(ROOT, "bench.py")).read()
+    uses = [m.start() for m in re.finditer(r"from oracle import", bench)]
+    assert uses, "bench.py's CPU legs are expected to use oracle.floatsim"
+    for pos in uses:
+        func = re.findall(r"^def (\w+)\(", bench[:pos], flags=re.M)[-1]
+        assert func in ("cpu_floatsim_rate", "run_reference"), func
