@@ -368,6 +368,67 @@ extern "C" int bnn_bconv2d_fused_fwd(const void* abits, const void* wbits, const
     return launch_bconv(abits, wbits, *geom, *epilogue, flags, (cudaStream_t)stream);
 }
 
+// the candidate of enumerate_plans() whose (P, C, TH, warps) match; TH <= 0 / warps <= 0 match the best-ranked one
+static int find_plan(const bnn_conv_geom& g, uint32_t flags, int P, int C, int TH, int warps, Plan* out) {
+    const int Ho = out_dim(g.h, g.kh, g.stride_h, g.pad_h, g.dil_h);
+    const int Wo = out_dim(g.w, g.kw, g.stride_w, g.pad_w, g.dil_w);
+    if (Ho <= 0 || Wo <= 0) return BNN_E_SHAPE;
+    std::vector<Cand> cands;
+    int rc = enumerate_plans(g, Ho, Wo, flags, 148, cands);
+    if (rc) return rc;
+    for (const Cand& c : cands)
+        if (c.pl.P == P && c.pl.C == C && (TH <= 0 || c.pl.TH == TH) && (warps <= 0 || c.pl.NW == warps)) {
+            *out = c.pl;
+            return 0;
+        }
+    return BNN_E_UNSUPPORTED;
+}
+
+extern "C" int bnn_bconv2d_fused_fwd_plan(const void* abits, const void* wbits, const bnn_conv_geom* geom,
+                                          const bnn_epilogue* epilogue, uint32_t flags, int32_t P, int32_t C,
+                                          int32_t TH, int32_t warps, void* stream) {
+    if (!geom || !epilogue) return BNN_E_NULL;
+    if (epilogue_kind(*epilogue)) flags &= ~BNN_F_NO_CSA;
+    Plan pl;
+    int rc = find_plan(*geom, flags, P, C, TH, warps, &pl);
+    if (rc) return rc;
+    return launch_bconv(abits, wbits, *geom, *epilogue, flags, (cudaStream_t)stream, &pl);
+}
+
+extern "C" int bnn_conv_plan_list(const bnn_conv_geom* g, uint32_t flags, int32_t* plans, int32_t cap, int32_t* count) {
+    if (!g || !count || (cap > 0 && !plans)) return BNN_E_NULL;
+    const int Ho = out_dim(g->h, g->kh, g->stride_h, g->pad_h, g->dil_h);
+    const int Wo = out_dim(g->w, g->kw, g->stride_w, g->pad_w, g->dil_w);
+    if (Ho <= 0 || Wo <= 0) return BNN_E_SHAPE;
+    std::vector<Cand> cands;
+    int rc = enumerate_plans(*g, Ho, Wo, flags, 148, cands);
+    if (rc) return rc;
+    *count = (int32_t)cands.size();
+    for (int i = 0; i < (int)cands.size() && i < cap; ++i) {
+        const Plan& pl = cands[i].pl;
+        const int v[12] = {pl.P, pl.C, pl.kwt, pl.swt, pl.mode, pl.TH, pl.TW, pl.NW, pl.tiles_h * pl.tiles_w * g->n,
+                           ceil_div(ceil_div(g->c_out, 32), pl.C), (int)pl.smem, pl.G};
+        for (int k = 0; k < 12; ++k) plans[i * 12 + k] = v[k];
+    }
+    return 0;
+}
+
+extern "C" int bnn_conv_instance(const bnn_conv_geom* g, const bnn_epilogue* ep, uint32_t flags, int32_t P, int32_t C,
+                                 int32_t TH, int32_t warps, int32_t* inst) {
+    if (!g || !ep || !inst) return BNN_E_NULL;
+    int epi = epilogue_kind(*ep);
+    if (epi) flags &= ~BNN_F_NO_CSA;
+    Plan pl;
+    int rc = find_plan(*g, flags, P, C, TH, warps, &pl);
+    if (rc) return rc;
+    const int Wo = out_dim(g->w, g->kw, g->stride_w, g->pad_w, g->dil_w);
+    if (epi >= 3 && !lean_plan_ok(pl, *g, Wo)) epi = 2;
+    if (!pick_kernel(pl, epi)) return BNN_E_UNSUPPORTED;
+    const int v[6] = {pl.P, pl.C, pl.kwt, pl.swt, pl.mode, epi};
+    for (int k = 0; k < 6; ++k) inst[k] = v[k];
+    return 0;
+}
+
 extern "C" int bnn_bconv2d_fwd(const void* abits, const void* wbits, const float* scale, const float* bias,
                                const float* post, float* out, int64_t on, int64_t oc, int64_t oh, int64_t ow,
                                const bnn_conv_geom* geom, uint32_t flags, void* stream) {

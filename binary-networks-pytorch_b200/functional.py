@@ -166,12 +166,15 @@ def bconv2d_fused(act: PackedActivations, wts: PackedWeights, *, bias=None, post
                   residual_after_act: bool = False, activation: int = native.ACT_NONE, act_slope=None,
                   want_out: bool = True, want_bits: bool = False, nx=None, stride=(1, 1), padding=(0, 0),
                   dilation=(1, 1), use_alpha: bool = True, flags: int = 0, channels_last: bool = False,
-                  out: Optional[torch.Tensor] = None, nx_relu: bool = False, bits_before_residual: bool = False):
+                  out: Optional[torch.Tensor] = None, nx_relu: bool = False, bits_before_residual: bool = False,
+                  plan: Optional[Tuple[int, int, int, int]] = None):
     """Binary convolution with the cross-module epilogue of ``struct bnn_epilogue``:
     ``y=(alpha*dot+bias)*post; z=y*bn[0]+bn[1]; (+residual); act; (+residual)`` -> fp32 ``out`` and/or the
     packed planes of ``sign(v*nx[0]+nx[1])`` for the next binarized layer.  Returns (out, PackedActivations).
     ``channels_last`` allocates ``out`` in torch's NHWC memory format: with lanes <-> channels in the kernel a
-    warp then stores (and reads the residual) as whole 128-byte lines, no transposition needed."""
+    warp then stores (and reads the residual) as whole 128-byte lines, no transposition needed.
+    ``plan=(P, C, TH, warps)`` forces the tile plan (``bnn_bconv2d_fused_fwd_plan``; TH / warps 0 = best of that
+    family) instead of the tuned / modelled one -- the parity suite sweeps every kernel instance with it."""
     if act.c != wts.c_in:
         raise native.NativeError(f"channel mismatch: activations {act.c}, weights {wts.c_in}")
     geom = ConvGeom(act.n, act.c, act.h, act.w, wts.c_out, wts.kh, wts.kw, stride[0], stride[1],
@@ -208,9 +211,14 @@ def bconv2d_fused(act: PackedActivations, wts: PackedWeights, *, bias=None, post
         if want_bits:
             bits = torch.empty((act.n, (wts.c_out + 63) // 64, ho, wo, 4), dtype=torch.int32, device=dev)
             ep.out_bits = bits.data_ptr()
-        _maybe_tune(act, wts, geom, ep, flags, dev)
-        rc = native.lib().bnn_bconv2d_fused_fwd(act.bits.data_ptr(), wts.bits.data_ptr(), ctypes.byref(geom),
-                                                ctypes.byref(ep), flags, _stream_ptr(dev))
+        if plan is not None:
+            rc = native.lib().bnn_bconv2d_fused_fwd_plan(act.bits.data_ptr(), wts.bits.data_ptr(), ctypes.byref(geom),
+                                                         ctypes.byref(ep), flags, *[int(v) for v in plan],
+                                                         _stream_ptr(dev))
+        else:
+            _maybe_tune(act, wts, geom, ep, flags, dev)
+            rc = native.lib().bnn_bconv2d_fused_fwd(act.bits.data_ptr(), wts.bits.data_ptr(), ctypes.byref(geom),
+                                                    ctypes.byref(ep), flags, _stream_ptr(dev))
     native.check(rc, "bnn_bconv2d_fused_fwd")
     packed = None if bits is None else PackedActivations(bits, act.n, wts.c_out, ho, wo)
     return out, packed

@@ -65,6 +65,11 @@ _SIGNATURES = {
                                  c_void_p]),
     "bnn_bconv2d_tune": (c_int, [c_void_p, c_void_p, POINTER(ConvGeom), POINTER(Epilogue), c_uint32, c_int32, c_void_p]),
     "bnn_conv_plan": (c_int, [POINTER(ConvGeom), c_uint32, c_int32, POINTER(c_int32)]),
+    "bnn_conv_plan_list": (c_int, [POINTER(ConvGeom), c_uint32, POINTER(c_int32), c_int32, POINTER(c_int32)]),
+    "bnn_bconv2d_fused_fwd_plan": (c_int, [c_void_p, c_void_p, POINTER(ConvGeom), POINTER(Epilogue), c_uint32, c_int32,
+                                           c_int32, c_int32, c_int32, c_void_p]),
+    "bnn_conv_instance": (c_int, [POINTER(ConvGeom), POINTER(Epilogue), c_uint32, c_int32, c_int32, c_int32, c_int32,
+                                  POINTER(c_int32)]),
 }
 
 _lib = None
@@ -114,6 +119,21 @@ def conv_plan(geom: ConvGeom, flags: int = 0, sms: int = 0) -> dict:
     arr = (c_int32 * 12)()
     check(lib().bnn_conv_plan(ctypes.byref(geom), flags, sms, arr), "bnn_conv_plan")
     return dict(zip(PLAN_FIELDS, list(arr)))
+
+
+def conv_plan_list(geom: ConvGeom, flags: int = 0, cap: int = 4096) -> list:
+    """Every feasible tile plan of a geometry, cost-model order (works without a GPU)."""
+    arr = (c_int32 * (12 * cap))()
+    n = c_int32(0)
+    check(lib().bnn_conv_plan_list(ctypes.byref(geom), flags, arr, cap, ctypes.byref(n)), "bnn_conv_plan_list")
+    return [dict(zip(PLAN_FIELDS, arr[12 * i: 12 * i + 12])) for i in range(min(cap, n.value))]
+
+
+def conv_instance(geom: ConvGeom, ep: "Epilogue", flags: int, P: int, C: int, TH: int = 0, warps: int = 0) -> dict:
+    """Kernel instance a forced-plan launch would run: P, C, kw / stride instance, carry-save mode, epilogue kind."""
+    arr = (c_int32 * 6)()
+    check(lib().bnn_conv_instance(ctypes.byref(geom), ctypes.byref(ep), flags, P, C, TH, warps, arr), "bnn_conv_instance")
+    return dict(zip(("P", "C", "kw_inst", "stride_inst", "csa", "epi"), list(arr)))
 
 
 def launch_count() -> int:

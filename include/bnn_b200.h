@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define BNN_B200_ABI_VERSION 3
+#define BNN_B200_ABI_VERSION 4
 
 /* argument errors (negative); positive codes are cudaError_t */
 #define BNN_E_NULL        (-1)  /* required pointer is NULL                         */
@@ -186,6 +186,21 @@ int bnn_bconv2d_tune(const void *abits, const void *wbits, const bnn_conv_geom *
  * sms <= 0 assumes 148.
  */
 int bnn_conv_plan(const bnn_conv_geom *geom, uint32_t flags, int32_t sms, int32_t *plan);
+
+/*
+ * Test / tuning hooks for the tile planner.  bnn_conv_plan_list enumerates every feasible tile plan of a geometry
+ * (rows of 12 ints in bnn_conv_plan's format, cost-model order, at most `cap` rows written, *count = how many exist).
+ * bnn_bconv2d_fused_fwd_plan is bnn_bconv2d_fused_fwd with the plan forced to the candidate whose (P, C, TH, warps)
+ * match (TH <= 0 / warps <= 0: best-ranked candidate of that (P, C) family); BNN_E_UNSUPPORTED if there is none.
+ * bnn_conv_instance reports which kernel instance that launch runs: inst[6] = {P, C, kw instance, stride instance,
+ * carry-save mode, epilogue instance 0..4}.  The parity suite sweeps every instance with these (tests/test_gpu_plans.py).
+ */
+int bnn_conv_plan_list(const bnn_conv_geom *geom, uint32_t flags, int32_t *plans, int32_t cap, int32_t *count);
+int bnn_bconv2d_fused_fwd_plan(const void *abits, const void *wbits, const bnn_conv_geom *geom,
+                               const bnn_epilogue *epilogue, uint32_t flags, int32_t P, int32_t C, int32_t TH,
+                               int32_t warps, void *stream);
+int bnn_conv_instance(const bnn_conv_geom *geom, const bnn_epilogue *epilogue, uint32_t flags, int32_t P, int32_t C,
+                      int32_t TH, int32_t warps, int32_t *inst);
 
 /*
  * bnn.layers.Linear.forward (bnn/layers/linear.py:22-27): rows x in_features

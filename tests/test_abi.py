@@ -36,7 +36,7 @@ def test_size_helpers_and_errors_without_gpu():
     assert lib.bnn_act_bits_bytes(1, 65, 1, 1) == 2 * 16
     assert lib.bnn_weight_bits_bytes(33, 64, 3, 3) == 2 * 9 * 32 * 8
     assert lib.bnn_act_bits_bytes(0, 1, 1, 1) == 0
-    assert native.query(native.Q_ABI_VERSION) == 3
+    assert native.query(native.Q_ABI_VERSION) == 4
     assert native.query(native.Q_SM_ARCH) == 100
     assert b"NULL" in lib.bnn_strerror(-1)
     # argument errors are reported before any CUDA call
