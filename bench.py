@@ -1,25 +1,29 @@
 #!/usr/bin/env python
-"""bench.py -- images/sec of the ResNet-18 XNOR-Net forward (BASELINE.json metric) on N B200s.
+"""bench.py -- images/sec of a binarized-network forward (BASELINE.json metric) on N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA engine
-    python bench.py --impl reference ...                            # reference CPU float-sim arm
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA engine, BASELINE configs[1]
+    python bench.py --config resnet50|hblock ...                    # BASELINE configs[2] / configs[3], same line
+    python bench.py --impl reference ...                            # the reference's CPU float-sim arm
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one forward pass of the prepared model over one synthetic batch of 256 images per
-GPU (BASELINE configs[1]; 224x224, random-init weights, randomised BatchNorm statistics --
-SURVEY.md section 8(d)).  One JSON line is printed by rank 0.
+A "step" is one forward pass of the prepared model over one synthetic batch per GPU (resnet18: 256 images of
+224x224, BASELINE configs[1]; resnet50: 128 of 224x224; hblock: 64 of 256x256), random-init weights, randomised
+BatchNorm statistics.  One JSON line is printed by rank 0.
 
   value      whole-job images/s, inputs resident in HBM, CUDA-event timed, max over ranks
   e2e        same metric through the public module API with PINNED HOST input every step
-             (H2D of the batch and D2H of the logits inside the timed region)
-  roofline   binarized-layer path (bit-pack + XNOR-popcount kernels): algorithmic bytes at the
-             drop-in contract (fp32 NCHW in + fp32 NCHW out per layer) divided by
-             the CUDA-event time of those launches, against MEASURED_PEAKS.json hbm_gbs
-  popc       same launches as binary MAC/s against the POPC-pipe peak measured by bnn_ubench
-  cpu_baseline  the oracle's float simulation (oracle/floatsim.py, a torch-CPU restatement of
-             the reference's forward) timed on this box's host cores on a bounded sample
+             (H2D of the batch and D2H of the logits inside the timed region); h2d_ceiling = what the box's
+             host->device path delivers for the same buffers with all ranks copying at once
+  roofline   the binarized layers' launches as binary MAC/s against the POPC-pipe peak measured on this GPU by
+             bnn_ubench (these layers are POPC-bound); roofline.hbm is the same launches as
+             algorithmic bytes/s against MEASURED_PEAKS.json hbm_gbs
+  tighter_roofline  sum over layers of max(bytes / HBM rate, bMAC / POPC rate) against the launches and the step
+  parity     rows of the TIMED graph's output (every rank's block at N > 1) against the reference's CPU forward
+  dropin     the same model without fuse.optimize (prepare_binary_model only: per-layer kernels + torch glue)
+  cpu_baseline  the reference's CPU float simulation on this box's host cores, bounded sample
 """
 import argparse
+import importlib
 import json
 import os
 import statistics
@@ -35,44 +39,92 @@ import torch.nn as nn
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "images/sec ResNet-18 XNOR fwd @bs256"
-BATCH_PER_GPU = 256
-RES = 224
+CONFIGS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on
+    "resnet18": dict(metric="images/sec ResNet-18 XNOR fwd @bs256", batch=256, res=224,
+                     what="resnet18 XNOR-Net ({variant}, 19 binarized convs, first/last fp32)"),
+    # configs[2]: ResNet-50, XNOR-Net++ (learned per-channel post scale), fc patched to 2048 inputs
+    "resnet50": dict(metric="images/sec ResNet-50 XNOR++ fwd @bs128", batch=128, res=224,
+                     what="resnet50 XNOR-Net++ (Bottleneck, 52 binarized convs, learned alpha, first/last fp32)"),
+    # configs[3]: Hierarchical-Block harness
+    "hblock": dict(metric="images/sec HBlock-net XNOR fwd @bs64", batch=64, res=256,
+                   what="HBlock harness (stem, HBlock(64,256)+BN-ReLU-1x1 shortcut, avgpool2, 4xHBlock(256,256); 16 binarized convs)"),
+}
 
 
-def build_model(variant: str):
+def workload_config(args, world):
+    """`config` of the JSON line: identical for the B200 arm and the reference arm of the same invocation."""
+    c = CONFIGS[args.config]
+    return {"workload": f"{c['what'].format(variant=args.variant)} {c['res']}x{c['res']} bs{args.batch}/GPU",
+            "global_batch": args.batch * world, "parallelism": f"dp{world}"}
+
+
+def build_model(config: str, variant: str):
+    """The workload prepared with THIS repo's package (bnn_b200)."""
     import bnn_b200 as bnn
     from bnn_b200 import workloads
-    from bnn_b200.ops import BasicInputBinarizer, XNORWeightBinarizer
+    from bnn_b200.ops import BasicInputBinarizer, BasicScaleBinarizer, XNORWeightBinarizer
     torch.manual_seed(0)
-    if variant == "pre_prelu":
-        model = workloads.resnet18(workloads.PreBasicBlock, nn.PReLU)
+    post = bnn.Identity
+    if config == "resnet18":
+        model = workloads.resnet18(workloads.PreBasicBlock, nn.PReLU) if variant == "pre_prelu" else workloads.resnet18()
+    elif config == "resnet50":
+        model, post = workloads.resnet50(), BasicScaleBinarizer
     else:
-        model = workloads.resnet18()
-    cfg = bnn.BConfig(BasicInputBinarizer, bnn.Identity,
-                      XNORWeightBinarizer.with_args(compute_alpha=True, center_weights=True))
+        model = workloads.HBlockNet()
+    cfg = bnn.BConfig(BasicInputBinarizer, post, XNORWeightBinarizer.with_args(compute_alpha=True, center_weights=True))
     model = bnn.prepare_binary_model(model, cfg, ignore_layers_name=["_first_", "_last_"])
     workloads.randomize_batchnorm(model, seed=1)
     return model.eval()
 
 
+def build_reference_model(config: str, variant: str, state_dict=None):
+    """The same workload built and prepared by the UNMODIFIED reference (oracle/_ref, byte-compiled from
+    /root/reference by oracle/build.py).  Returns None when oracle/_ref is absent.  With `state_dict`, the
+    parameters of a bnn_b200-prepared model are loaded (the keys interchange by design)."""
+    from oracle import build as oracle_build
+    ref = oracle_build.load_ref()
+    if ref is None:
+        return None
+    from bnn_b200 import workloads                       # randomize_batchnorm + the harness skeleton only
+    rops = importlib.import_module("bnn_ref.ops")
+    rresnet = importlib.import_module("bnn_ref.models.resnet")
+    rlayers = importlib.import_module("bnn_ref.models.layers")
+    torch.manual_seed(0)
+    post = ref.Identity
+    if config == "resnet18":
+        model = (rresnet.resnet18(block_type=rlayers.PreBasicBlock, activation=nn.PReLU) if variant == "pre_prelu"
+                 else rresnet.resnet18())
+    elif config == "resnet50":
+        model = rresnet.resnet50()
+        model.fc = nn.Linear(2048, 1000)                 # upstream wires fc to 512 features (resnet.py:101,143)
+        post = rops.BasicScaleBinarizer
+    else:
+        model = workloads.HBlockNet(hblock=lambda i, p, d: rlayers.HBlock(i, p, downsample=d, norm_layer=nn.BatchNorm2d))
+    cfg = ref.BConfig(activation_pre_process=rops.BasicInputBinarizer, activation_post_process=post,
+                      weight_pre_process=rops.XNORWeightBinarizer.with_args(compute_alpha=True, center_weights=True))
+    model = ref.prepare_binary_model(model, cfg, ignore_layers_name=["_first_", "_last_"])
+    workloads.randomize_batchnorm(model, seed=1)
+    if state_dict is not None:
+        model.load_state_dict(state_dict)
+    return model.eval()
+
+
 def layer_algorithmics(model, batch, res):
     """Algorithmic bytes / binary MACs per binarized layer at the drop-in contract."""
+    import copy
     import bnn_b200 as bnn
     shapes = {}
+    twin = copy.deepcopy(model).cpu()
     hooks = []
-    for name, m in model.named_modules():
+    for name, m in twin.named_modules():
         if isinstance(m, bnn.layers.Conv2d):
             hooks.append(m.register_forward_hook(
                 lambda mod, inp, out, name=name: shapes.__setitem__(name, (tuple(inp[0].shape), tuple(out.shape)))))
     with torch.no_grad(), bnn.runtime.floatsim_enabled():
-        twin_in = torch.zeros(1, 3, res, res)
-        import copy
-        copy.deepcopy(model).cpu()(twin_in)
-    for h in hooks:
-        h.remove()
+        twin(torch.zeros(1, 3, res, res))
     table = {}
-    for name, m in model.named_modules():
+    for name, m in twin.named_modules():
         if name in shapes:
             (_, ci, h, w), (_, co, ho, wo) = shapes[name]
             k = ci * m.kernel_size[0] * m.kernel_size[1]
@@ -82,13 +134,18 @@ def layer_algorithmics(model, batch, res):
 
 
 def fused_layer_order(model):
-    """Names of the binarized convs in the order the fused engine launches them (shortcut first)."""
+    """Names of the binarized convs in the order the fused engines launch them (shortcut first)."""
     names = []
-    for lname in ("layer1", "layer2", "layer3", "layer4"):
-        for bi, blk in enumerate(getattr(model, lname)):
-            if getattr(blk, "downsample", None) is not None:
-                names.append(f"{lname}.{bi}.downsample.1")
-            names += [f"{lname}.{bi}.conv1", f"{lname}.{bi}.conv2"]
+    if hasattr(model, "layer1"):
+        for lname in ("layer1", "layer2", "layer3", "layer4"):
+            for bi, blk in enumerate(getattr(model, lname)):
+                if getattr(blk, "downsample", None) is not None:
+                    names.append(f"{lname}.{bi}.downsample.1")
+                names += [f"{lname}.{bi}.{c}" for c in ("conv1", "conv2", "conv3") if hasattr(blk, c)]
+    elif hasattr(model, "block0"):
+        names += ["block0.downsample.2", "block0.conv1", "block0.conv2", "block0.conv3"]
+        for bi in range(len(model.blocks)):
+            names += [f"blocks.{bi}.{c}" for c in ("conv1", "conv2", "conv3")]
     return names
 
 
@@ -156,10 +213,10 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback"
 
 
-def measured_traffic():
+def measured_traffic(config):
     """DRAM bytes of the binarized-path launches of one step, from the committed ncu capture (profiles/traffic.json)."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(path):
+    if config == "resnet18" and os.path.exists(path):
         with open(path) as f:
             return json.load(f)
     return None
@@ -167,7 +224,7 @@ def measured_traffic():
 
 def bind_host_to_gpu_numa(dev_index: int):
     """Multi-GPU runs: run this rank's host threads (and therefore first-touch its pinned upload buffers) on the NUMA
-    node the GPU hangs off, so eight ranks do not pull their 154 MB batches across the socket interconnect.  Best
+    node the GPU hangs off, so eight ranks do not pull their batches across the socket interconnect.  Best
     effort: any missing sysfs entry or permission leaves the affinity as it was.  Returns the node or None."""
     try:
         props = torch.cuda.get_device_properties(dev_index)
@@ -190,12 +247,12 @@ def bind_host_to_gpu_numa(dev_index: int):
         return None
 
 
-def pick_cpu_threads(twin):
+def pick_cpu_threads(twin, res):
     """The float simulation is many small torch ops; on a many-core host the default (all cores) is not always
     the fastest setting.  Give the CPU arm its best case: try a few intra-op thread counts on a tiny batch."""
     ncpu = os.cpu_count() or 1
     cands = sorted({ncpu, max(1, ncpu // 2), max(1, ncpu // 4), min(ncpu, 16)}, reverse=True)
-    x = torch.randn(8, 3, RES, RES, generator=torch.Generator().manual_seed(0))
+    x = torch.randn(8, 3, res, res, generator=torch.Generator().manual_seed(0))
     best, best_t = cands[0], float("inf")
     with torch.no_grad():
         for t in cands:
@@ -210,34 +267,44 @@ def pick_cpu_threads(twin):
     return best
 
 
-def cpu_floatsim_rate(model, sample_batch, iters, threads):
-    """images/s of the oracle float simulation on host cores (bounded sample)."""
+def cpu_twin(config, variant, model_cpu=None):
+    """The CPU arm's model: the unmodified reference (oracle/_ref) when it is there, else the oracle's port of it.
+    Returns (module, kind, description)."""
+    sd = None if model_cpu is None else model_cpu.state_dict()
+    ref_model = build_reference_model(config, variant, sd)
+    if ref_model is not None:
+        return ref_model, "reference", "unmodified reference bnn 0.1.2 (oracle/_ref/bnn_ref, byte-compiled from /root/reference)"
     from oracle import floatsim
-    twin = floatsim.mirror_model(model)
-    threads = pick_cpu_threads(twin)
-    x = torch.randn(sample_batch, 3, RES, RES, generator=torch.Generator().manual_seed(0))
+    return floatsim.mirror_model(model_cpu if model_cpu is not None else build_model(config, variant)), "port", \
+        "oracle/floatsim.py (torch CPU restatement of the reference's forward)"
+
+
+def cpu_floatsim_rate(config, variant, model_cpu, sample_batch, iters, res):
+    """images/s of the reference's CPU float simulation on host cores (bounded sample)."""
+    twin, kind, what = cpu_twin(config, variant, model_cpu)
+    threads = pick_cpu_threads(twin, res)
+    x = torch.randn(sample_batch, 3, res, res, generator=torch.Generator().manual_seed(0))
     with torch.no_grad():
         twin(x)                                           # warm-up
         t0 = time.perf_counter()
         for _ in range(iters):
             twin(x)
         dt = time.perf_counter() - t0
-    return sample_batch * iters / dt, threads
+    return sample_batch * iters / dt, threads, kind, what
 
 
 def run_reference(args, rank, world):
-    """Reference arm: the reference's CPU float-sim forward (oracle port: the reference is pure Python
-    over torch and is not installed on the GPU box) on all host cores, bounded sample per step."""
+    """Reference arm: the reference's own CPU float-sim forward on all host cores; every step is one forward over a
+    bounded sample (--ref-batch images, default = the full per-GPU batch of the configuration)."""
     if rank != 0:
         return
-    model = build_model(args.variant)
-    from oracle import floatsim
-    twin = floatsim.mirror_model(model)
-    threads = pick_cpu_threads(twin)
-    sample = args.ref_batch
-    x = torch.randn(sample, 3, RES, RES, generator=torch.Generator().manual_seed(0))
+    c = CONFIGS[args.config]
+    twin, kind, what = cpu_twin(args.config, args.variant)
+    threads = pick_cpu_threads(twin, c["res"])
+    sample = args.ref_batch or args.batch
+    x = torch.randn(sample, 3, c["res"], c["res"], generator=torch.Generator().manual_seed(0))
     with torch.no_grad():
-        for _ in range(max(1, min(args.warmup, 2))):
+        for _ in range(args.warmup):
             twin(x)
         t0 = time.perf_counter()
         for _ in range(args.steps):
@@ -245,18 +312,26 @@ def run_reference(args, rank, world):
         dt = time.perf_counter() - t0
     value = sample * args.steps / dt
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": c["metric"], "value": value, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"resnet18 XNOR-Net ({args.variant}, first/last fp32) {RES}x{RES}",
-                   "sample": f"{sample} images per step on CPU"},
-        "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} forwards of {sample} images, oracle/floatsim.py (torch CPU fp32), "
+        "config": workload_config(args, max(1, args.gpus)),
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": kind,
+                         "sample": f"{args.steps} forwards of {sample} images, {what}, torch CPU fp32, "
                                    f"{threads} of {os.cpu_count()} host threads (fastest of a small sweep)"},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def percentile(v, q):
+    s = sorted(v)
+    if not s:
+        return None
+    i = (len(s) - 1) * q
+    lo, hi = int(i), min(int(i) + 1, len(s) - 1)
+    return s[lo] + (s[hi] - s[lo]) * (i - lo)
 
 
 def main():
@@ -265,17 +340,22 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="resnet18", choices=sorted(CONFIGS))
     ap.add_argument("--variant", default="basic_relu", choices=["basic_relu", "pre_prelu"])
-    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="images per GPU per step")
-    ap.add_argument("--ref-batch", type=int, default=64, help="images per CPU step of the reference arm")
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: the configuration's)")
+    ap.add_argument("--ref-batch", type=int, default=0, help="images per CPU step of the reference arm (default: --batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA graph")
     ap.add_argument("--no-fuse", action="store_true", help="per-layer kernels + torch glue (no cross-module fusion)")
-    ap.add_argument("--stem", default="mma", choices=["mma", "fma"],
-                    help="fused engine's stem kernel: mma.sync split-fp16 (default) or the fp32 fma chain")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the extra timing of the unfused drop-in path")
+    ap.add_argument("--stem", default="auto", choices=["auto", "tc", "mma", "fma"],
+                    help="fused engine's stem kernel: tcgen05 (tc), mma.sync split-fp16 (mma) or the fp32 fma chain")
     ap.add_argument("--layers-out", default=None, help="write the per-layer table to this JSON file")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    cfgd = CONFIGS[args.config]
+    args.batch = args.batch or cfgd["batch"]
+    RES = cfgd["res"]
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -293,7 +373,7 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         import datetime
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     # fp32 glue (stem conv, fc) in true fp32: the reference's CPU float-sim is the parity target
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -302,15 +382,16 @@ def main():
     from bnn_b200 import functional as BF
     from bnn_b200 import native, sharded
 
-    model_cpu = build_model(args.variant)
+    model_cpu = build_model(args.config, args.variant)
     algo = layer_algorithmics(model_cpu, args.batch, RES)
-    model = model_cpu.to(dev)
+    import copy
+    model = copy.deepcopy(model_cpu).to(dev)
     from bnn_b200 import fuse
     engine = model if args.no_fuse else fuse.optimize(model, stem=args.stem)   # public API: bnn_b200.fuse.optimize
     B = args.batch
-    x_dev = torch.randn(B, 3, RES, RES, device=dev)       # 154 MB at bs256 > 126 MB L2
-    x_host = torch.randn(B, 3, RES, RES).pin_memory()
-    stream = torch.cuda.current_stream()
+    # every rank gets its own images (seed 1000 + rank): rank 0 can regenerate any rank's rows for the parity check
+    x_host = torch.randn(B, 3, RES, RES, generator=torch.Generator().manual_seed(1000 + rank)).pin_memory()
+    x_dev = x_host.to(dev)                                 # 154 MB at bs256 > 126 MB L2
 
     def step_resident():
         y = engine(x_dev)
@@ -325,17 +406,30 @@ def main():
             torch.cuda.synchronize()
 
     def timed(fn, steps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        """EXACTLY `steps` calls bracketed by barrier + synchronize; returns (total ms, max over ranks; per-step ms list)."""
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
         sync_all()
-        e0.record()
-        for _ in range(steps):
+        evs[0].record()
+        for i in range(steps):
             fn()
-        e1.record()
+            evs[i + 1].record()
         sync_all()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        ms = torch.tensor([evs[0].elapsed_time(evs[-1])], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        return float(ms.item()), [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
+
+    def capture(eng):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            eng(x_dev)
+            side.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):          # the forward only; the collective stays outside
+                out = eng(x_dev)
+        torch.cuda.current_stream().wait_stream(side)
+        return g, out
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -347,18 +441,8 @@ def main():
 
         graph = None
         if not args.no_graph:
-            # the whole forward as one CUDA graph: ~60 launches per step stop costing host time
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                step_resident()
-                side.synchronize()
-                engine(x_dev)
-                side.synchronize()
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph, stream=side):      # the forward only; the collective stays outside
-                    graph_out = engine(x_dev)
-            torch.cuda.current_stream().wait_stream(side)
+            # the whole forward as one CUDA graph: the launches of a step stop costing host time
+            graph, graph_out = capture(engine)
 
             def step_graph():
                 graph.replay()
@@ -372,17 +456,62 @@ def main():
         t_region0 = time.perf_counter()
         launches_per_step = None
         if graph is not None:
-            ms = timed(step_graph, args.steps)
+            ms, per_step = timed(step_graph, args.steps)
+            timed_out = step_graph().clone()
             # a replay re-issues every captured launch; count them from one eager step
             l0 = native.launch_count(); step_resident(); launches_per_step = native.launch_count() - l0
         else:
-            ms = timed(step_resident, args.steps)
-            launches_per_step = (native.launch_count() - launches0) // args.steps
+            ms, per_step = timed(step_resident, args.steps)
+            timed_out = step_resident().clone()
+            launches_per_step = (native.launch_count() - launches0) // (args.steps + 1)
         if rank == 0:
             sampler.window(t_region0, time.perf_counter())
         clocks = sampler.stop() if rank == 0 else None
 
-        # end to end through the public API (bnn_b200.pipeline.HostPipeline): every step uploads the batch from
+        # ---- parity of what was just timed (outside the timed region): rows of every rank's block of the output of the
+        # timed graph against the reference's CPU forward on the same rows
+        parity = None
+        if rank == 0:
+            rows_per_rank = max(2, -(-8 // world))
+            twin, twin_kind, _ = cpu_twin(args.config, args.variant, model_cpu)
+            torch.set_num_threads(os.cpu_count() or 1)
+            got, want = [], []
+            for r in range(world):
+                xr = x_host if r == 0 else torch.randn(B, 3, RES, RES, generator=torch.Generator().manual_seed(1000 + r))
+                want.append(twin(xr[:rows_per_rank].clone()))
+                got.append(timed_out[r * B: r * B + rows_per_rank].float().cpu())
+            got, want = torch.cat(got), torch.cat(want)
+            err = float((got - want).abs().max() / want.abs().max())
+            parity = {"max_rel_err": err, "rows": int(got.shape[0]), "ranks": world,
+                      "argmax_equal": bool((got.argmax(1) == want.argmax(1)).all()), "tolerance": 1e-3,
+                      "against": f"{twin_kind} CPU fp32 forward of the same parameters, rows 0..{rows_per_rank - 1} of "
+                                 "every rank's block of the timed (graph-replayed, all-gathered) logits"}
+            if not (err <= 1e-3):
+                raise SystemExit(f"bench.py: parity FAILED on the timed output: {json.dumps(parity)}")
+
+        # ---- host -> device ceiling of this box for the same pinned buffers, every rank copying at once
+        h2d_buf = torch.empty_like(x_dev)
+        cs = torch.cuda.Stream()
+        with torch.cuda.stream(cs):
+            for _ in range(2):
+                h2d_buf.copy_(x_host, non_blocking=True)
+        sync_all()
+        ce0, ce1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ncopies = 10
+        with torch.cuda.stream(cs):
+            ce0.record(cs)
+            for _ in range(ncopies):
+                h2d_buf.copy_(x_host, non_blocking=True)
+            ce1.record(cs)
+        sync_all()
+        h2d_ms = torch.tensor([ce0.elapsed_time(ce1)], device=dev)
+        if world > 1:
+            dist.all_reduce(h2d_ms, op=dist.ReduceOp.MAX)
+        h2d_bytes = x_host.numel() * 4
+        h2d_ceiling_gbs = world * ncopies * h2d_bytes / (float(h2d_ms.item()) * 1e-3) * 1e-9
+        del h2d_buf
+
+        # ---- end to end through the public API (bnn_b200.pipeline.HostPipeline): every step uploads the batch from
         # pinned host memory and downloads the logits; upload of batch i+1 overlaps the forward of batch i
         from bnn_b200.pipeline import HostPipeline
         pipe = HostPipeline(engine, x_host, dev, use_graphs=(graph is not None),
@@ -402,9 +531,30 @@ def main():
         if world > 1:
             dist.all_reduce(ms_e2e_t, op=dist.ReduceOp.MAX)
         ms_e2e = float(ms_e2e_t.item())
+        e2e_diff = float((last_logits[:B].float() - timed_out[:B].float().cpu()).abs().max())
         assert torch.isfinite(last_logits).all()
+        del pipe
 
-        # per-launch CUDA-event timing of the binarized path (same data, same stream, warm)
+        # ---- the literal drop-in (prepare_binary_model only, no fuse.optimize): per-layer kernels + torch glue
+        dropin = None
+        if not args.no_fuse and not args.no_dropin:
+            for _ in range(3):
+                model(x_dev)
+            sync_all()
+            dsteps = max(3, min(10, args.steps))
+            try:
+                g2, _ = capture(model)
+                for _ in range(2):
+                    g2.replay()
+                dms, _ = timed(g2.replay, dsteps)
+                del g2
+            except RuntimeError:                         # not capturable on this torch build: eager timing
+                dms, _ = timed(lambda: model(x_dev), dsteps)
+            dropin = {"value": B * world / (dms / dsteps * 1e-3), "unit": "images/s", "ms_per_step": dms / dsteps,
+                      "steps": dsteps, "what": "prepare_binary_model only: bit-pack + bnn_bconv2d_fwd per layer, fp32 NCHW "
+                                               "between layers, torch stem / BN / act / add (input resident, CUDA graph)"}
+
+        # ---- per-launch CUDA-event timing of the binarized path (same data, same stream, warm)
         per_layer = {}
         if rank == 0:
             records = []
@@ -480,7 +630,7 @@ def main():
         return
 
     peaks, peak_kind = measured_peaks()
-    traffic = measured_traffic()
+    traffic = measured_traffic(args.config)
     n_conv = sum(1 for k, d in per_layer.items() if d.get("conv_ms", 0) > 0)
     total_bytes = sum(d["bytes"] for d in per_layer.values())
     total_bmac = sum(d["bmac"] for d in per_layer.values())
@@ -495,43 +645,56 @@ def main():
     popc_peak_tbmac = popc_gops * 32 * 1e-3 if popc_gops else None     # one POPC = 32 binary MACs
     images = B * world
     value = images / (ms / args.steps * 1e-3)
+    e2e_value = images / (ms_e2e / args.steps * 1e-3)
+    achieved_tbmac = total_bmac / (conv_ms * 1e-3) * 1e-12 if conv_ms else None
+    stem_name = getattr(engine, "stem_kernel_used", None)
+    config = workload_config(args, world)
     line = {
-        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "metric": cfgd["metric"], "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": f"resnet18 XNOR-Net ({args.variant}, 19 binarized convs, first/last fp32) {RES}x{RES} bs{B}/GPU",
-                   "global_batch": images, "parallelism": f"dp{world}",
-                   "l2": f"input batch {B * 3 * RES * RES * 4 / 1e6:.0f} MB + activations exceed the 126 MB L2",
+        "config": config,
+        "engine": {"l2": f"input batch {B * 3 * RES * RES * 4 / 1e6:.0f} MB + activations exceed the 126 MB L2",
                    "launch": "cuda_graph" if graph is not None else "eager",
                    "fusion": "per-layer" if args.no_fuse else "bnn_b200.fuse.optimize (BN/act/residual/sign in conv epilogues)",
-                   "glue": ("torch fp32 (TF32 off): stem conv7x7+BN+ReLU+maxpool, BN/act/add per layer, avgpool, fc"
-                            if args.no_fuse else f"stem = {'bnn_stem_mma_fwd' if args.stem == 'mma' else 'bnn_stem_fwd'}; "
-                                              "torch fp32 only for global avgpool + fc")},
+                   "glue": ("torch fp32 (TF32 off): stem conv+BN+ReLU(+maxpool), BN/act/add per layer, avgpool, fc"
+                            if args.no_fuse else f"stem kernel = {stem_name}; torch fp32 only for global avgpool + fc")},
+        "ms_per_step_stats": {"median": statistics.median(per_step), "p10": percentile(per_step, 0.1),
+                              "p90": percentile(per_step, 0.9), "what": "per-step CUDA-event times of the timed region, rank 0"},
         "clocks": clocks,
-        "e2e": {"value": images / (ms_e2e / args.steps * 1e-3), "unit": "images/s",
-                "h2d_bytes_per_step": B * 3 * RES * RES * 4 * world, "d2h_bytes_per_step": images * 1000 * 4 * world,
-                "ms_per_step": ms_e2e / args.steps,
+        "parity": parity,
+        "e2e": {"value": e2e_value, "unit": "images/s",
+                "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": images * 1000 * 4 * world,
+                "ms_per_step": ms_e2e / args.steps, "max_abs_diff_vs_resident_logits": e2e_diff,
+                "h2d_ceiling_gbs": h2d_ceiling_gbs,
+                "h2d_frac_of_ceiling": (h2d_bytes * world / (ms_e2e / args.steps * 1e-3) * 1e-9) / h2d_ceiling_gbs,
+                "h2d_ceiling_what": f"{ncopies} back-to-back cudaMemcpyAsync of the same pinned {h2d_bytes / 1e6:.0f} MB batch "
+                                    f"on {world} rank(s) at once, no compute: aggregate GB/s (max time over ranks)",
                 "how": "bnn_b200.pipeline.HostPipeline: pinned-host batch -> H2D -> fused engine -> D2H logits, "
                        "double-buffered (upload of step i+1 overlaps the forward of step i)"
                        + (f"; rank 0 host threads and pinned buffers bound to NUMA node {numa_node}" if numa_node is not None else "")},
         "gpu_launches": int(launches_per_step * args.steps) if launches_per_step else 0,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": achieved / peaks["hbm_gbs"],
+        "roofline": {"bound": "popc", "achieved": achieved_tbmac, "peak": popc_peak_tbmac, "unit": "T bMAC/s",
+                     "frac": (achieved_tbmac / popc_peak_tbmac) if (popc_peak_tbmac and achieved_tbmac) else None,
+                     "peak_kind": "bnn_ubench(0): POPC warp-lane ops/s measured on this GPU in this run x 32 binary MACs "
+                                  "(SASS loop: profiles/r02_ubench_popc_sass.txt); nominal 148 SM x 16 lanes x 1.965 GHz x 32 = 148.9",
+                     "launches": n_conv, "algorithmic_bmac_per_launch": total_bmac / max(1, n_conv),
+                     "avg_launch_ms": conv_ms / max(1, n_conv), "lop3_popc_iadd_gwords_s": mix_gwords,
                      "traffic": (traffic["binarized_path_dram_bytes_per_step"] / max(1, n_conv)
-                                 if traffic and not args.no_fuse and B == BATCH_PER_GPU else None),
+                                 if traffic and not args.no_fuse and B == cfgd["batch"] else None),
                      "traffic_what": "ncu dram__bytes_read+write of the same launches, per conv launch "
                                      "(profiles/traffic.json; fused engine at bs 256): below the algorithmic bytes "
                                      "because fused layers exchange bit planes instead of fp32 NCHW tensors",
-                     "launches": n_conv, "algorithmic_bytes_per_launch": total_bytes / max(1, n_conv),
-                     "avg_launch_ms": path_ms / max(1, n_conv), "peak_kind": peak_kind,
-                     "what": "bit-pack + XNOR-popcount launches of the 19 binarized layers, algorithmic bytes "
-                             f"{total_bytes / 1e9:.3f} GB/step over {path_ms:.3f} ms/step; these layers are "
-                             "POPC-bound, see 'popc'"},
-        "popc": {"achieved_tbmac_s": total_bmac / (conv_ms * 1e-3) * 1e-12, "peak_tbmac_s": popc_peak_tbmac,
-                 "frac": (total_bmac / (conv_ms * 1e-3) * 1e-12 / popc_peak_tbmac) if popc_peak_tbmac else None,
-                 "peak_kind": "bnn_ubench(POPC) x 32 on this GPU", "lop3_popc_iadd_gwords_s": mix_gwords,
-                 "conv_ms_per_step": conv_ms, "binarized_path_ms_per_step": path_ms},
+                     "what": f"XNOR-popcount launches of the {len(algo)} binarized layers: {total_bmac / 1e9:.1f} G binary MACs "
+                             f"per step over {conv_ms:.3f} ms; every 3x3 layer is POPC-bound (SURVEY.md 8(d))",
+                     "hbm": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": achieved / peaks["hbm_gbs"], "peak_kind": peak_kind,
+                             "algorithmic_bytes_per_launch": total_bytes / max(1, n_conv),
+                             "what": f"same launches (+ bit-pack launches) as algorithmic bytes at the drop-in contract: "
+                                     f"{total_bytes / 1e9:.3f} GB/step over {path_ms:.3f} ms/step"}},
     }
+    if dropin is not None:
+        line["dropin"] = dropin
     if popc_peak_tbmac:
         # north_star's yardstick: per layer t >= max(bytes / BW_HBM, bMAC / P_popc), summed over the
         # binarized layers, against (i) the time of those launches and (ii) the WHOLE step (stem, classifier included)
@@ -543,13 +706,13 @@ def main():
             "binarized_path_frac": bound_ms / path_ms if path_ms else None,
             "whole_step_frac": bound_ms / (ms / args.steps),
             "what": "sum over the binarized layers of max(algorithmic bytes / measured HBM rate, binary MACs / measured "
-                    "POPC rate); the POPC term is the larger one for every 3x3 layer, so roofline.frac (HBM) is low by "
-                    "construction and this object is the one north_star's '>= 60 % of the tighter roofline' refers to"}
+                    "POPC rate), against the time of those launches and against the whole step (stem, shortcuts, "
+                    "classifier included): the figure north_star's '>= 60 % of the tighter roofline' refers to"}
     if world == 1 and not args.no_cpu_baseline:
-        sample, iters = 64, 10          # ~6-20 s of host work depending on the box
-        rate, threads = cpu_floatsim_rate(model_cpu, sample, iters, None)
-        line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
-                                "sample": f"{iters} forwards of {sample} images (oracle/floatsim.py, torch CPU fp32, "
+        sample, iters = min(64, B), 10          # ~6-20 s of host work depending on the box
+        rate, threads, kind, what = cpu_floatsim_rate(args.config, args.variant, model_cpu, sample, iters, RES)
+        line["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": threads, "kind": kind,
+                                "sample": f"{iters} forwards of {sample} images ({what}, torch CPU fp32, "
                                           f"{threads} of {os.cpu_count()} host threads: the fastest of a small sweep)"}
     if args.layers_out:
         os.makedirs(os.path.dirname(os.path.abspath(args.layers_out)), exist_ok=True)

@@ -10,7 +10,7 @@ layer's forward runs hand-written sm_100a kernels through the C ABI in include/b
 from .bconfig import BConfig, Identity
 from . import ops, layers, runtime, native, functional
 from .convert import (B200_MODULE_MAPPING, DEFAULT_MODULE_MAPPING, get_modules_to_binarize,
-                      get_unique_devices_, mapping_for_reference, prepare_binary_model,
+                      get_unique_devices_, invalidate, mapping_for_reference, prepare_binary_model,
                       swap_modules_by_name)
 
 __version__ = "0.1.0"

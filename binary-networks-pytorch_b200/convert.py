@@ -133,3 +133,16 @@ def prepare_binary_model(model: nn.Module, bconfig: BConfig,
     replacements = get_modules_to_binarize(model, bconfig, modules_mapping, custom_config_layers_name,
                                            ignore_layers_name)
     return swap_modules_by_name(model, replacements, modules_mapping)
+
+
+def invalidate(model: nn.Module) -> nn.Module:
+    """Drop every cached derivative of the model's parameters (packed weight planes, alpha, folded BatchNorm
+    constants, stem operands).  The caches follow the tensors' version counters, so they only go stale after writes
+    made through ``.data`` (``w.data.clamp_(-1, 1)`` in BNN training loops), which do not bump the counter; call this
+    after such updates.  Works on a prepared model and on the engines of ``bnn_b200.fuse``.  Returns ``model``."""
+    for m in model.modules():
+        if hasattr(m, "repack"):
+            m.repack()
+        if hasattr(m, "invalidate_caches"):
+            m.invalidate_caches()
+    return model

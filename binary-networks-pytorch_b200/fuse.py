@@ -43,7 +43,7 @@ class _FoldedBN:
     def get(self) -> Tuple[torch.Tensor, torch.Tensor]:
         bn = self.bn
         tensors = (bn.running_mean, bn.running_var, bn.weight, bn.bias)
-        key = tuple((t.data_ptr(), t._version) if t is not None else None for t in tensors)
+        key = tuple((t.data_ptr(), t._version) if t is not None else None for t in tensors) + (float(bn.eps),)
         if key != self.key:
             with torch.no_grad():
                 g = torch.rsqrt(bn.running_var + bn.eps)
@@ -69,6 +69,10 @@ def _activation_spec(mod: nn.Module):
 
 def _fusable_conv(conv) -> bool:
     if not isinstance(conv, Conv2d) or conv._is_float_layer():
+        return False
+    if conv.groups != 1:
+        # grouped convs (ResNeXt-style ``groups`` kwarg, BATS cells) run as per-group launches of the per-layer path
+        # (Conv2d._forward_grouped); a block holding one is not fused and keeps its own forward
         return False
     try:
         low = conv._lowering()
@@ -165,6 +169,7 @@ class _StemPlan:
             self.ok, self.conv, self.bn = True, conv, _FoldedBN(bn)
             self.key, self.w_t = None, None
             self.mma_key, self.mma_w = None, None
+            self.tc_key, self.tc_w = None, None
 
     def weight(self) -> torch.Tensor:
         w = self.conv.weight
@@ -188,12 +193,14 @@ class _StemPlan:
 class FusedResNet(nn.Module):
     """Inference engine over a prepared ResNet; same call signature as the wrapped model."""
 
-    def __init__(self, model: nn.Module, fuse_stem: bool = True, stem: str = "mma") -> None:
+    def __init__(self, model: nn.Module, fuse_stem: bool = True, stem: str = "auto") -> None:
         super().__init__()
-        if stem not in ("mma", "fma"):
-            raise ValueError(f"stem must be 'mma' (mma.sync, split fp16) or 'fma' (fp32 fma chain), got {stem!r}")
+        self.stem_kernel_used = "torch"
+        if stem not in ("auto", "tc", "mma", "fma"):
+            raise ValueError("stem must be 'auto', 'tc' (tcgen05, split fp16), 'mma' (mma.sync, split fp16) or 'fma' "
+                             f"(fp32 fma chain), got {stem!r}")
         self.model = model
-        self.stem_kernel = stem
+        self.stem_kernel = "mma" if stem == "auto" else stem
         blocks: List[nn.Module] = []
         for name in ("layer1", "layer2", "layer3", "layer4"):
             blocks += list(getattr(model, name))
@@ -203,6 +210,18 @@ class FusedResNet(nn.Module):
     @property
     def fused_blocks(self) -> int:
         return sum(p.fused for p in self.plans)
+
+    def invalidate_caches(self) -> None:
+        """Forget folded BatchNorm constants and stem operands (see ``bnn_b200.invalidate``)."""
+        for p in self.plans:
+            if p.fused:
+                for _, bn, _ in p.stages:
+                    bn.key = None
+                if p.shortcut is not None:
+                    p.shortcut[2].key = None
+        if self.stem is not None and self.stem.ok:
+            self.stem.bn.key = self.stem.key = self.stem.mma_key = None
+            self.stem.tc_key = None
 
     # what the NEXT block needs in front of its first sign(): its bn1 if it is pre-activation
     @staticmethod
@@ -274,6 +293,7 @@ class FusedResNet(nn.Module):
             if (self.stem is not None and self.stem.ok and first is not None and first.fused and x.is_cuda
                     and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == 3 and min(x.shape[2:]) >= 7):
                 # fp32 stem in one kernel: NHWC residual stream + the first binarized conv's planes
+                self.stem_kernel_used = {"mma": "bnn_stem_mma_fwd", "fma": "bnn_stem_fwd", "tc": "bnn_stem_tc_fwd"}[self.stem_kernel]
                 if self.stem_kernel == "mma":
                     x, bits = BF.stem_mma(x.contiguous(), self.stem.mma_weight(), self.stem.bn.get(),
                                           nx=self._entry_affine(first))
@@ -361,6 +381,14 @@ class FusedHBlockNet(nn.Module):
     def fused_blocks(self) -> int:
         return sum(p.ok for p in self.plans)
 
+    def invalidate_caches(self) -> None:
+        for p in self.plans:
+            if p.ok:
+                for bn in p.bns:
+                    bn.key = None
+                if p.shortcut is not None:
+                    p.shortcut[0].key = None
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         m = self.model
         if m.training:
@@ -374,7 +402,7 @@ class FusedHBlockNet(nn.Module):
             return m.fc(torch.flatten(m.avgpool(x), 1))
 
 
-def optimize(model: nn.Module, fuse_stem: bool = True, stem: str = "mma") -> nn.Module:
+def optimize(model: nn.Module, fuse_stem: bool = True, stem: str = "auto") -> nn.Module:
     """Return the fused inference engine for ``model`` if its layout is recognised, else ``model``.
     ``stem``: "mma" = the stem kernel on mma.sync with split-fp16 operands (fp32-level accuracy, default),
     "fma" = the fp32 fma-chain stem kernel (bit-identical to the oracle's summation order)."""

@@ -11,6 +11,7 @@ dense fp32 tensors it runs   bit-pack(x) -> XNOR/popcount kernel with fused epil
 through the C ABI (include/bnn_b200.h).  Packed weights are a cache keyed on the weight's
 storage and version counter, so ``load_state_dict`` / optimizer steps invalidate it.
 """
+import warnings
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -22,6 +23,18 @@ from .. import functional as BF
 from .. import runtime
 from ..bconfig import BConfig
 from ..native import NativeError
+
+
+_warned_training = False
+
+
+def _warn_training_floatsim() -> None:
+    global _warned_training
+    if not _warned_training:
+        _warned_training = True
+        warnings.warn("bnn_b200: a binarized layer in train() mode with autograd enabled runs the reference's fp32 "
+                      "simulation (straight-through gradients, torch ops); the B200 kernels are the eval()/no_grad "
+                      "forward path.  This warning is shown once.", RuntimeWarning, stacklevel=3)
 
 
 class NotLowerable(Exception):
@@ -140,7 +153,10 @@ class _BinaryLayer:
         return self._packed
 
     def repack(self) -> None:
-        """Drop the packed-weight cache (it is also invalidated automatically)."""
+        """Drop the packed-weight cache.  The cache follows the weight's storage pointer and version counter, so
+        ``load_state_dict``, optimizer steps and in-place tensor ops invalidate it automatically; writes made THROUGH
+        ``weight.data`` (``w.data.clamp_(-1, 1)``, ``w.data.copy_(...)``) do not bump the version counter -- call
+        ``repack()`` (or ``bnn_b200.invalidate(model)``) after such updates."""
         self._pack_key = self._packed = None
 
     # -- forward ------------------------------------------------------------------------------
@@ -159,7 +175,10 @@ class _BinaryLayer:
             low, reason = None, str(e)
         if low is not None:
             if self._wants_autograd(input):
-                reason = "training-mode autograd needs the float simulation"
+                # train() + autograd: the reference's own forward (bnn/layers/conv.py:90-97) with the straight-through
+                # estimator (bnn/ops.py:68-73), built from torch ops; the packed kernels are inference-only
+                _warn_training_floatsim()
+                return self._forward_floatsim(input)
             elif not input.is_cuda:
                 reason = f"input is on {input.device}; the B200 path has no CPU implementation"
             elif input.dtype != torch.float32:

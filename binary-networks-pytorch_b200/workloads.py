@@ -210,15 +210,20 @@ class HBlockNet(nn.Module):
     fp stem to 64 ch at /2, HBlock(64->256) with a BN-ReLU-1x1 shortcut, 2x2 avg-pool,
     4 x HBlock(256->256), global pool, fc."""
 
-    def __init__(self, num_classes: int = 1000, depth: int = 4):
+    def __init__(self, num_classes: int = 1000, depth: int = 4, hblock: Optional[Callable[..., nn.Module]] = None):
+        """``hblock(inplanes, planes, downsample)`` builds one block; the default is this module's ``HBlock``.  The
+        golden generator and bench.py's reference arm pass the reference's own class here
+        (``bnn.models.layers.HBlock(i, p, downsample=d, norm_layer=nn.BatchNorm2d)``): module names, construction
+        order and therefore seeded parameters are the same either way."""
         super().__init__()
+        hblock = hblock or (lambda i, p, d: HBlock(i, p, downsample=d))
         self.conv1 = nn.Conv2d(3, 64, kernel_size=7, stride=2, padding=3, bias=False)
         self.bn1 = nn.BatchNorm2d(64)
         self.relu = nn.ReLU(inplace=True)
         shortcut = nn.Sequential(nn.BatchNorm2d(64), nn.ReLU(inplace=True), _conv1x1(64, 256))
-        self.block0 = HBlock(64, 256, downsample=shortcut)
+        self.block0 = hblock(64, 256, shortcut)
         self.pool = nn.AvgPool2d(2)
-        self.blocks = nn.Sequential(*[HBlock(256, 256) for _ in range(depth)])
+        self.blocks = nn.Sequential(*[hblock(256, 256, None) for _ in range(depth)])
         self.avgpool = nn.AdaptiveAvgPool2d((1, 1))
         self.fc = nn.Linear(256, num_classes)
         _reference_init(self)

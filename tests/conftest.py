@@ -15,6 +15,21 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """A plain ``pytest`` on a CUDA-less host skips the GPU tests instead of failing at the first one.  An explicit
+    ``-m gpu`` run (the B200 box) never skips: there a missing device or library must be a loud failure."""
+    if "gpu" in (config.getoption("-m") or ""):
+        return
+    import torch
+    from bnn_b200 import native
+    if torch.cuda.is_available() and native.available():
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device and the built libbnn_b200.so")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def golden_layers():
     import numpy as np

@@ -21,12 +21,15 @@ def test_reference_arm_prints_the_contract_line():
     r = _run("--impl", "reference", "--steps", "1", "--warmup", "1", "--ref-batch", "2")
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["config"]["global_batch"] == 256 and "bs256/GPU" in line["config"]["workload"]
     assert line["impl"] == "reference" and line["unit"] == "images/s" and line["higher_is_better"] is True
     assert line["metric"].startswith("images/sec ResNet-18 XNOR fwd") and line["value"] > 0
     assert line["n_gpus"] == 1 and line["steps"] == 1 and line["vs_baseline"] is None and line["data"] == "synthetic"
     assert line["scaling"] == "weak" and line["dtype"] == "f32" and "workload" in line["config"]
     cb = line["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
+    from oracle import build as oracle_build
+    want_kind = "reference" if os.path.exists(os.path.join(oracle_build.REF_PKG, "__init__.pyc")) else "port"
+    assert cb["kind"] == want_kind and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
     assert line["e2e"] == {"value": line["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["gpu_launches"] == 0
 
@@ -62,7 +65,15 @@ def test_product_package_never_touches_the_oracle():
     # bench.py reaches the oracle only inside its CPU-baseline / reference-arm functions
     bench = open(os.path.join(ROOT, "bench.py")).read()
     uses = [m.start() for m in re.finditer(r"from oracle import", bench)]
-    assert uses, "bench.py's CPU legs are expected to use oracle.floatsim"
+    assert uses, "bench.py's CPU legs are expected to use oracle/"
     for pos in uses:
         func = re.findall(r"^def (\w+)\(", bench[:pos], flags=re.M)[-1]
-        assert func in ("cpu_floatsim_rate", "run_reference"), func
+        # the two builders of the CPU arm's model; their callers are the reference arm, cpu_baseline and the parity CHECK
+        assert func in ("build_reference_model", "cpu_twin"), func
+    callers = set()
+    for m in re.finditer(r"(?<!def )\b(cpu_twin|build_reference_model)\(", bench):
+        callers.add(re.findall(r"^def (\w+)\(", bench[:m.start()], flags=re.M)[-1])
+    assert callers <= {"build_reference_model", "cpu_twin", "cpu_floatsim_rate", "run_reference", "main"}, callers
+    # ... and in main() only inside the parity block, never inside what is timed
+    main_src = bench[bench.index("def main()"):]
+    assert main_src.count("cpu_twin(") == 1 and main_src.index("cpu_twin(") > main_src.index("parity of what was just timed")

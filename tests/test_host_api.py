@@ -112,12 +112,51 @@ def test_default_forward_never_falls_back_silently():
     x = torch.randn(1, 64, 8, 8)
     with torch.no_grad(), pytest.raises(NativeError, match="no CPU implementation"):
         layer(x)
-    layer.train()
-    with pytest.raises(NativeError, match="float simulation"):
-        layer(x)
-    with runtime.floatsim_enabled():
+    with runtime.floatsim_enabled(), torch.no_grad():
+        assert layer(x).shape == (1, 64, 8, 8)
+    assert runtime.floatsim() is False
+
+
+def test_training_mode_routes_to_the_float_simulation_with_one_warning():
+    """reference bnn/layers/conv.py:90-97 runs under autograd; a prepared bnn_b200 module in train() mode does the same
+    through the torch float simulation (STE backward, bnn/ops.py:68-73) and says so once."""
+    import warnings as w
+    from bnn_b200.layers import binary_modules
+    binary_modules._warned_training = False
+    layer = bnn.prepare_binary_model(nn.Conv2d(64, 64, 3, padding=1), CFG)          # default state: training
+    x = torch.randn(2, 64, 8, 8)
+    with pytest.warns(RuntimeWarning, match="fp32 simulation"):
         y = layer(x)
-    assert y.shape == (1, 64, 8, 8) and y.grad_fn is not None
+    assert y.grad_fn is not None
+    y.sum().backward()
+    assert layer.weight.grad is not None and torch.isfinite(layer.weight.grad).all()
+    with w.catch_warnings():
+        w.simplefilter("error")                        # second call: no warning any more
+        layer(x)
+    # same numbers as the explicit opt-in / the reference's forward
+    with runtime.floatsim_enabled(), torch.no_grad():
+        assert torch.equal(layer.eval()(x), y.detach())
+    # eval-mode CPU tensors still raise: no silent fallback outside training
+    with torch.no_grad(), pytest.raises(NativeError, match="no CPU implementation"):
+        layer(x)
+
+
+def test_runtime_switches_are_process_wide_with_thread_local_override():
+    import threading
+    seen = {}
+    runtime.floatsim(True)
+    try:
+        t = threading.Thread(target=lambda: seen.setdefault("worker", runtime.floatsim()))
+        t.start(); t.join()
+        assert seen["worker"] is True                  # nn.DataParallel replica threads see the main thread's opt-in
+        with runtime.floatsim_enabled(False):
+            assert runtime.floatsim() is False
+            t = threading.Thread(target=lambda: seen.setdefault("worker2", runtime.floatsim()))
+            t.start(); t.join()
+            assert seen["worker2"] is True             # the override is per thread
+        assert runtime.floatsim() is True
+    finally:
+        runtime.floatsim(False)
     assert runtime.floatsim() is False
 
 
