@@ -52,6 +52,8 @@ struct StemMmaArgs {
     float* out;               // [n,hp,wp,64]
     uint4* obits;             // [n][1][hp][wp]
     float x_scale, inv_scale; // 2^sx, 2^-(sx+sw)
+    const float* x_amax;      // device scalar max|x|: when given, sx is chosen in the kernel (max|x| * 2^sx in [2^14, 2^15))
+    int w_log2_scale;
     int N, H, W, Hc, Wc, Hp, Wp, tiles_h, tiles_w;
 };
 
@@ -97,6 +99,16 @@ stem_mma_kernel(const __grid_constant__ StemMmaArgs a) {
         mbar_expect_tx(bar, (unsigned)SM_W_BYTES);
         bulk_load_1d(const_cast<uint4*>(w_s), a.wfrag, (unsigned)SM_W_BYTES, bar);
     }
+    float x_scale = a.x_scale, inv_scale = a.inv_scale;
+    if (a.x_amax != nullptr) {
+        // guarded input range: the power-of-two scale follows the measured max|x| (bnn_amax_f32), so no input can
+        // leave the fp16 range whatever its magnitude
+        const int e = (int)((__float_as_uint(__ldg(a.x_amax)) >> 23) & 0xffu) - 126;
+        int sx = 15 - e;
+        sx = sx < -60 ? -60 : (sx > 60 ? 60 : sx);
+        x_scale = __int_as_float((127 + sx) << 23);
+        inv_scale = __int_as_float((127 - (sx + a.w_log2_scale)) << 23);
+    }
     // input window: fp32 -> scaled (hi, lo) fp16 pairs; zero fill = the convolution's padding.  Column 35 of a
     // row is the zero-weight eighth tap of the last pixel: it must be finite, so it is zero as well.
     {
@@ -123,7 +135,7 @@ stem_mma_kernel(const __grid_constant__ StemMmaArgs a) {
         for (int k = 0; k < ITERS; ++k) {
             const int i = threadIdx.x + k * SM_WARPS * 32;
             uint32_t h, l;
-            split2(v0[k] * a.x_scale, v1[k] * a.x_scale, h, l);
+            split2(v0[k] * x_scale, v1[k] * x_scale, h, l);
             if (k + 1 < ITERS || i < SM_IN_WORDS) { in_hi[i] = h; in_lo[i] = l; }
         }
     }
@@ -220,8 +232,8 @@ stem_mma_kernel(const __grid_constant__ StemMmaArgs a) {
                 // positions outside the conv output are max-pool padding: 0 is neutral after the ReLU
                 const bool ok = (unsigned)(cr0 + r) < (unsigned)a.Hc && (unsigned)(cc0 + c) < (unsigned)a.Wc && p < SM_NPIX;
                 float2 v;
-                v.x = ok ? fmaxf(__fmaf_rn(acc[mt][j][2 * hh] * a.inv_scale, gs.x, hs.x), 0.0f) : 0.0f;
-                v.y = ok ? fmaxf(__fmaf_rn(acc[mt][j][2 * hh + 1] * a.inv_scale, gs.y, hs.y), 0.0f) : 0.0f;
+                v.x = ok ? fmaxf(__fmaf_rn(acc[mt][j][2 * hh] * inv_scale, gs.x, hs.x), 0.0f) : 0.0f;
+                v.y = ok ? fmaxf(__fmaf_rn(acc[mt][j][2 * hh + 1] * inv_scale, gs.y, hs.y), 0.0f) : 0.0f;
                 *reinterpret_cast<float2*>(conv_s + p * SM_CPITCH + ch) = v;
             }
     }
@@ -300,7 +312,7 @@ extern "C" int bnn_stem_mma_pack_weight(const float* w, int32_t w_log2_scale, vo
 }
 
 extern "C" int bnn_stem_mma_fwd(const float* x, int32_t n, int32_t h, int32_t w, const void* w_frag,
-                                int32_t x_log2_scale, int32_t w_log2_scale, const float* bn_scale,
+                                int32_t x_log2_scale, const float* x_amax, int32_t w_log2_scale, const float* bn_scale,
                                 const float* bn_shift, const float* nx_scale, const float* nx_shift, float* out,
                                 void* out_bits, uint32_t flags, void* stream_) {
     if (!x || !w_frag || !bn_scale || !bn_shift || !out) return BNN_E_NULL;
@@ -315,6 +327,7 @@ extern "C" int bnn_stem_mma_fwd(const float* x, int32_t n, int32_t h, int32_t w,
     a.nx_scale = nx_scale; a.nx_shift = nx_shift; a.out = out; a.obits = (uint4*)out_bits;
     a.x_scale = ldexpf(1.0f, x_log2_scale);
     a.inv_scale = ldexpf(1.0f, -(x_log2_scale + w_log2_scale));
+    a.x_amax = x_amax; a.w_log2_scale = w_log2_scale;
     a.N = n; a.H = h; a.W = w;
     a.Hc = (h + 6 - 7) / 2 + 1; a.Wc = (w + 6 - 7) / 2 + 1;
     a.Hp = (a.Hc + 2 - 3) / 2 + 1; a.Wp = (a.Wc + 2 - 3) / 2 + 1;

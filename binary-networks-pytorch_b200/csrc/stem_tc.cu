@@ -1,0 +1,406 @@
+// stem_tc.cu -- the fp32 stem of bnn.models.resnet on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM):
+//     conv 7x7 / stride 2 / pad 3 (3 -> 64)  ->  eval BatchNorm  ->  ReLU  ->  MaxPool 3x3 / 2 / pad 1
+// (reference bnn/models/resnet.py:85-92,147-153).  Same contract and the same split-fp16 arithmetic as stem_mma.cu
+// (x*2^sx = xh + xl, w*2^sw = wh + wl, x*w ~= xh*wh + xh*wl + xl*wh: 22 significand bits per operand, products exact in
+// the fp32 accumulator), re-designed around what tcgen05 wants:
+//
+// * Implicit GEMM per CONV ROW: M = 128 consecutive conv columns of one conv row (lane m <-> column 2*pc0 - 1 + m, so a
+//   tile of up to 63 pooled columns has its 3-wide pooling windows inside one M tile), N = 64 channels, K = 192.
+// * No im2col tile is ever materialised.  The input is staged as 16-byte UNITS  U[ci][u] = {x[ci][y0+i][c0+2u+b]},
+//   i = 0..3 (four input rows of a "group"), b = 0,1 (a column pair): 8 fp16 values.  Conv column m needs, for its kernel
+//   columns (2p, 2p+1), p = 0..3, exactly unit m + p -- a Hankel matrix A[m][chunk j] = U[m + j].  The K-major no-swizzle
+//   shared-memory descriptor expresses that directly: rows of a core matrix 16 bytes apart (fixed by the layout),
+//   8-row groups 128 bytes apart (SBO), the second 16-byte K chunk 16 bytes further (LBO = 16: overlapping core
+//   matrices).  One MMA (K = 16) covers kernel rows 4g..4g+3 x kernel columns 4pp..4pp+3 of one input channel; a conv row
+//   is 2 groups x 3 channels x 2 column halves = 12 K steps (K = 192 for the 147 real taps: row 7 and column 7 are
+//   zero weights).  Conv row r uses groups r and r + 2 (group k = input rows 2k-3 .. 2k), so consecutive conv rows
+//   share three quarters of their operands: a group is converted once and read by two conv rows.
+// * Per K step two instructions: A_hi x [wh | wl] (N = 128: xh*wh into columns 0..63, xh*wl into 64..127) and
+//   A_lo x wh (N = 64, accumulating into columns 0..63); the epilogue adds the two column halves with a rounded fp32
+//   add.  14 KB of shared-memory operand reads per 96 tensor cycles.
+// * Warp-specialised persistent CTA, one per SM, walking a contiguous range of (image, pooled row):
+//     warps 0-3   convert fp32 input rows to (hi, lo) fp16 units into a 6-deep ring of groups (mbarrier full / empty)
+//     warp 12     one thread issues the MMAs of a conv row into one of 4 TMEM accumulator stages, tcgen05.commit
+//                 releases the stage to the epilogue and the oldest group back to the converters
+//     warps 4-11  tcgen05.ld the accumulators (warp % 4 = TMEM lane quarter, two channel halves), BatchNorm + ReLU, keep
+//                 the running vertical max of the 3 conv rows of a pooled row in REGISTERS (thread = conv column), park
+//                 it in shared memory once per pooled row, then take the horizontal 3-max with lanes <-> channels, store
+//                 NHWC lines and ballot the first binarized layer's planes.
+#include "tc05.cuh"
+
+#include <cuda_fp16.h>
+
+namespace bnn {
+
+constexpr int TC_NU = 132;                               // 16-byte units per (group, channel, hi/lo) row: m + p <= 130
+constexpr int TC_D = 6;                                  // groups in the ring
+constexpr int TC_SLOT = 3 * 2 * TC_NU * 16;              // 12672 bytes per group
+constexpr int TC_KSTEPS = 12;
+constexpr int TC_BSTEP = 4096;                           // [wh (64 rows) | wl (64 rows)] x 32 bytes per K step
+constexpr int TC_B_BYTES = TC_KSTEPS * TC_BSTEP;         // 49152
+constexpr int TC_VPITCH = 68;                            // floats per parked conv column (conflict-free STS.128)
+constexpr int TC_VBUF = 128 * TC_VPITCH * 4;             // 34816
+constexpr int TC_STAGES = 4;                             // TMEM accumulator stages of 128 columns
+constexpr int TC_CONV_WARPS = 4, TC_EPI_WARPS = 8;
+constexpr int TC_THREADS = (TC_CONV_WARPS + TC_EPI_WARPS + 1) * 32;      // 416
+constexpr int TC_OFF_CONST = 256, TC_OFF_B = 2048, TC_OFF_RING = TC_OFF_B + TC_B_BYTES;
+constexpr int TC_OFF_VBUF = TC_OFF_RING + TC_D * TC_SLOT;
+constexpr int TC_SMEM = TC_OFF_VBUF + 2 * TC_VBUF;                        // 196864
+constexpr int TC_MAX_PT = 63;                            // pooled columns per M tile: 2 * PT + 1 <= 127 conv columns
+
+struct StemTcArgs {
+    const float* x;           // [n,3,h,w] contiguous fp32
+    const void* wops;         // bnn_stem_tc_pack_weight output
+    const float *bn_scale, *bn_shift, *nx_scale, *nx_shift;
+    const float* x_amax;      // device scalar max|x| (NULL: x_log2_scale is used as given)
+    float* out;               // [n,hp,wp,64]
+    uint4* obits;             // [n][1][hp][wp]
+    int x_log2_scale, w_log2_scale;
+    int N, H, W, Hc, Wc, Hp, Wp, tiles_w, PT;
+    long long total_rows;     // N * tiles_w * Hp pooled rows, split evenly over the CTAs
+};
+
+struct Seg { int n, pc0, ph_a, r_first, nrows; };
+
+// next run of pooled rows of one (image, column tile) inside [pos, hi)
+__device__ __forceinline__ bool next_seg(long long& pos, long long hi, const StemTcArgs& a, Seg& s) {
+    if (pos >= hi) return false;
+    const long long img = pos / a.Hp;
+    const int ph_a = (int)(pos - img * a.Hp);
+    const long long end = (img + 1) * a.Hp < hi ? (img + 1) * a.Hp : hi;
+    const int ph_b = ph_a + (int)(end - pos);
+    s.n = (int)(img / a.tiles_w);
+    s.pc0 = (int)(img % a.tiles_w) * a.PT;
+    s.ph_a = ph_a;
+    s.r_first = 2 * ph_a - 1 > 0 ? 2 * ph_a - 1 : 0;
+    const int r_last = 2 * ph_b - 1 < a.Hc - 1 ? 2 * ph_b - 1 : a.Hc - 1;
+    s.nrows = r_last - s.r_first + 1;
+    pos = end;
+    return true;
+}
+
+__device__ __forceinline__ float pow2f(int e) { return __int_as_float((127 + e) << 23); }      // e in [-126, 127]
+
+// power-of-two input scale: the immediate, or from max|x| so that max|x| * 2^sx lies in [2^14, 2^15)
+__device__ __forceinline__ int input_log2_scale(const StemTcArgs& a) {
+    if (a.x_amax == nullptr) return a.x_log2_scale;
+    const int e = (int)((__float_as_uint(__ldg(a.x_amax)) >> 23) & 0xffu) - 126;       // amax = m * 2^e, m in [0.5, 1)
+    const int sx = 15 - e;
+    return sx < -60 ? -60 : (sx > 60 ? 60 : sx);
+}
+
+__device__ __forceinline__ void split8(const float (&v)[8], float xs, uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float a = v[2 * i] * xs, b = v[2 * i + 1] * xs;
+        const __half2 hh = __floats2half2_rn(a, b);
+        const float2 hf = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn(a - hf.x, b - hf.y);
+        h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+        l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) stem_tc_kernel(const __grid_constant__ StemTcArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);             // [TC_D]   converters -> MMA
+    uint64_t* empty = full + TC_D;                                  // [TC_D]   MMA (commit) -> converters
+    uint64_t* acc_full = empty + TC_D;                              // [TC_STAGES] MMA (commit) -> epilogue
+    uint64_t* acc_empty = acc_full + TC_STAGES;                     // [TC_STAGES] epilogue -> MMA
+    uint64_t* bbar = acc_empty + TC_STAGES;                         // weights landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bbar + 1);
+    float* consts = reinterpret_cast<float*>(smem + TC_OFF_CONST);  // [4][64]: bn_scale, bn_shift, nx_scale, nx_shift
+    unsigned char* b_s = smem + TC_OFF_B;
+    unsigned char* ring = smem + TC_OFF_RING;
+    float* vbuf = reinterpret_cast<float*>(smem + TC_OFF_VBUF);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long lo_row = a.total_rows * blockIdx.x / gridDim.x, hi_row = a.total_rows * (blockIdx.x + 1) / gridDim.x;
+
+    if (warp == TC_CONV_WARPS + TC_EPI_WARPS) {
+        if (lane == 0) {
+            for (int i = 0; i < TC_D; ++i) { mbar_init(full + i, TC_CONV_WARPS); mbar_init(empty + i, 1); }
+            for (int i = 0; i < TC_STAGES; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, TC_EPI_WARPS); }
+            mbar_init(bbar, 1);
+            fence_mbar_init();
+            mbar_expect_tx(bbar, (unsigned)TC_B_BYTES);
+            bulk_load_1d(b_s, a.wops, (unsigned)TC_B_BYTES, bbar);
+        }
+        __syncwarp();
+        tc05::tmem_alloc<512>(tmem_slot);
+    }
+    for (int i = tid; i < 256; i += TC_THREADS) {
+        const int which = i >> 6, c = i & 63;
+        const float* src = which == 0 ? a.bn_scale : which == 1 ? a.bn_shift : which == 2 ? a.nx_scale : a.nx_shift;
+        consts[i] = src ? __ldg(src + c) : (which == 2 ? 1.0f : 0.0f);
+    }
+    tc05::fence_before_sync();
+    __syncthreads();
+    tc05::fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const int sx = input_log2_scale(a);
+
+    if (warp < TC_CONV_WARPS) {
+        // =================== converters: fp32 input rows -> (hi, lo) fp16 units of a group ===================
+        const float xs = pow2f(sx);
+        long long pos = lo_row, K = 0;
+        Seg s;
+        while (next_seg(pos, hi_row, a, s)) {
+            const float* xn = a.x + (size_t)s.n * 3 * a.H * a.W;
+            const int ngroups = s.nrows + 2;
+            for (int k = 0; k < ngroups; ++k, ++K) {
+                const int slot = (int)(K % TC_D);
+                const long long use = K / TC_D;
+                if (use > 0) mbar_wait(empty + slot, (uint32_t)((use - 1) & 1));
+                unsigned char* sb = ring + (size_t)slot * TC_SLOT;
+                const int y0 = 2 * (s.r_first + k) - 3;
+                for (int u = tid; u < TC_NU; u += TC_CONV_WARPS * 32) {
+                    const int c0 = 4 * s.pc0 - 5 + 2 * u;
+                    const bool ok0 = (unsigned)c0 < (unsigned)a.W, ok1 = (unsigned)(c0 + 1) < (unsigned)a.W;
+                    float v[3][8];
+#pragma unroll
+                    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int y = y0 + i;
+                            const bool rok = (unsigned)y < (unsigned)a.H;
+                            const float* p = xn + ((size_t)ci * a.H + (rok ? y : 0)) * a.W + c0;
+                            v[ci][2 * i] = (rok && ok0) ? __ldg(p) : 0.0f;
+                            v[ci][2 * i + 1] = (rok && ok1) ? __ldg(p + 1) : 0.0f;
+                        }
+#pragma unroll
+                    for (int ci = 0; ci < 3; ++ci) {
+                        uint4 hi, lo;
+                        split8(v[ci], xs, hi, lo);
+                        *reinterpret_cast<uint4*>(sb + ((size_t)(ci * 2 + 0) * TC_NU + u) * 16) = hi;
+                        *reinterpret_cast<uint4*>(sb + ((size_t)(ci * 2 + 1) * TC_NU + u) * 16) = lo;
+                    }
+                }
+                fence_proxy_async();                  // generic-proxy stores -> visible to the tensor core's async proxy
+                __syncwarp();
+                if (lane == 0) tc05::mbar_arrive(full + slot);
+            }
+        }
+    } else if (warp == TC_CONV_WARPS + TC_EPI_WARPS) {
+        // =================== MMA issuer ===================
+        mbar_wait(bbar, 0);
+        const uint32_t idesc128 = tc05::idesc_f16_f32(128, 128), idesc64 = tc05::idesc_f16_f32(128, 64);
+        const uint32_t ring_u = smem_u32(ring), b_u = smem_u32(b_s);
+        long long pos = lo_row, K = 0, J = 0;
+        Seg s;
+        while (next_seg(pos, hi_row, a, s)) {
+            for (int j = 0; j < s.nrows; ++j, ++J) {
+                const int stage = (int)(J % TC_STAGES);
+                const long long ause = J / TC_STAGES;
+                if (ause > 0) mbar_wait(acc_empty + stage, (uint32_t)((ause - 1) & 1));
+                const long long k0 = K + j, k2 = K + j + 2;
+                const int s0 = (int)(k0 % TC_D), s2 = (int)(k2 % TC_D);
+                mbar_wait(full + s0, (uint32_t)((k0 / TC_D) & 1));
+                mbar_wait(full + s2, (uint32_t)((k2 / TC_D) & 1));
+                tc05::fence_after_sync();
+                if (lane == 0) {
+                    const uint32_t d = tmem + (uint32_t)stage * 128u;
+#pragma unroll
+                    for (int ks = 0; ks < TC_KSTEPS; ++ks) {
+                        const int grp = ks / 6, ci = (ks >> 1) % 3, pp = ks & 1;
+                        const uint32_t abase = ring_u + (uint32_t)(grp ? s2 : s0) * TC_SLOT + 32u * pp;
+                        const uint64_t a_hi = tc05::smem_desc(abase + (uint32_t)(ci * 2 + 0) * TC_NU * 16, 16, 128);
+                        const uint64_t a_lo = tc05::smem_desc(abase + (uint32_t)(ci * 2 + 1) * TC_NU * 16, 16, 128);
+                        const uint64_t bd = tc05::smem_desc(b_u + (uint32_t)ks * TC_BSTEP, 128, 256);
+                        tc05::mma_f16_ss(d, a_hi, bd, idesc128, ks > 0);       // xh*wh -> cols 0..63, xh*wl -> cols 64..127
+                        tc05::mma_f16_ss(d, a_lo, bd, idesc64, 1);             // xl*wh -> cols 0..63
+                    }
+                    tc05::commit(acc_full + stage);
+                    tc05::commit(empty + s0);                                  // group j is not needed any more
+                    if (j == s.nrows - 1) {
+                        tc05::commit(empty + (int)((K + s.nrows) % TC_D));
+                        tc05::commit(empty + (int)((K + s.nrows + 1) % TC_D));
+                    }
+                }
+                __syncwarp();
+            }
+            K += s.nrows + 2;
+        }
+    } else {
+        // =================== epilogue: TMEM -> BN + ReLU -> vertical max (registers) -> horizontal max -> NHWC + planes
+        const int e = warp - TC_CONV_WARPS;            // 0..7
+        const int lq = warp & 3;                       // TMEM lane quarter this warp may read
+        const int cb = 32 * (e >> 2);                  // channel half
+        const int m = 32 * lq + lane;                  // conv column inside the M tile
+        const float inv_scale = pow2f(-(sx + a.w_log2_scale));
+        const bool has_nx = a.nx_scale != nullptr;
+        long long pos = lo_row, J = 0;
+        int emits = 0;
+        Seg s;
+        while (next_seg(pos, hi_row, a, s)) {
+            const int c = 2 * s.pc0 - 1 + m;
+            const bool col_ok = (unsigned)c < (unsigned)a.Wc;
+            float state[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) state[i] = 0.0f;
+            for (int j = 0; j < s.nrows; ++j, ++J) {
+                const int r = s.r_first + j;
+                const int stage = (int)(J % TC_STAGES);
+                mbar_wait(acc_full + stage, (uint32_t)((J / TC_STAGES) & 1));
+                tc05::fence_after_sync();
+                const uint32_t taddr = tmem + ((uint32_t)(32 * lq) << 16) + (uint32_t)(stage * 128 + cb);
+                float cur[32];
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    float p[16], q[16];
+                    tc05::tmem_ld16x2_sync(taddr + 16 * hh, taddr + 64 + 16 * hh, p, q);
+#pragma unroll
+                    for (int i4 = 0; i4 < 16; i4 += 4) {
+                        const float4 g = *reinterpret_cast<const float4*>(consts + cb + 16 * hh + i4);
+                        const float4 h = *reinterpret_cast<const float4*>(consts + 64 + cb + 16 * hh + i4);
+                        const float gg[4] = {g.x, g.y, g.z, g.w}, hv[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float conv = __fadd_rn(p[i4 + i], q[i4 + i]) * inv_scale;
+                            const float v = fmaxf(__fmaf_rn(conv, gg[i], hv[i]), 0.0f);
+                            cur[16 * hh + i4 + i] = col_ok ? v : 0.0f;       // outside the conv output: max-pool padding
+                        }
+                    }
+                }
+                tc05::fence_before_sync();
+                __syncwarp();
+                if (lane == 0) tc05::mbar_arrive(acc_empty + stage);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) state[i] = fmaxf(state[i], cur[i]);
+                const int ph = (r & 1) ? (r - 1) >> 1 : r >> 1;
+                const bool emit = ((r & 1) || r == a.Hc - 1) && ph >= s.ph_a;
+                if (emit) {
+                    float* vb = vbuf + (size_t)(emits & 1) * (TC_VBUF / 4);
+                    ++emits;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4)
+                        *reinterpret_cast<float4*>(vb + m * TC_VPITCH + cb + i) = make_float4(state[i], state[i + 1], state[i + 2], state[i + 3]);
+                    asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");
+                    // horizontal 3-max, lanes <-> channels: whole 128-byte lines in and out
+                    const size_t prow = ((size_t)s.n * a.Hp + ph) * a.Wp;
+                    for (int jp = e; jp < a.PT; jp += TC_EPI_WARPS) {
+                        const int pc = s.pc0 + jp;
+                        if (pc >= a.Wp) break;
+                        const float* v0 = vb + (2 * jp) * TC_VPITCH + lane;
+                        uint32_t sw[2], mw[2];
+#pragma unroll
+                        for (int hb = 0; hb < 2; ++hb) {
+                            const float mx = fmaxf(fmaxf(v0[32 * hb], v0[TC_VPITCH + 32 * hb]), v0[2 * TC_VPITCH + 32 * hb]);
+                            a.out[(prow + pc) * 64 + 32 * hb + lane] = mx;
+                            const float b = has_nx ? __fmaf_rn(consts[128 + 32 * hb + lane], mx, consts[192 + 32 * hb + lane]) : mx;
+                            sw[hb] = __ballot_sync(0xffffffffu, b > 0.0f);
+                            mw[hb] = __ballot_sync(0xffffffffu, b > 0.0f || b < 0.0f);
+                        }
+                        if (lane == 0 && a.obits) a.obits[prow + pc] = make_uint4(sw[0], sw[1], mw[0], mw[1]);
+                    }
+                    if (r & 1) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) state[i] = cur[i];      // an odd conv row also opens the next pooled row
+                    }
+                }
+            }
+        }
+    }
+    tc05::fence_before_sync();
+    __syncthreads();
+    if (warp == TC_CONV_WARPS + TC_EPI_WARPS) tc05::tmem_dealloc<512>(tmem);
+}
+
+// conv weight [64,3,7,7] fp32 -> the B operand image: 12 K steps x [wh | wl] rows x 16 K elements, K-major no-swizzle core
+// matrices (8 rows x 16 bytes, the two K chunks 128 bytes apart, 8-row groups 256 bytes apart).
+// K step ks = (grp * 3 + ci) * 2 + pp; K element jj * 8 + i * 2 + b  <->  w[n][ci][kh = 4 grp + i][kw = 4 pp + 2 jj + b].
+__global__ void stem_tc_pack_weight_kernel(const float* __restrict__ w, float w_scale, __half* __restrict__ ops) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;       // one fp16 element of the image
+    if (idx >= TC_B_BYTES / 2) return;
+    const int ks = idx / (TC_BSTEP / 2), rem = idx % (TC_BSTEP / 2);
+    const int n8 = rem / 128, jj = (rem % 128) / 64, nr = (rem % 64) / 8, el = rem % 8;
+    const int n = n8 * 8 + nr;                                   // 0..63: wh rows, 64..127: wl rows
+    const int grp = ks / 6, ci = (ks >> 1) % 3, pp = ks & 1;
+    const int kh = 4 * grp + (el >> 1), kw = 4 * pp + 2 * jj + (el & 1);
+    float v = 0.0f;
+    if (kh < 7 && kw < 7) v = w[(((n & 63) * 3 + ci) * 7 + kh) * 7 + kw] * w_scale;
+    const __half hi = __float2half_rn(v);
+    ops[idx] = n < 64 ? hi : __float2half_rn(v - __half2float(hi));
+}
+
+// max |x| over a tensor (NaN ignored), atomically merged into *amax (which the caller zeroes first)
+__global__ void amax_kernel(const float* __restrict__ x, long long count, float* __restrict__ amax) {
+    float m = 0.0f;
+    const long long n4 = count >> 2;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(x4 + i);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+    for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
+        m = fmaxf(m, fabsf(__ldg(x + i)));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(reinterpret_cast<unsigned int*>(amax), __float_as_uint(m));
+}
+
+}  // namespace bnn
+
+using namespace bnn;
+
+extern "C" size_t bnn_stem_tc_weight_bytes(void) { return TC_B_BYTES; }
+
+extern "C" int bnn_stem_tc_pack_weight(const float* w, int32_t w_log2_scale, void* w_ops, void* stream_) {
+    if (!w || !w_ops) return BNN_E_NULL;
+    if (w_log2_scale < -60 || w_log2_scale > 60) return BNN_E_SHAPE;
+    if ((uintptr_t)w_ops & 15) return BNN_E_ALIGN;
+    const int total = TC_B_BYTES / 2;
+    stem_tc_pack_weight_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(w, ldexpf(1.0f, w_log2_scale), (__half*)w_ops);
+    count_launch(1);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int bnn_amax_f32(const float* x, int64_t count, float* amax, void* stream_) {
+    if (!x || !amax) return BNN_E_NULL;
+    if (count <= 0) return BNN_E_SHAPE;
+    if ((uintptr_t)x & 15) return BNN_E_ALIGN;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    cudaError_t ce = cudaMemsetAsync(amax, 0, sizeof(float), stream);
+    if (ce != cudaSuccess) return (int)ce;
+    const long long want = (count / 4 + 255) / 256;
+    const int blocks = (int)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
+    amax_kernel<<<blocks, 256, 0, stream>>>(x, (long long)count, amax);
+    count_launch(1);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int bnn_stem_tc_fwd(const float* x, int32_t n, int32_t h, int32_t w, const void* w_ops, int32_t x_log2_scale,
+                               const float* x_amax, int32_t w_log2_scale, const float* bn_scale, const float* bn_shift,
+                               const float* nx_scale, const float* nx_shift, float* out, void* out_bits, uint32_t flags,
+                               void* stream_) {
+    (void)flags;
+    if (!x || !w_ops || !bn_scale || !bn_shift || !out) return BNN_E_NULL;
+    if ((nx_scale == nullptr) != (nx_shift == nullptr)) return BNN_E_NULL;
+    if (n <= 0 || h < 7 || w < 7) return BNN_E_SHAPE;
+    if ((long long)h * w * 3 >= 0x7fffffffLL) return BNN_E_UNSUPPORTED;
+    if (x_log2_scale < -60 || x_log2_scale > 60 || w_log2_scale < -60 || w_log2_scale > 60) return BNN_E_SHAPE;
+    if (((uintptr_t)w_ops & 15) || ((uintptr_t)out_bits & 15)) return BNN_E_ALIGN;
+    StemTcArgs a{};
+    a.x = x; a.wops = w_ops; a.bn_scale = bn_scale; a.bn_shift = bn_shift; a.nx_scale = nx_scale; a.nx_shift = nx_shift;
+    a.x_amax = x_amax; a.out = out; a.obits = (uint4*)out_bits;
+    a.x_log2_scale = x_log2_scale; a.w_log2_scale = w_log2_scale;
+    a.N = n; a.H = h; a.W = w;
+    a.Hc = (h + 6 - 7) / 2 + 1; a.Wc = (w + 6 - 7) / 2 + 1;
+    a.Hp = (a.Hc + 2 - 3) / 2 + 1; a.Wp = (a.Wc + 2 - 3) / 2 + 1;
+    a.tiles_w = (a.Wp + TC_MAX_PT - 1) / TC_MAX_PT;
+    a.PT = (a.Wp + a.tiles_w - 1) / a.tiles_w;
+    a.total_rows = (long long)n * a.tiles_w * a.Hp;
+    int dev = 0, sms = 148;
+    cudaError_t ce = cudaGetDevice(&dev);
+    if (ce != cudaSuccess) return (int)ce;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    ce = cudaFuncSetAttribute((const void*)stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM);
+    if (ce != cudaSuccess) return (int)ce;
+    const long long ctas = a.total_rows < sms ? a.total_rows : sms;
+    stem_tc_kernel<<<(unsigned)ctas, TC_THREADS, TC_SMEM, (cudaStream_t)stream_>>>(a);
+    count_launch(1);
+    return (int)cudaGetLastError();
+}

@@ -329,29 +329,80 @@ def stem_mma_weights(w: torch.Tensor):
     return frag, log2_scale
 
 
-def stem_mma(x: torch.Tensor, wfrag, bn: Tuple[torch.Tensor, torch.Tensor], nx=None, want_bits: bool = True,
-             x_log2_scale: int = STEM_X_LOG2_SCALE, flags: int = 0):
-    """``stem`` on the mma.sync path (split-fp16 operands, fp32-level accuracy; see include/bnn_b200.h).
-    ``wfrag`` = ``stem_mma_weights(conv.weight)``.  Same outputs as ``stem``."""
+def amax(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """max|x| of a contiguous fp32 tensor as a device scalar (``bnn_amax_f32``; no host synchronisation, capturable):
+    the input-range guard of the split-fp16 stem kernels."""
+    _require_cuda_f32(x, "input")
+    if not x.is_contiguous():
+        raise native.NativeError("amax expects a contiguous tensor")
+    dev = x.device
+    with torch.cuda.device(dev):
+        if out is None:
+            out = torch.empty((1,), dtype=torch.float32, device=dev)
+        rc = native.lib().bnn_amax_f32(x.data_ptr(), x.numel(), out.data_ptr(), _stream_ptr(dev))
+    native.check(rc, "bnn_amax_f32")
+    return out
+
+
+def _stem_split(kernel: str, x: torch.Tensor, wops, bn, nx, want_bits, x_log2_scale, guard, flags):
     _require_cuda_f32(x, "input")
     if x.dim() != 4 or x.shape[1] != 3 or not x.is_contiguous():
         raise native.NativeError(f"stem expects a contiguous [n,3,h,w] tensor, got {tuple(x.shape)}")
-    frag, w_log2_scale = wfrag
+    buf, w_log2_scale = wops
     n, _, h, w = x.shape
     hp, wp = ctypes.c_int32(0), ctypes.c_int32(0)
     native.check(native.lib().bnn_stem_out_hw(h, w, ctypes.byref(hp), ctypes.byref(wp)), "bnn_stem_out_hw")
     hp, wp = hp.value, wp.value
     dev = x.device
     with torch.cuda.device(dev):
+        x_amax = None
+        if guard is True:
+            x_amax = amax(x)
+        elif isinstance(guard, torch.Tensor):
+            x_amax = guard
         out = torch.empty((n, 64, hp, wp), dtype=torch.float32, device=dev, memory_format=torch.channels_last)
         bits = torch.empty((n, 1, hp, wp, 4), dtype=torch.int32, device=dev) if want_bits else None
-        rc = native.lib().bnn_stem_mma_fwd(x.data_ptr(), n, h, w, frag.data_ptr(), x_log2_scale, w_log2_scale,
-                                           bn[0].data_ptr(), bn[1].data_ptr(),
-                                           None if nx is None else nx[0].data_ptr(),
-                                           None if nx is None else nx[1].data_ptr(), out.data_ptr(),
-                                           None if bits is None else bits.data_ptr(), flags, _stream_ptr(dev))
-    native.check(rc, "bnn_stem_mma_fwd")
+        fn = native.lib().bnn_stem_mma_fwd if kernel == "mma" else native.lib().bnn_stem_tc_fwd
+        rc = fn(x.data_ptr(), n, h, w, buf.data_ptr(), x_log2_scale, None if x_amax is None else x_amax.data_ptr(),
+                w_log2_scale, bn[0].data_ptr(), bn[1].data_ptr(), None if nx is None else nx[0].data_ptr(),
+                None if nx is None else nx[1].data_ptr(), out.data_ptr(), None if bits is None else bits.data_ptr(),
+                flags, _stream_ptr(dev))
+    native.check(rc, f"bnn_stem_{kernel}_fwd")
     return out, (None if bits is None else PackedActivations(bits, n, 64, hp, wp))
+
+
+def stem_mma(x: torch.Tensor, wfrag, bn: Tuple[torch.Tensor, torch.Tensor], nx=None, want_bits: bool = True,
+             x_log2_scale: int = STEM_X_LOG2_SCALE, flags: int = 0, guard=False):
+    """``stem`` on the mma.sync path (split-fp16 operands, fp32-level accuracy; see include/bnn_b200.h).
+    ``wfrag`` = ``stem_mma_weights(conv.weight)``.  Same outputs as ``stem``.  ``guard=True`` measures max|x| on the
+    device first (``amax``) and lets the kernel choose the input scale, so no input magnitude can overflow fp16;
+    ``guard=False`` uses ``x_log2_scale`` as given (|x| * 2^x_log2_scale < 65504 is then the caller's promise)."""
+    return _stem_split("mma", x, wfrag, bn, nx, want_bits, x_log2_scale, guard, flags)
+
+
+def stem_tc_weights(w: torch.Tensor):
+    """[64,3,7,7] fp32 conv weight -> (B-operand image, w_log2_scale) for ``stem_tc`` (bnn_stem_tc_pack_weight)."""
+    _require_cuda_f32(w, "stem weight")
+    if tuple(w.shape) != (64, 3, 7, 7):
+        raise native.NativeError(f"stem weight must be [64,3,7,7], got {tuple(w.shape)}")
+    w = w.detach().contiguous()
+    wmax = float(w.abs().max())
+    if not math.isfinite(wmax):
+        raise native.NativeError("stem weight has non-finite values")
+    log2_scale = 0 if wmax == 0.0 else max(-60, min(60, 13 - math.frexp(wmax)[1]))
+    dev = w.device
+    with torch.cuda.device(dev):
+        ops = torch.empty(native.lib().bnn_stem_tc_weight_bytes() // 4, dtype=torch.int32, device=dev)
+        rc = native.lib().bnn_stem_tc_pack_weight(w.data_ptr(), log2_scale, ops.data_ptr(), _stream_ptr(dev))
+    native.check(rc, "bnn_stem_tc_pack_weight")
+    return ops, log2_scale
+
+
+def stem_tc(x: torch.Tensor, wops, bn: Tuple[torch.Tensor, torch.Tensor], nx=None, want_bits: bool = True,
+            x_log2_scale: int = STEM_X_LOG2_SCALE, flags: int = 0, guard=False):
+    """``stem`` on the tcgen05 tensor cores (``bnn_stem_tc_fwd``, csrc/stem_tc.cu): split-fp16 operands, accumulators in
+    tensor memory.  ``wops`` = ``stem_tc_weights(conv.weight)``; ``guard`` as in ``stem_mma``.  Same outputs as ``stem``."""
+    return _stem_split("tc", x, wops, bn, nx, want_bits, x_log2_scale, guard, flags)
 
 
 def ubench(which: int, iters: int = 200) -> float:

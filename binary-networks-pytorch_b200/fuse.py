@@ -23,6 +23,7 @@ max-pool, reference resnet.py:85-92) is one kernel too (``bnn_stem_mma_fwd`` by 
 ``stem="fma"``) when it has the reference's shape;
 global pooling and the classifier stay torch ops.
 """
+import math
 from typing import List, Optional, Tuple
 
 import torch
@@ -189,18 +190,34 @@ class _StemPlan:
             self.mma_key = key
         return self.mma_w
 
+    def tc_weight(self):
+        """(B-operand image, log2 scale) for the tcgen05 stem kernel, cached per weight version."""
+        w = self.conv.weight
+        key = (w.data_ptr(), w._version)
+        if key != self.tc_key:
+            self.tc_w = BF.stem_tc_weights(w)
+            self.tc_key = key
+        return self.tc_w
+
 
 class FusedResNet(nn.Module):
     """Inference engine over a prepared ResNet; same call signature as the wrapped model."""
 
-    def __init__(self, model: nn.Module, fuse_stem: bool = True, stem: str = "auto") -> None:
+    def __init__(self, model: nn.Module, fuse_stem: bool = True, stem: str = "auto", input_range: float = None) -> None:
         super().__init__()
         self.stem_kernel_used = "torch"
         if stem not in ("auto", "tc", "mma", "fma"):
             raise ValueError("stem must be 'auto', 'tc' (tcgen05, split fp16), 'mma' (mma.sync, split fp16) or 'fma' "
                              f"(fp32 fma chain), got {stem!r}")
         self.model = model
-        self.stem_kernel = "mma" if stem == "auto" else stem
+        self.stem_kernel = "tc" if stem == "auto" else stem
+        # split-fp16 stems: None = guarded (max|x| is measured on the device every forward, any magnitude is safe);
+        # a number = the caller's bound on |x| (e.g. 3.0 for normalised images): fixed scale, no measuring pass
+        if input_range is not None and not (input_range > 0 and math.isfinite(input_range)):
+            raise ValueError(f"input_range must be a positive finite bound on |x|, got {input_range!r}")
+        self.input_range = input_range
+        self._x_log2_scale = (BF.STEM_X_LOG2_SCALE if input_range is None
+                              else max(-60, min(60, 15 - math.frexp(float(input_range))[1])))
         blocks: List[nn.Module] = []
         for name in ("layer1", "layer2", "layer3", "layer4"):
             blocks += list(getattr(model, name))
@@ -294,9 +311,14 @@ class FusedResNet(nn.Module):
                     and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == 3 and min(x.shape[2:]) >= 7):
                 # fp32 stem in one kernel: NHWC residual stream + the first binarized conv's planes
                 self.stem_kernel_used = {"mma": "bnn_stem_mma_fwd", "fma": "bnn_stem_fwd", "tc": "bnn_stem_tc_fwd"}[self.stem_kernel]
-                if self.stem_kernel == "mma":
+                if self.stem_kernel == "tc":
+                    x, bits = BF.stem_tc(x.contiguous(), self.stem.tc_weight(), self.stem.bn.get(),
+                                         nx=self._entry_affine(first), guard=self.input_range is None,
+                                         x_log2_scale=self._x_log2_scale)
+                elif self.stem_kernel == "mma":
                     x, bits = BF.stem_mma(x.contiguous(), self.stem.mma_weight(), self.stem.bn.get(),
-                                          nx=self._entry_affine(first))
+                                          nx=self._entry_affine(first), guard=self.input_range is None,
+                                          x_log2_scale=self._x_log2_scale)
                 else:
                     x, bits = BF.stem(x.contiguous(), self.stem.weight(), self.stem.bn.get(),
                                       nx=self._entry_affine(first), flags=runtime.kernel_flags())
@@ -402,13 +424,16 @@ class FusedHBlockNet(nn.Module):
             return m.fc(torch.flatten(m.avgpool(x), 1))
 
 
-def optimize(model: nn.Module, fuse_stem: bool = True, stem: str = "auto") -> nn.Module:
+def optimize(model: nn.Module, fuse_stem: bool = True, stem: str = "auto", input_range: float = None) -> nn.Module:
     """Return the fused inference engine for ``model`` if its layout is recognised, else ``model``.
-    ``stem``: "mma" = the stem kernel on mma.sync with split-fp16 operands (fp32-level accuracy, default),
-    "fma" = the fp32 fma-chain stem kernel (bit-identical to the oracle's summation order)."""
+    ``stem``: "tc" (= "auto") the stem kernel on the tcgen05 tensor cores, "mma" the same arithmetic on mma.sync (both:
+    split-fp16 operands, fp32-level accuracy), "fma" the fp32 fma-chain stem kernel (bit-identical to the oracle's
+    summation order).  ``input_range``: a bound on |x| the caller guarantees (e.g. 3.0 for normalised images) -- the
+    split-fp16 stems then use a fixed input scale; by default (None) they measure max|x| on the device every forward
+    (one extra pass over the input, graph-capturable), so inputs of any magnitude are handled."""
     needed = ("conv1", "layer1", "layer2", "layer3", "layer4", "avgpool", "fc")
     if all(hasattr(model, k) for k in needed):
-        engine = FusedResNet(model, fuse_stem=fuse_stem, stem=stem)
+        engine = FusedResNet(model, fuse_stem=fuse_stem, stem=stem, input_range=input_range)
         if engine.fused_blocks:
             return engine
     if all(hasattr(model, k) for k in ("conv1", "bn1", "relu", "block0", "pool", "blocks", "avgpool", "fc")):

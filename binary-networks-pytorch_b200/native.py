@@ -58,8 +58,13 @@ _SIGNATURES = {
                              c_void_p, c_void_p, c_uint32, c_void_p]),
     "bnn_stem_mma_weight_bytes": (c_size_t, []),
     "bnn_stem_mma_pack_weight": (c_int, [c_void_p, c_int32, c_void_p, c_void_p]),
-    "bnn_stem_mma_fwd": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_void_p,
-                                 c_void_p, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p]),
+    "bnn_stem_mma_fwd": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p]),
+    "bnn_amax_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "bnn_stem_tc_weight_bytes": (c_size_t, []),
+    "bnn_stem_tc_pack_weight": (c_int, [c_void_p, c_int32, c_void_p, c_void_p]),
+    "bnn_stem_tc_fwd": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p]),
     "bnn_shortcut_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                                  c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_uint32,
                                  c_void_p]),

@@ -242,9 +242,33 @@ int bnn_stem_fwd(const float *x, int32_t n, int32_t h, int32_t w, const float *w
 size_t bnn_stem_mma_weight_bytes(void);
 int bnn_stem_mma_pack_weight(const float *w, int32_t w_log2_scale, void *w_frag, void *stream);
 int bnn_stem_mma_fwd(const float *x, int32_t n, int32_t h, int32_t w, const void *w_frag,
-                     int32_t x_log2_scale, int32_t w_log2_scale, const float *bn_scale, const float *bn_shift,
-                     const float *nx_scale, const float *nx_shift, float *out, void *out_bits, uint32_t flags,
-                     void *stream);
+                     int32_t x_log2_scale, const float *x_amax, int32_t w_log2_scale, const float *bn_scale,
+                     const float *bn_shift, const float *nx_scale, const float *nx_shift, float *out, void *out_bits,
+                     uint32_t flags, void *stream);
+
+/*
+ * Guarded input range for the split-fp16 stems: x_amax (device scalar, may be NULL) holds max|x| of the batch, written by
+ * bnn_amax_f32 on the same stream (one extra pass over the input, ~25 us for 154 MB).  When it is given the kernels pick
+ * the power-of-two input scale themselves (max|x| * 2^sx in [2^14, 2^15)), so no finite input can overflow fp16 and
+ * x_log2_scale is ignored; with x_amax == NULL the caller guarantees |x| * 2^x_log2_scale < 65504.
+ * bnn_amax_f32: x 16-byte aligned, `count` elements; *amax = max |x[i]| (NaN ignored); no host synchronisation.
+ */
+int bnn_amax_f32(const float *x, int64_t count, float *amax, void *stream);
+
+/*
+ * The same stem on the 5th-generation tensor cores (tcgen05.mma, accumulators in tensor memory; csrc/stem_tc.cu): same
+ * contract, same split-fp16 arithmetic and accuracy class as bnn_stem_mma_fwd, NOT bit-identical to it (the tensor core
+ * sums the 147 taps of an output in one accumulator chain).  Implicit GEMM per conv row, the im2col view expressed by
+ * the shared-memory matrix descriptor itself (no A tile is materialised), persistent warp-specialised CTAs.
+ * w_ops: bnn_stem_tc_weight_bytes() bytes, 16-byte aligned, written by bnn_stem_tc_pack_weight from the plain
+ * [64,3,7,7] fp32 conv weight.  x_amax as above.
+ */
+size_t bnn_stem_tc_weight_bytes(void);
+int bnn_stem_tc_pack_weight(const float *w, int32_t w_log2_scale, void *w_ops, void *stream);
+int bnn_stem_tc_fwd(const float *x, int32_t n, int32_t h, int32_t w, const void *w_ops, int32_t x_log2_scale,
+                    const float *x_amax, int32_t w_log2_scale, const float *bn_scale, const float *bn_shift,
+                    const float *nx_scale, const float *nx_shift, float *out, void *out_bits, uint32_t flags,
+                    void *stream);
 
 /*
  * The down-sampling shortcut of bnn.models.resnet (bnn/models/resnet.py:129-133) as one kernel:

@@ -55,8 +55,26 @@ def test_size_helpers_and_errors_without_gpu():
     assert lib.bnn_stem_mma_weight_bytes() == 11 * 8 * 32 * 16
     assert lib.bnn_stem_mma_pack_weight(None, 0, None, None) == -1
     assert lib.bnn_stem_mma_pack_weight(one, 99, one, None) == -2
-    assert lib.bnn_stem_mma_fwd(None, 1, 8, 8, None, 7, 0, None, None, None, None, None, None, 0, None) == -1
-    assert lib.bnn_stem_mma_fwd(one, 1, 5, 5, one, 7, 0, one, one, None, None, one, None, 0, None) == -2                    # smaller than the kernel
+    assert lib.bnn_stem_mma_fwd(None, 1, 8, 8, None, 7, None, 0, None, None, None, None, None, None, 0, None) == -1
+    assert lib.bnn_stem_mma_fwd(one, 1, 5, 5, one, 7, None, 0, one, one, None, None, one, None, 0, None) == -2              # smaller than the kernel
+    # ABI v4: tcgen05 stem, input-range guard, planner hooks
+    assert lib.bnn_stem_tc_weight_bytes() == 12 * 4096
+    assert lib.bnn_stem_tc_pack_weight(None, 0, None, None) == -1
+    assert lib.bnn_stem_tc_pack_weight(one, 99, one, None) == -2
+    assert lib.bnn_stem_tc_fwd(None, 1, 8, 8, None, 7, None, 0, None, None, None, None, None, None, 0, None) == -1
+    assert lib.bnn_stem_tc_fwd(one, 1, 5, 5, one, 7, None, 0, one, one, None, None, one, None, 0, None) == -2
+    assert lib.bnn_stem_tc_fwd(one, 1, 8, 8, one, 7, None, 0, one, one, one, None, one, None, 0, None) == -1               # nx_scale without nx_shift
+    assert lib.bnn_amax_f32(None, 4, None, None) == -1
+    assert lib.bnn_amax_f32(one, 0, one, None) == -2
+    assert lib.bnn_amax_f32(ctypes.c_void_p(4), 4, one, None) == -5
+    n = ctypes.c_int32(0)
+    g3 = native.ConvGeom(2, 64, 8, 56, 128, 3, 3, 1, 1, 1, 1, 1, 1)
+    assert lib.bnn_conv_plan_list(ctypes.byref(g3), 0, None, 0, ctypes.byref(n)) == 0 and n.value > 10
+    assert lib.bnn_conv_plan_list(None, 0, None, 0, ctypes.byref(n)) == -1
+    ep = native.Epilogue()
+    assert lib.bnn_bconv2d_fused_fwd_plan(one, one, ctypes.byref(g3), ctypes.byref(ep), 0, 5, 3, 0, 0, None) == -3       # no such family
+    inst = (ctypes.c_int32 * 6)()
+    assert lib.bnn_conv_instance(ctypes.byref(g3), ctypes.byref(ep), 0, 8, 2, 0, 0, inst) == 0 and list(inst) == [8, 2, 3, 1, 1, 0]
     assert lib.bnn_stem_fwd(None, 1, 8, 8, None, None, None, None, None, None, None, 0, None) == -1
     hp, wp = ctypes.c_int32(0), ctypes.c_int32(0)
     assert lib.bnn_stem_out_hw(224, 224, ctypes.byref(hp), ctypes.byref(wp)) == 0 and (hp.value, wp.value) == (56, 56)
@@ -72,5 +90,6 @@ def test_sass_contains_tma_and_popc():
         pytest.skip("no cuobjdump")
     sass = subprocess.run([cuobjdump, "-sass", native.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in sass
-    for mnemonic in ("UTMALDG", "UBLKCP", "POPC", "LOP3", "HMMA.16816.F32", "FFMA2"):     # + the two stem kernels
+    for mnemonic in ("UTMALDG", "UBLKCP", "POPC", "LOP3", "HMMA.16816.F32", "FFMA2",      # + the mma.sync / fma stems
+                     "UTCHMMA", "LDTM", "UTCBAR"):                                        # tcgen05 stem: MMA, TMEM load, commit
         assert mnemonic in sass, mnemonic

@@ -160,13 +160,21 @@ def _stem_f64(x, w, g, h):
     return torch.nn.functional.max_pool2d(y, 3, 2, 1).permute(0, 2, 3, 1).numpy()
 
 
-@pytest.mark.parametrize("hw,xscale", [((64, 64), 1.0), ((224, 224), 1.0), ((37, 52), 1.0), ((30, 30), 1.0),
-                                       ((64, 64), 100.0), ((64, 64), 1e-3)])
-def test_stem_mma_kernel_fp32_accuracy(hw, xscale):
-    """The mma.sync stem (split-fp16 operands) is as accurate as the fp32 fma-chain stem against a float64
-    convolution, and its planes are exactly the planes of the fp32 tensor it returns."""
+STEM_KERNELS = {"mma": (BF.stem_mma_weights, BF.stem_mma), "tc": (BF.stem_tc_weights, BF.stem_tc)}
+
+
+@pytest.mark.parametrize("kernel", ["mma", "tc"])
+@pytest.mark.parametrize("hw,xscale,guard", [((64, 64), 1.0, False), ((224, 224), 1.0, False), ((37, 52), 1.0, False),
+                                             ((30, 30), 1.0, True), ((64, 64), 100.0, False), ((64, 64), 1e-3, False),
+                                             ((64, 64), 1e-3, True), ((64, 64), 3e4, True), ((500, 300), 1.0, True),
+                                             ((7, 7), 1.0, True), ((9, 260), 1.0, False)])
+def test_stem_mma_kernel_fp32_accuracy(hw, xscale, guard, kernel):
+    """The split-fp16 stems (mma.sync and tcgen05) are as accurate as the fp32 fma-chain stem against a float64
+    convolution, and their planes are exactly the planes of the fp32 tensor they return.  ``guard``: the input scale
+    follows max|x| measured on the device (bnn_amax_f32) -- 3e4-sized inputs would overflow the fixed 2^7 scale."""
     rng = np.random.default_rng(6)
-    x = (rng.standard_normal((2, 3) + hw) * xscale).astype(np.float32)
+    n = 2 if hw != (500, 300) else 1
+    x = (rng.standard_normal((n, 3) + hw) * xscale).astype(np.float32)
     w = (rng.standard_normal((64, 3, 7, 7)) * 0.1).astype(np.float32)
     g, h = ((0.5 + rng.random(64)) / xscale).astype(np.float32), (rng.standard_normal(64) * 0.3).astype(np.float32)
     nx = ((0.5 + rng.random(64)).astype(np.float32), (rng.standard_normal(64) * 0.2).astype(np.float32))
@@ -174,29 +182,59 @@ def test_stem_mma_kernel_fp32_accuracy(hw, xscale):
     scale = np.abs(exact).max()
     fma, _ = BF.stem(_d(x), BF.stem_weight_layout(_d(w)), (_d(g), _d(h)))
     err_fma = np.abs(fma.permute(0, 2, 3, 1).cpu().numpy() - exact).max() / scale
-    wfrag = BF.stem_mma_weights(_d(w))
+    pack, run = STEM_KERNELS[kernel]
+    wops = pack(_d(w))
     for nxa in (None, nx):
-        out, bits = BF.stem_mma(_d(x), wfrag, (_d(g), _d(h)), nx=None if nxa is None else (_d(nxa[0]), _d(nxa[1])))
-        assert out.shape == (2, 64) + exact.shape[1:3] and out.is_contiguous(memory_format=torch.channels_last)
+        out, bits = run(_d(x), wops, (_d(g), _d(h)), nx=None if nxa is None else (_d(nxa[0]), _d(nxa[1])), guard=guard)
+        assert out.shape == (n, 64) + exact.shape[1:3] and out.is_contiguous(memory_format=torch.channels_last)
         got = out.permute(0, 2, 3, 1).cpu().numpy()
-        err_mma = np.abs(got - exact).max() / scale
-        print(f"stem {hw} x{xscale}: max err / max|y| vs float64: mma {err_mma:.2e}  fma chain {err_fma:.2e}")
-        assert err_mma <= max(3.0 * err_fma, 3e-7)
+        err = np.abs(got - exact).max() / scale
+        print(f"stem {kernel} {hw} x{xscale} guard={guard}: max err / max|y| vs float64: {err:.2e}  fma chain {err_fma:.2e}")
+        assert err <= max(3.0 * err_fma, 3e-7)
         nchw = np.ascontiguousarray(got.transpose(0, 3, 1, 2))
         want_bits = co.pack_act(nchw) if nxa is None else co.pack_act(nchw, pre_scale=nxa[0], pre_shift=nxa[1])
         assert np.array_equal(bits.bits.cpu().numpy().view(np.uint32), want_bits)
 
 
-def test_stem_mma_rejects_bad_arguments():
+def test_stem_tc_matches_mma_stem_on_a_full_batch():
+    """bs 32 at 224x224: every CTA of the persistent tcgen05 kernel walks several images (segment boundaries, the ring and
+    the TMEM stages wrap many times); results must agree with the mma.sync stem to accumulation-order rounding."""
+    torch.manual_seed(5)
+    x = torch.randn(32, 3, 224, 224, device=DEV)
     w = torch.randn(64, 3, 7, 7, device=DEV) * 0.1
-    wfrag = BF.stem_mma_weights(w)
+    g, h = 0.5 + torch.rand(64, device=DEV), torch.randn(64, device=DEV) * 0.3
+    a, abits = BF.stem_mma(x, BF.stem_mma_weights(w), (g, h))
+    b, bbits = BF.stem_tc(x, BF.stem_tc_weights(w), (g, h), guard=True)
+    err = float((a - b).abs().max() / a.abs().max())
+    assert err <= 2e-6, err
+    differ = int((abits.bits != bbits.bits).sum())
+    assert differ <= abits.bits.numel() * 1e-4, differ      # planes may differ only where |value| ~ rounding noise
+    # bit-identical run to run (no atomics, fixed work split)
+    b2, _ = BF.stem_tc(x, BF.stem_tc_weights(w), (g, h), guard=True)
+    assert torch.equal(b, b2)
+
+
+def test_amax_kernel():
+    torch.manual_seed(1)
+    for shape in [(1, 3, 7, 7), (3, 3, 37, 52), (4, 3, 224, 224)]:
+        x = torch.randn(shape, device=DEV)
+        x.view(-1)[5] = float("nan")
+        x.view(-1)[11] = -123.5
+        assert float(BF.amax(x)) == 123.5
+
+
+@pytest.mark.parametrize("kernel", ["mma", "tc"])
+def test_stem_mma_rejects_bad_arguments(kernel):
+    pack, run = STEM_KERNELS[kernel]
+    w = torch.randn(64, 3, 7, 7, device=DEV) * 0.1
+    wfrag = pack(w)
     g, h = torch.ones(64, device=DEV), torch.zeros(64, device=DEV)
     with pytest.raises(native.NativeError):
-        BF.stem_mma(torch.randn(1, 3, 5, 5, device=DEV), wfrag, (g, h))            # smaller than the kernel
+        run(torch.randn(1, 3, 5, 5, device=DEV), wfrag, (g, h))            # smaller than the kernel
     with pytest.raises(native.NativeError):
-        BF.stem_mma(torch.randn(1, 4, 32, 32, device=DEV), wfrag, (g, h))          # not 3 channels
+        run(torch.randn(1, 4, 32, 32, device=DEV), wfrag, (g, h))          # not 3 channels
     with pytest.raises(native.NativeError):
-        BF.stem_mma_weights(torch.randn(32, 3, 7, 7, device=DEV))
+        pack(torch.randn(32, 3, 7, 7, device=DEV))
 
 
 @pytest.fixture(autouse=True)
@@ -220,13 +258,21 @@ def test_fused_engine_matches_reference_and_unfused(variant, golden_models):
         before = native.launch_count()
         fused = engine(x).cpu().numpy()
     launches = native.launch_count() - before
-    assert launches == 1 + 16 + 3                  # stem + 2 per block + one kernel per down-sampling shortcut
+    assert launches == 2 + 16 + 3                  # amax + stem + 2 per block + one kernel per down-sampling shortcut
+    assert engine.stem_kernel_used == "bnn_stem_tc_fwd"
     with torch.no_grad():
         no_stem = fuse.optimize(m, fuse_stem=False)(x).cpu().numpy()
         fma_stem = fuse.optimize(m, stem="fma")(x).cpu().numpy()
-    print(variant, "stem kernel (mma) vs torch stem", rel_err(fused, no_stem), "fma-chain stem kernel vs torch stem",
-          rel_err(fma_stem, no_stem))
-    assert rel_err(fused, no_stem) <= 1e-3 and rel_err(fma_stem, no_stem) <= 1e-3
+        mma_stem = fuse.optimize(m, stem="mma")(x).cpu().numpy()
+        ranged = fuse.optimize(m, input_range=8.0)
+        ranged(x)
+        before = native.launch_count()
+        ranged_out = ranged(x).cpu().numpy()
+        assert native.launch_count() - before == 1 + 16 + 3       # a caller-supplied bound: no measuring pass
+    print(variant, "stem kernel (tcgen05) vs torch stem", rel_err(fused, no_stem), "fma-chain stem kernel vs torch stem",
+          rel_err(fma_stem, no_stem), "mma.sync stem", rel_err(mma_stem, no_stem))
+    assert rel_err(fused, no_stem) <= 1e-3 and rel_err(fma_stem, no_stem) <= 1e-3 and rel_err(mma_stem, no_stem) <= 1e-3
+    assert rel_err(ranged_out, no_stem) <= 1e-3
     ref = golden_models[variant + "_logits"]
     print(variant, "fused vs reference", rel_err(fused, ref), "fused vs unfused", rel_err(fused, eager))
     assert rel_err(fused, ref) <= 1e-3
