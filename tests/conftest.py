@@ -48,6 +48,31 @@ def golden_models():
     return np.load(os.path.join(GOLDEN, "models.npz"))
 
 
+@pytest.fixture(scope="session")
+def golden_cfg34():
+    import numpy as np
+    return np.load(os.path.join(GOLDEN, "models_cfg34.npz"))
+
+
+def build_config34(which):
+    """BASELINE configs[2] / configs[3] prepared with bnn_b200, seeded exactly like tests/golden/make_golden.py builds them
+    on the real reference; returns (prepared eval model on CPU, input [2,3,res,res])."""
+    import torch
+    import bnn_b200 as bnn
+    from bnn_b200 import workloads
+    from bnn_b200.ops import BasicInputBinarizer, BasicScaleBinarizer, XNORWeightBinarizer
+    torch.manual_seed(0)
+    if which == "resnet50":
+        m, post, res = workloads.resnet50(), BasicScaleBinarizer, 96
+    else:
+        m, post, res = workloads.HBlockNet(), bnn.Identity, 64
+    cfg = bnn.BConfig(BasicInputBinarizer, post, XNORWeightBinarizer.with_args(compute_alpha=True, center_weights=True))
+    m = bnn.prepare_binary_model(m, cfg, ignore_layers_name=["_first_", "_last_"])
+    workloads.randomize_batchnorm(m, seed=1)
+    x = torch.randn(2, 3, res, res, generator=torch.Generator().manual_seed(0))
+    return m.eval(), x
+
+
 def rel_err(a, b):
     import numpy as np
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)

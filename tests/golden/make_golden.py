@@ -7,6 +7,8 @@ Outputs (small .npz files next to this script):
   layers.npz            reference CPU-fp32 outputs for every case of tests/cases.py
   models.npz            logits of reference ResNet-18 models (64x64 inputs, randomised BN) + a
                         parameter checksum so the seeded re-construction can be verified
+  models_cfg34.npz      the same for BASELINE configs[2] (ResNet-50 XNOR-Net++, 96x96) and configs[3] (the
+                        Hierarchical-Block harness around the reference's HBlock, 64x64)
 Nothing here is imported at test time; tests only read the .npz files.
 """
 import importlib
@@ -109,7 +111,34 @@ def model_logits(variant):
     return m(x).numpy(), param_checksum(m), m.double()(x.double()).numpy()
 
 
+def config34_logits(which):
+    """BASELINE configs[2] / configs[3] on the REAL reference: ResNet-50 XNOR-Net++ (fc patched to 2048 inputs, learned
+    per-channel post scale randomised) and the Hierarchical-Block harness built around the reference's own HBlock."""
+    torch.manual_seed(0)
+    if which == "resnet50":
+        m = ref_resnet.resnet50()
+        m.fc = nn.Linear(2048, 1000)                       # upstream wires fc to 512 features (resnet.py:101,143)
+        post, res = ref_ops.BasicScaleBinarizer, 96
+    else:
+        m = workloads.HBlockNet(hblock=lambda i, p, d: ref_blocks.HBlock(i, p, downsample=d, norm_layer=nn.BatchNorm2d))
+        post, res = bnn_ref.Identity, 64
+    cfg = bnn_ref.BConfig(activation_pre_process=ref_ops.BasicInputBinarizer, activation_post_process=post,
+                          weight_pre_process=ref_ops.XNORWeightBinarizer.with_args(compute_alpha=True, center_weights=True))
+    m = bnn_ref.prepare_binary_model(m, cfg, ignore_layers_name=["_first_", "_last_"])
+    workloads.randomize_batchnorm(m, seed=1)
+    m.eval()
+    x = torch.randn(2, 3, res, res, generator=torch.Generator().manual_seed(0))
+    return m(x).numpy(), param_checksum(m), m.double()(x.double()).numpy()
+
+
 def main():
+    cfg34 = {}
+    for which in ("resnet50", "hblock"):
+        logits, chk, logits64 = config34_logits(which)
+        cfg34[which + "_logits"], cfg34[which + "_checksum"] = logits, chk
+        cfg34[which + "_logits_fp64"] = logits64.astype(np.float64)
+        print(which, logits.shape, "fp32 vs fp64 of the reference itself:", np.abs(logits - logits64).max() / np.abs(logits64).max())
+    np.savez_compressed(os.path.join(HERE, "models_cfg34.npz"), **cfg34)
     np.savez_compressed(os.path.join(HERE, "ref_unit_vectors.npz"), **unit_vectors())
     layers = {}
     for case in cases.CASES:

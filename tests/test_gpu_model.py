@@ -156,3 +156,22 @@ def test_baseline_config4_hierarchical_block_net():
         want = twin(x).numpy()
         got = m.to(DEV)(x.to(DEV)).cpu().numpy()
     assert rel_err(got, want) <= 1e-3, rel_err(got, want)
+
+
+@pytest.mark.parametrize("which", ["resnet50", "hblock"])
+def test_config34_logits_match_the_real_reference(which, golden_cfg34):
+    """BASELINE configs[2] / [3] against logits of the REAL reference (tests/golden/models_cfg34.npz, generated by
+    tests/golden/make_golden.py from /root/reference): per-layer path and fused engine, tolerance 1e-3 (north_star)."""
+    from conftest import build_config34
+    from bnn_b200 import fuse
+    m, x = build_config34(which)
+    ref = golden_cfg34[which + "_logits"]
+    m = m.to(DEV)
+    with torch.no_grad():
+        per_layer = m(x.to(DEV)).cpu().numpy()
+        engine = fuse.optimize(m)
+        assert engine is not m
+        fused = engine(x.to(DEV)).cpu().numpy()
+    print(which, "per-layer vs reference", rel_err(per_layer, ref), "fused vs reference", rel_err(fused, ref))
+    assert rel_err(per_layer, ref) <= 1e-3 and rel_err(fused, ref) <= 1e-3
+    assert (np.argmax(per_layer, 1) == np.argmax(ref, 1)).all() and (np.argmax(fused, 1) == np.argmax(ref, 1)).all()

@@ -173,6 +173,24 @@ def test_whole_model_twin_matches_reference_logits(golden_models):
     torch.set_grad_enabled(True)
 
 
+@pytest.mark.parametrize("which,nconv", [("resnet50", 52), ("hblock", 16)])
+def test_config34_twin_matches_reference_logits(which, nconv, golden_cfg34):
+    """BASELINE configs[2] / [3]: the seeded workload definitions reproduce the real reference's parameters (checksum)
+    and the oracle's float-simulated twin reproduces the real reference's logits (tests/golden/models_cfg34.npz)."""
+    from conftest import build_config34
+    import bnn_b200 as bnn
+    torch.set_grad_enabled(False)
+    try:
+        m, x = build_config34(which)
+        assert sum(isinstance(mod, bnn.layers.Conv2d) for mod in m.modules()) == nconv
+        chk = np.array([float(p.double().abs().sum()) for p in m.state_dict().values() if p.dtype.is_floating_point])
+        assert np.allclose(chk, golden_cfg34[which + "_checksum"], rtol=1e-12)
+        y = fs.mirror_model(m)(x).numpy()
+        assert rel_err(y, golden_cfg34[which + "_logits"]) <= 1e-6
+    finally:
+        torch.set_grad_enabled(True)
+
+
 # ----------------------------------------------------------------------------------------------
 # cross-module fusion epilogue (struct bnn_epilogue) and the pooled / affine bit-pack
 # ----------------------------------------------------------------------------------------------
