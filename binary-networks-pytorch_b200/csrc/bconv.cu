@@ -193,8 +193,11 @@ static int make_plan(const bnn_conv_geom& g, int Ho, int Wo, uint32_t flags, int
     return 0;
 }
 
+// a launch over a chunk range of a wider layer (split-K): strides of the full packed tensors
+struct Slice { int nch_total, nk_total; };
+
 static int launch_bconv(const void* abits, const void* wbits, const bnn_conv_geom& g, const bnn_epilogue& ep,
-                        uint32_t flags, cudaStream_t stream, const Plan* forced = nullptr) {
+                        uint32_t flags, cudaStream_t stream, const Plan* forced = nullptr, const Slice* slice = nullptr) {
     if (!abits || !wbits || (!ep.out && !ep.out_bits)) return BNN_E_NULL;
     if (g.n <= 0 || g.c_in <= 0 || g.h <= 0 || g.w <= 0 || g.c_out <= 0 || g.kh <= 0 || g.kw <= 0 ||
         g.stride_h <= 0 || g.stride_w <= 0 || g.pad_h < 0 || g.pad_w < 0 || g.dil_h <= 0 || g.dil_w <= 0)
@@ -256,6 +259,8 @@ static int launch_bconv(const void* abits, const void* wbits, const bnn_conv_geo
     a.act_bytes = (unsigned)((size_t)a.nch * pl.BH * pl.BW * 16);
     a.w_bytes = (unsigned)((size_t)a.nk * 256);
     a.stage_ldg = (flags & BNN_F_STAGE_LDG) ? 1 : 0;
+    a.nch_total = slice ? slice->nch_total : a.nch;
+    a.w_blk_stride = (unsigned)((slice ? slice->nk_total : a.nk) * 32);
 
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
@@ -265,7 +270,7 @@ static int launch_bconv(const void* abits, const void* wbits, const bnn_conv_geo
         // abits as a 5-D u32 tensor, fastest first: {4 words, W, H, chunks, N}
         const cuuint64_t gdim[5] = {4, (cuuint64_t)g.w, (cuuint64_t)g.h, (cuuint64_t)a.nch, (cuuint64_t)g.n};
         const cuuint64_t gstr[4] = {16, (cuuint64_t)g.w * 16, (cuuint64_t)g.w * g.h * 16,
-                                    (cuuint64_t)g.w * g.h * a.nch * 16};
+                                    (cuuint64_t)g.w * g.h * a.nch_total * 16};
         const cuuint32_t box[5] = {4, (cuuint32_t)pl.BW, (cuuint32_t)pl.BH, (cuuint32_t)a.nch, 1};
         const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
         CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 5, const_cast<void*>(abits), gdim, gstr, box, estr,
@@ -393,6 +398,96 @@ extern "C" int bnn_bconv2d_fused_fwd_plan(const void* abits, const void* wbits, 
     int rc = find_plan(*geom, flags, P, C, TH, warps, &pl);
     if (rc) return rc;
     return launch_bconv(abits, wbits, *geom, *epilogue, flags, (cudaStream_t)stream, &pl);
+}
+
+// ---------------------------------------------------------------------------
+// split-K: layers whose full reduction does not fit one CTA's shared memory (Linear(25088, 4096), > 16384 input
+// channels) are contracted chunk range by chunk range; every launch writes exact integer dots (as fp32) of its range
+// and bnn_dot_finish_f32 sums them and applies the reference epilogue.  The same finish kernel averages the two
+// launches of a TERNARY weight tensor (exact-zero weights, sign(0) = 0): zeros packed once as +1 and once as -1.
+// ---------------------------------------------------------------------------
+static bool plans_exist(const bnn_conv_geom& g, uint32_t flags) {
+    const int Ho = out_dim(g.h, g.kh, g.stride_h, g.pad_h, g.dil_h);
+    const int Wo = out_dim(g.w, g.kw, g.stride_w, g.pad_w, g.dil_w);
+    std::vector<Cand> cands;
+    return Ho > 0 && Wo > 0 && enumerate_plans(g, Ho, Wo, flags, 148, cands) == 0;
+}
+
+extern "C" int bnn_conv_split(const bnn_conv_geom* g, uint32_t flags, int32_t* chunks_per_part, int32_t* nparts) {
+    if (!g || !chunks_per_part || !nparts) return BNN_E_NULL;
+    if (g->c_in <= 0 || g->kh <= 0 || g->kw <= 0) return BNN_E_SHAPE;
+    const int nch = ceil_div(g->c_in, 64);
+    if (plans_exist(*g, flags)) { *chunks_per_part = nch; *nparts = 1; return 0; }
+    // largest chunk range that has a plan (feasibility is monotone in the number of chunks: smaller tiles always fit)
+    int lo = 0, hi = nch;                      // lo: feasible (0 = none found yet), hi: infeasible
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) / 2;
+        bnn_conv_geom sub = *g;
+        sub.c_in = mid * 64;
+        if (plans_exist(sub, flags)) lo = mid; else hi = mid;
+    }
+    if (lo == 0) return BNN_E_UNSUPPORTED;
+    const int parts = ceil_div(nch, lo);
+    *chunks_per_part = ceil_div(nch, parts);   // balanced ranges
+    *nparts = ceil_div(nch, *chunks_per_part);
+    return 0;
+}
+
+extern "C" int bnn_bconv2d_partial_fwd(const void* abits, const void* wbits, const bnn_conv_geom* geom, int32_t chunk0,
+                                       int32_t nchunks, float* part, uint32_t flags, void* stream) {
+    if (!geom || !part) return BNN_E_NULL;
+    const bnn_conv_geom& g = *geom;
+    if (g.c_in <= 0 || g.h <= 0 || g.w <= 0 || g.kh <= 0 || g.kw <= 0) return BNN_E_SHAPE;
+    const int nch_total = ceil_div(g.c_in, 64);
+    if (chunk0 < 0 || nchunks <= 0 || chunk0 + nchunks > nch_total) return BNN_E_SHAPE;
+    const int Ho = out_dim(g.h, g.kh, g.stride_h, g.pad_h, g.dil_h);
+    const int Wo = out_dim(g.w, g.kw, g.stride_w, g.pad_w, g.dil_w);
+    if (Ho <= 0 || Wo <= 0) return BNN_E_SHAPE;
+    bnn_conv_geom sub = g;
+    sub.c_in = std::min(g.c_in - chunk0 * 64, nchunks * 64);
+    const Slice sl{nch_total, nch_total * g.kh * g.kw};
+    bnn_epilogue ep{};
+    ep.out = part;
+    ep.ostride_n = (int64_t)g.c_out * Ho * Wo; ep.ostride_c = (int64_t)Ho * Wo; ep.ostride_h = Wo; ep.ostride_w = 1;
+    const unsigned char* a0 = abits ? (const unsigned char*)abits + (size_t)chunk0 * g.h * g.w * 16 : nullptr;
+    const unsigned char* w0 = wbits ? (const unsigned char*)wbits + (size_t)chunk0 * g.kh * g.kw * 256 : nullptr;
+    return launch_bconv(a0, w0, sub, ep, flags, (cudaStream_t)stream, nullptr, &sl);
+}
+
+namespace bnn {
+__global__ void __launch_bounds__(256)
+dot_finish_kernel(const float* __restrict__ parts, int nparts, long long count, float inv_div, const float* __restrict__ scale,
+                  const float* __restrict__ bias, const float* __restrict__ post, float* __restrict__ out,
+                  long long on, long long oc, long long oh, long long ow, int C, int H, int W) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    float dot = 0.0f;
+    for (int r = 0; r < nparts; ++r) dot = __fadd_rn(dot, parts[(long long)r * count + i]);      // exact: small integers
+    dot = __fmul_rn(dot, inv_div);                                                              // exact: even sums, 1 or 1/2
+    const int w = (int)(i % W);
+    long long t = i / W;
+    const int h = (int)(t % H);
+    t /= H;
+    const int c = (int)(t % C);
+    const long long n = t / C;
+    const float k0 = scale ? __ldg(scale + c) : 1.0f, k1 = bias ? __ldg(bias + c) : 0.0f, k2 = post ? __ldg(post + c) : 1.0f;
+    // reference order (conv.py:92-97, ops.py:136,202): (alpha*dot + bias) * alpha_post, three rounded operations
+    out[n * on + c * oc + h * oh + w * ow] = __fmul_rn(__fadd_rn(__fmul_rn(k0, dot), k1), k2);
+}
+}  // namespace bnn
+
+extern "C" int bnn_dot_finish_f32(const float* parts, int32_t nparts, int32_t divisor, const float* scale, const float* bias,
+                                  const float* post, float* out, int64_t on, int64_t oc, int64_t oh, int64_t ow, int32_t n,
+                                  int32_t c_out, int32_t ho, int32_t wo, void* stream) {
+    if (!parts || !out) return BNN_E_NULL;
+    if (nparts <= 0 || (divisor != 1 && divisor != 2) || n <= 0 || c_out <= 0 || ho <= 0 || wo <= 0) return BNN_E_SHAPE;
+    const long long count = (long long)n * c_out * ho * wo;
+    const long long blocks = (count + 255) / 256;
+    if (blocks > 0x7fffffffLL) return BNN_E_UNSUPPORTED;
+    dot_finish_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(parts, nparts, count, 1.0f / (float)divisor, scale, bias,
+                                                                         post, out, on, oc, oh, ow, c_out, ho, wo);
+    count_launch(1);
+    return (int)cudaGetLastError();
 }
 
 extern "C" int bnn_conv_plan_list(const bnn_conv_geom* g, uint32_t flags, int32_t* plans, int32_t cap, int32_t* count) {

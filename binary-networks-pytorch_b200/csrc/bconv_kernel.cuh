@@ -48,6 +48,9 @@ struct ConvArgs {
     int tiles_h, tiles_w;
     unsigned act_bytes, w_bytes;  // bytes per staged activation box / per 32-channel weight block
     int stage_ldg;
+    // split-K launches contract a chunk range of a wider layer: the packed tensors keep the FULL layer's strides
+    int nch_total;                // chunks per image of the abits tensor (>= nch)
+    unsigned w_blk_stride;        // uint2 elements between consecutive 32-channel weight blocks (nk_total * 32 >= nk * 32)
 };
 
 // per-CTA table of per-channel epilogue constants in shared memory: [EP_N][32*C]
@@ -106,7 +109,7 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
             mbar_expect_tx(bar, a.act_bytes + (unsigned)nvalid * a.w_bytes);
             tma_load_5d(act, &tmap, bar, 0, wi0, hi0, 0, n);
             for (int j = 0; j < nvalid; ++j)
-                bulk_load_1d(wsm + (size_t)j * nk32, a.wbits + (size_t)(blk0 + j) * nk32, a.w_bytes, bar);
+                bulk_load_1d(wsm + (size_t)j * nk32, a.wbits + (size_t)(blk0 + j) * a.w_blk_stride, a.w_bytes, bar);
         }
     } else {
         const int units = a.nch * a.BH * a.BW;
@@ -117,12 +120,12 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
             const int hi = hi0 + rr, wi = wi0 + c;
             uint4 v = make_uint4(0u, 0u, 0u, 0u);
             if ((unsigned)hi < (unsigned)a.H && (unsigned)wi < (unsigned)a.W)
-                v = a.abits[(((size_t)n * a.nch + ch) * a.H + hi) * a.W + wi];
+                v = a.abits[(((size_t)n * a.nch_total + ch) * a.H + hi) * a.W + wi];
             act[i] = v;
         }
         for (int j = 0; j < C; ++j) {
             if (blk0 + j >= a.nblk32) break;
-            const uint2* src = a.wbits + (size_t)(blk0 + j) * nk32;
+            const uint2* src = a.wbits + (size_t)(blk0 + j) * a.w_blk_stride;
             for (int i = threadIdx.x; i < nk32; i += blockDim.x) wsm[(size_t)j * nk32 + i] = src[i];
         }
     }

@@ -212,7 +212,7 @@ __device__ __forceinline__ double block_sum(double v, double* scratch) {
 
 __global__ void __launch_bounds__(128)
 pack_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, int nch,
-                   int center, int compute_alpha, uint32_t* __restrict__ wbits,
+                   int center, int compute_alpha, uint32_t* __restrict__ wbits, uint32_t* __restrict__ wzero,
                    float* __restrict__ alpha, int* __restrict__ n_zero) {
     extern __shared__ double sm_d[];
     double* scratch = sm_d;                                 // [4]
@@ -250,7 +250,7 @@ pack_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, int
     for (int item = threadIdx.x; item < nk * 2; item += blockDim.x) {
         const int ks = item >> 1, word = item & 1;
         const int ch = ks / taps, t = ks - ch * taps;
-        uint32_t bits = 0u;
+        uint32_t bits = 0u, zbits = 0u;
         for (int b = 0; b < 32; ++b) {
             const int ci = ch * 64 + word * 32 + b;
             if (ci >= Cin) break;
@@ -258,9 +258,12 @@ pack_weight_kernel(const float* __restrict__ w, int Cout, int Cin, int taps, int
             const float v = center ? raw - mean[t] : raw;
             const bool pos = v > 0.0f, neg = v < 0.0f;
             bits |= (uint32_t)pos << b;
+            zbits |= (uint32_t)(!pos && !neg) << b;
             zeros += (!pos && !neg);
         }
-        wbits[((((long long)(co >> 5) * nk + ks) * 32) + (co & 31)) * 2 + word] = bits;
+        const long long widx = ((((long long)(co >> 5) * nk + ks) * 32) + (co & 31)) * 2 + word;
+        wbits[widx] = bits;
+        if (wzero != nullptr) wzero[widx] = zbits;       // plane of exactly-zero (centred) weights: sign 0 in the reference
     }
     if (n_zero != nullptr) {
         for (int o = 16; o > 0; o >>= 1) zeros += __shfl_down_sync(0xffffffffu, zeros, o);
@@ -344,6 +347,12 @@ extern "C" int bnn_avgpool_pack_f32(const float* x, int64_t sn, int64_t sc, int6
 extern "C" int bnn_pack_weight_f32(const float* w, int32_t c_out, int32_t c_in, int32_t kh, int32_t kw,
                                    int32_t center, int32_t compute_alpha, void* wbits, float* alpha,
                                    int32_t* n_zero, void* stream_) {
+    return bnn_pack_weight_ternary_f32(w, c_out, c_in, kh, kw, center, compute_alpha, wbits, nullptr, alpha, n_zero, stream_);
+}
+
+extern "C" int bnn_pack_weight_ternary_f32(const float* w, int32_t c_out, int32_t c_in, int32_t kh, int32_t kw,
+                                           int32_t center, int32_t compute_alpha, void* wbits, void* wzero, float* alpha,
+                                           int32_t* n_zero, void* stream_) {
     if (!w || !wbits || !alpha) return BNN_E_NULL;
     if (c_out <= 0 || c_in <= 0 || kh <= 0 || kw <= 0) return BNN_E_SHAPE;
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -351,6 +360,10 @@ extern "C" int bnn_pack_weight_f32(const float* w, int32_t c_out, int32_t c_in, 
     // padded output channels / channels beyond c_in keep all-zero bits
     e = cudaMemsetAsync(wbits, 0, bnn_weight_bits_bytes(c_out, c_in, kh, kw), stream);
     if (e != cudaSuccess) return (int)e;
+    if (wzero) {
+        e = cudaMemsetAsync(wzero, 0, bnn_weight_bits_bytes(c_out, c_in, kh, kw), stream);
+        if (e != cudaSuccess) return (int)e;
+    }
     if (n_zero) {
         e = cudaMemsetAsync(n_zero, 0, sizeof(int32_t), stream);
         if (e != cudaSuccess) return (int)e;
@@ -359,7 +372,7 @@ extern "C" int bnn_pack_weight_f32(const float* w, int32_t c_out, int32_t c_in, 
     const size_t smem = 4 * sizeof(double) + (size_t)taps * sizeof(float);
     if (smem > 48 * 1024) return BNN_E_UNSUPPORTED;
     pack_weight_kernel<<<c_out, 128, smem, stream>>>(w, c_out, c_in, taps, nch, center, compute_alpha,
-                                                     (uint32_t*)wbits, alpha, n_zero);
+                                                     (uint32_t*)wbits, (uint32_t*)wzero, alpha, n_zero);
     count_launch(1);
     return (int)cudaGetLastError();
 }

@@ -47,6 +47,12 @@ _SIGNATURES = {
                                      c_int32, c_int32, c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
     "bnn_pack_weight_f32": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                                     c_void_p, c_void_p, c_void_p, c_void_p]),
+    "bnn_pack_weight_ternary_f32": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "bnn_conv_split": (c_int, [POINTER(ConvGeom), c_uint32, POINTER(c_int32), POINTER(c_int32)]),
+    "bnn_bconv2d_partial_fwd": (c_int, [c_void_p, c_void_p, POINTER(ConvGeom), c_int32, c_int32, c_void_p, c_uint32, c_void_p]),
+    "bnn_dot_finish_f32": (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
+                                   c_int64, c_int64, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "bnn_bconv2d_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_int64, c_int64, c_int64, c_int64, POINTER(ConvGeom), c_uint32, c_void_p]),
     "bnn_bconv2d_fused_fwd": (c_int, [c_void_p, c_void_p, POINTER(ConvGeom), POINTER(Epilogue), c_uint32, c_void_p]),
@@ -139,6 +145,13 @@ def conv_instance(geom: ConvGeom, ep: "Epilogue", flags: int, P: int, C: int, TH
     arr = (c_int32 * 6)()
     check(lib().bnn_conv_instance(ctypes.byref(geom), ctypes.byref(ep), flags, P, C, TH, warps, arr), "bnn_conv_instance")
     return dict(zip(("P", "C", "kw_inst", "stride_inst", "csa", "epi"), list(arr)))
+
+
+def conv_split(geom: ConvGeom, flags: int = 0):
+    """(chunks per part, number of parts) of the split-K decomposition; (all chunks, 1) when none is needed."""
+    cpp, parts = c_int32(0), c_int32(0)
+    check(lib().bnn_conv_split(ctypes.byref(geom), flags, ctypes.byref(cpp), ctypes.byref(parts)), "bnn_conv_split")
+    return cpp.value, parts.value
 
 
 def launch_count() -> int:

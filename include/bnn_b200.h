@@ -109,11 +109,42 @@ int bnn_avgpool_pack_f32(const float *x, int64_t stride_n, int64_t stride_c, int
  * w is contiguous [c_out, c_in, kh, kw] (Linear: kh = kw = 1).
  * n_zero (device int32, may be NULL) receives the number of centred weights
  * that are exactly 0 -- their sign is 0 in the reference, which one bit cannot
- * hold; callers must not use the packed path when it is non-zero.
+ * hold; when it is non-zero the layer has to run the ternary form below.
  */
 int bnn_pack_weight_f32(const float *w, int32_t c_out, int32_t c_in, int32_t kh, int32_t kw,
                         int32_t center_weights, int32_t compute_alpha,
                         void *wbits, float *alpha, int32_t *n_zero, void *stream);
+
+/*
+ * Ternary weights.  The reference evaluates sign(0) = 0 for weights too (bnn/ops.py:66,136): an exactly-zero (centred)
+ * weight contributes nothing.  bnn_pack_weight_ternary_f32 is bnn_pack_weight_f32 plus `wzero` (same layout and size as
+ * wbits, may be NULL): the plane of those exactly-zero weights.  With  t- = wbits  (zeros packed as -1) and
+ * t+ = wbits | wzero  (zeros packed as +1) the ternary dot is the mean of two binary dots,
+ *     dot = (dot(t-) + dot(t+)) / 2      (exact: the sum is always even),
+ * which bnn_bconv2d_partial_fwd (twice) + bnn_dot_finish_f32(divisor = 2) compute.
+ */
+int bnn_pack_weight_ternary_f32(const float *w, int32_t c_out, int32_t c_in, int32_t kh, int32_t kw,
+                                int32_t center_weights, int32_t compute_alpha, void *wbits, void *wzero,
+                                float *alpha, int32_t *n_zero, void *stream);
+
+/*
+ * Split-K.  bnn_bconv2d_fwd keeps a CTA's whole reduction (all input chunks of the kernel window) in shared memory; a
+ * layer that cannot (Linear(25088, 4096): 392 chunks; convolutions over more than 16384 channels) is contracted chunk
+ * range by chunk range.  bnn_conv_split says how: *nparts == 1 means the plain entry points work; otherwise the layer
+ * is cut into *nparts ranges of *chunks_per_part 64-channel chunks (the last one may be shorter).
+ * bnn_bconv2d_partial_fwd contracts input chunks [chunk0, chunk0 + nchunks) of the FULL packed tensors abits / wbits
+ * (geom describes the full layer) and writes the integer dots of that range, as exact fp32 values, to
+ * part[n, c_out, ho, wo] (contiguous).  bnn_dot_finish_f32 adds `nparts` such buffers (parts = [nparts][n*c_out*ho*wo]),
+ * divides by `divisor` (1, or 2 for the two launches of a ternary weight tensor) and applies the reference epilogue
+ *     y = (scale[co] * dot + bias[co]) * post[co]
+ * with element strides for the output, like bnn_bconv2d_fwd.
+ */
+int bnn_conv_split(const bnn_conv_geom *geom, uint32_t flags, int32_t *chunks_per_part, int32_t *nparts);
+int bnn_bconv2d_partial_fwd(const void *abits, const void *wbits, const bnn_conv_geom *geom, int32_t chunk0,
+                            int32_t nchunks, float *part, uint32_t flags, void *stream);
+int bnn_dot_finish_f32(const float *parts, int32_t nparts, int32_t divisor, const float *scale, const float *bias,
+                       const float *post, float *out, int64_t ostride_n, int64_t ostride_c, int64_t ostride_h,
+                       int64_t ostride_w, int32_t n, int32_t c_out, int32_t ho, int32_t wo, void *stream);
 
 /*
  * bnn.layers.Conv2d.forward (bnn/layers/conv.py:90-97) on packed operands:

@@ -13,9 +13,10 @@ from bnn_b200 import fuse  # noqa: E402
 fused = "--no-fuse" not in sys.argv
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
-model = bench.build_model("basic_relu").cuda()
+config = next((a.split("=", 1)[1] for a in sys.argv if a.startswith("--config=")), "resnet18")
+model = bench.build_model(config, "basic_relu").cuda()
 engine = fuse.optimize(model) if fused else model
-x = torch.randn(256, 3, 224, 224, device="cuda")
+x = torch.randn(bench.CONFIGS[config]["batch"], 3, bench.CONFIGS[config]["res"], bench.CONFIGS[config]["res"], device="cuda")
 with torch.no_grad():
     for _ in range(3):
         engine(x)
