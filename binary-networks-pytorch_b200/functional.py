@@ -39,11 +39,12 @@ class PackedWeights:
     """Sign planes + XNOR alpha of one weight tensor."""
     bits: torch.Tensor       # int32 [c_out/32, ksteps, 32, 2]
     alpha: torch.Tensor      # float32 [c_out]
-    n_zero: int              # exactly-zero (centred) weights: must be 0 for the packed path
+    n_zero: int              # exactly-zero (centred) weights: sign 0 in the reference (ternary tensor)
     c_out: int
     c_in: int
     kh: int
     kw: int
+    hi: Optional["PackedWeights"] = None     # ternary tensors: the same planes with the zeros packed as +1 (bits: as -1)
 
 
 def pack_activations(x: torch.Tensor, linear_rows: bool = False, pre: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
@@ -81,7 +82,9 @@ def pack_activations(x: torch.Tensor, linear_rows: bool = False, pre: Optional[T
 
 
 def pack_weights(weight: torch.Tensor, center_weights: bool, compute_alpha: bool) -> PackedWeights:
-    """``XNORWeightBinarizer`` (reference bnn/ops.py:129-140) as a prepare-time pack."""
+    """``XNORWeightBinarizer`` (reference bnn/ops.py:129-140) as a prepare-time pack.  A tensor with exactly-zero
+    (centred) weights -- sign 0 in the reference, bnn/ops.py:66,136 -- comes back with ``hi`` set: a second set of
+    planes with the zeros packed as +1 (``bits`` has them as -1); the ternary dot is the mean of the two binary dots."""
     _require_cuda_f32(weight, "weight")
     w = weight.detach().contiguous()
     if w.dim() == 2:
@@ -97,11 +100,16 @@ def pack_weights(weight: torch.Tensor, center_weights: bool, compute_alpha: bool
         bits = torch.empty(((c_out + 31) // 32, nk, 32, 2), dtype=torch.int32, device=w.device)
         alpha = torch.empty((c_out,), dtype=torch.float32, device=w.device)
         nz = torch.zeros((1,), dtype=torch.int32, device=w.device)
-        rc = native.lib().bnn_pack_weight_f32(w.data_ptr(), c_out, c_in, kh, kw, int(center_weights),
-                                              int(compute_alpha), bits.data_ptr(), alpha.data_ptr(),
-                                              nz.data_ptr(), _stream_ptr(w.device))
-    native.check(rc, "bnn_pack_weight_f32")
-    return PackedWeights(bits, alpha, int(nz.item()), c_out, c_in, kh, kw)
+        zero = torch.empty_like(bits)
+        rc = native.lib().bnn_pack_weight_ternary_f32(w.data_ptr(), c_out, c_in, kh, kw, int(center_weights),
+                                                      int(compute_alpha), bits.data_ptr(), zero.data_ptr(),
+                                                      alpha.data_ptr(), nz.data_ptr(), _stream_ptr(w.device))
+    native.check(rc, "bnn_pack_weight_ternary_f32")
+    n_zero = int(nz.item())
+    packed = PackedWeights(bits, alpha, n_zero, c_out, c_in, kh, kw)
+    if n_zero:
+        packed.hi = PackedWeights(bits | zero, alpha, n_zero, c_out, c_in, kh, kw)
+    return packed
 
 
 def _opt_ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -132,6 +140,59 @@ def _out_hw(act, wts, stride, padding, dilation):
     return ho, wo
 
 
+_split_cache = {}
+
+
+def conv_split(geom: ConvGeom, flags: int = 0):
+    """(chunks per part, parts) of the split-K decomposition of a geometry (``bnn_conv_split``, host only, cached)."""
+    key = (geom.c_in, geom.c_out, geom.kh, geom.kw, geom.stride_h, geom.stride_w, geom.dil_h, geom.dil_w, geom.h, geom.w,
+           geom.pad_h, geom.pad_w, flags & native.F_NO_CSA)
+    if key not in _split_cache:
+        _split_cache[key] = native.conv_split(geom, flags)
+    return _split_cache[key]
+
+
+def needs_general_path(wts: PackedWeights, stride=(1, 1), dilation=(1, 1)) -> bool:
+    """True when a layer cannot run as ONE launch of the conv kernel: ternary weights (exact zeros) or a reduction too
+    large for a CTA's shared memory (split-K).  Such layers run ``_bconv2d_general`` and are never fused."""
+    if wts.hi is not None:
+        return True
+    probe = ConvGeom(1, wts.c_in, max(8, wts.kh * dilation[0]), max(8, wts.kw * dilation[1]), wts.c_out, wts.kh, wts.kw,
+                     stride[0], stride[1], 0, 0, dilation[0], dilation[1])
+    try:
+        return conv_split(probe)[1] > 1
+    except native.NativeError:
+        return True
+
+
+def _bconv2d_general(act: PackedActivations, wts: PackedWeights, geom: ConvGeom, ho: int, wo: int, bias, post, use_alpha,
+                     flags, out: torch.Tensor) -> torch.Tensor:
+    """Ternary weights and / or split-K: integer dots of every (weight set, chunk range) by ``bnn_bconv2d_partial_fwd``,
+    summed (and halved for a ternary pair) and put through the reference epilogue by ``bnn_dot_finish_f32``."""
+    dev = act.bits.device
+    cpp, nparts = conv_split(geom, flags)
+    nch = (geom.c_in + 63) // 64
+    sets = [wts] if wts.hi is None else [wts, wts.hi]
+    count = act.n * wts.c_out * ho * wo
+    lib = native.lib()
+    with torch.cuda.device(dev):
+        parts = torch.empty((len(sets) * nparts, count), dtype=torch.float32, device=dev)
+        i = 0
+        for ws in sets:
+            for p in range(nparts):
+                c0 = p * cpp
+                rc = lib.bnn_bconv2d_partial_fwd(act.bits.data_ptr(), ws.bits.data_ptr(), ctypes.byref(geom), c0,
+                                                 min(cpp, nch - c0), parts[i].data_ptr(), flags, _stream_ptr(dev))
+                native.check(rc, "bnn_bconv2d_partial_fwd")
+                i += 1
+        on, oc, oh, ow = out.stride()
+        rc = lib.bnn_dot_finish_f32(parts.data_ptr(), len(sets) * nparts, len(sets),
+                                    wts.alpha.data_ptr() if use_alpha else None, _opt_ptr(bias), _opt_ptr(post),
+                                    out.data_ptr(), on, oc, oh, ow, act.n, wts.c_out, ho, wo, _stream_ptr(dev))
+    native.check(rc, "bnn_dot_finish_f32")
+    return out
+
+
 def bconv2d(act: PackedActivations, wts: PackedWeights, bias: Optional[torch.Tensor] = None,
             post: Optional[torch.Tensor] = None, stride: Tuple[int, int] = (1, 1),
             padding: Tuple[int, int] = (0, 0), dilation: Tuple[int, int] = (1, 1),
@@ -148,6 +209,8 @@ def bconv2d(act: PackedActivations, wts: PackedWeights, bias: Optional[torch.Ten
             out = torch.empty((act.n, wts.c_out, ho, wo), dtype=torch.float32, device=dev)
         elif tuple(out.shape) != (act.n, wts.c_out, ho, wo) or out.dtype != torch.float32 or not out.is_cuda:
             raise native.NativeError(f"out must be a float32 CUDA tensor of shape {(act.n, wts.c_out, ho, wo)}")
+        if wts.hi is not None or conv_split(geom, flags)[1] > 1:
+            return _bconv2d_general(act, wts, geom, ho, wo, bias, post, use_alpha, flags, out)
         on, oc, oh, ow = out.stride()
         ep = native.Epilogue()
         ep.scale = wts.alpha.data_ptr() if use_alpha else None
@@ -177,6 +240,8 @@ def bconv2d_fused(act: PackedActivations, wts: PackedWeights, *, bias=None, post
     family) instead of the tuned / modelled one -- the parity suite sweeps every kernel instance with it."""
     if act.c != wts.c_in:
         raise native.NativeError(f"channel mismatch: activations {act.c}, weights {wts.c_in}")
+    if wts.hi is not None:
+        raise native.NativeError("ternary weights (exact zeros) have no fused lowering; use bconv2d")
     geom = ConvGeom(act.n, act.c, act.h, act.w, wts.c_out, wts.kh, wts.kw, stride[0], stride[1],
                     padding[0], padding[1], dilation[0], dilation[1])
     ho, wo = _out_hw(act, wts, stride, padding, dilation)
@@ -229,6 +294,14 @@ def blinear(act: PackedActivations, wts: PackedWeights, bias: Optional[torch.Ten
     """Packed binary linear layer: activations packed with ``linear_rows=True`` -> [rows, out]."""
     rows = act.w
     dev = act.bits.device
+    geom = ConvGeom(1, act.c, 1, rows, wts.c_out, 1, 1, 1, 1, 0, 0, 1, 1)
+    if wts.hi is not None or conv_split(geom, flags)[1] > 1:
+        # rows play the role of the image width: out[rows, out] is the [1, out, 1, rows] result with strides (0, 1, 0, out)
+        with torch.cuda.device(dev):
+            out = torch.empty((rows, wts.c_out), dtype=torch.float32, device=dev)
+        view = out.as_strided((1, wts.c_out, 1, rows), (0, 1, 0, wts.c_out))
+        _bconv2d_general(act, wts, geom, 1, rows, bias, post, use_alpha, flags, view)
+        return out
     with torch.cuda.device(dev):
         out = torch.empty((rows, wts.c_out), dtype=torch.float32, device=dev)
         rc = native.lib().bnn_blinear_fwd(act.bits.data_ptr(), wts.bits.data_ptr(),

@@ -79,6 +79,8 @@ def _fusable_conv(conv) -> bool:
         low = conv._lowering()
     except NotLowerable:
         return False
+    if conv.weight.is_cuda and BF.needs_general_path(conv._packed_weights(low), _pair(conv.stride), _pair(conv.dilation)):
+        return False           # ternary weights / split-K reductions run the per-layer general path
     return (not low.has_post) or low.fused_post
 
 

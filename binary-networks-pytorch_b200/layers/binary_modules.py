@@ -144,12 +144,9 @@ class _BinaryLayer:
         w = self.weight
         key = (w.data_ptr(), w._version, w.device, tuple(w.shape), low.center_weights, low.compute_alpha)
         if self._pack_key != key:
-            packed = BF.pack_weights(w, low.center_weights, low.compute_alpha)
-            if packed.n_zero:
-                raise NativeError(
-                    f"{packed.n_zero} weights are exactly zero after centring: sign(0)=0 makes them ternary "
-                    "(reference bnn/ops.py:66) which the 1-bit weight plane cannot hold")
-            self._packed, self._pack_key = packed, key
+            # exactly-zero (centred) weights have sign 0 in the reference (bnn/ops.py:66,136): pack_weights then returns a
+            # ternary pair of planes and the layer runs as two binary launches + an exact integer mean
+            self._packed, self._pack_key = BF.pack_weights(w, low.center_weights, low.compute_alpha), key
         return self._packed
 
     def repack(self) -> None:
@@ -287,8 +284,6 @@ class Conv2d(_ConvNd, nn.Conv2d):
             cout_g = self.out_channels // self.groups
             packed = [BF.pack_weights(w[i * cout_g:(i + 1) * cout_g], low.center_weights, low.compute_alpha)
                       for i in range(self.groups)]
-            if any(p.n_zero for p in packed):
-                raise NativeError("exactly-zero (centred) weights cannot be held by the 1-bit weight plane")
             self._packed, self._pack_key = packed, key
         return self._packed
 

@@ -73,6 +73,16 @@ def test_size_helpers_and_errors_without_gpu():
     assert lib.bnn_conv_plan_list(None, 0, None, 0, ctypes.byref(n)) == -1
     ep = native.Epilogue()
     assert lib.bnn_bconv2d_fused_fwd_plan(one, one, ctypes.byref(g3), ctypes.byref(ep), 0, 5, 3, 0, 0, None) == -3       # no such family
+    # split-K decomposition (host only): the VGG classifier shape needs it, a ResNet layer does not
+    assert native.conv_split(native.ConvGeom(1, 25088, 1, 8, 4096, 1, 1, 1, 1, 0, 0, 1, 1))[1] > 1
+    assert native.conv_split(native.ConvGeom(256, 512, 7, 7, 512, 3, 3, 1, 1, 1, 1, 1, 1)) == (8, 1)
+    cpp, parts = native.conv_split(native.ConvGeom(1, 16448, 4, 4, 64, 1, 1, 1, 1, 0, 0, 1, 1))
+    assert parts > 1 and cpp * parts >= 257 and cpp * (parts - 1) < 257 and cpp <= 256
+    assert lib.bnn_bconv2d_partial_fwd(one, one, ctypes.byref(g3), 0, 2, one, 0, None) == -2        # only one chunk exists
+    assert lib.bnn_bconv2d_partial_fwd(one, one, ctypes.byref(g3), 0, 1, None, 0, None) == -1
+    assert lib.bnn_dot_finish_f32(one, 2, 3, None, None, None, one, 0, 0, 0, 0, 1, 1, 1, 1, None) == -2   # divisor 1 or 2
+    assert lib.bnn_dot_finish_f32(None, 1, 1, None, None, None, one, 0, 0, 0, 0, 1, 1, 1, 1, None) == -1
+    assert lib.bnn_pack_weight_ternary_f32(None, 1, 1, 1, 1, 0, 1, None, None, None, None, None) == -1
     inst = (ctypes.c_int32 * 6)()
     assert lib.bnn_conv_instance(ctypes.byref(g3), ctypes.byref(ep), 0, 8, 2, 0, 0, inst) == 0 and list(inst) == [8, 2, 3, 1, 1, 0]
     assert lib.bnn_stem_fwd(None, 1, 8, 8, None, None, None, None, None, None, None, 0, None) == -1

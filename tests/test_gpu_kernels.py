@@ -189,14 +189,120 @@ def test_weight_cache_follows_load_state_dict_and_inplace_updates():
         assert torch.equal(a(x), -ya)                     # repacked: alpha unchanged, every dot negated
 
 
-def test_exact_zero_weights_are_refused_not_approximated():
+def _sign_dot_f64(x, w_centred, stride, pad, dil, groups=1):
+    """exact integer dot of the reference's ternary operands: conv(sign(x), sign(w)) in float64"""
+    return torch.nn.functional.conv2d(torch.sign(torch.from_numpy(x).double()), torch.sign(torch.from_numpy(w_centred).double()),
+                                      None, stride, pad, dil, groups).numpy()
+
+
+@pytest.mark.parametrize("center", [False, True])
+def test_exact_zero_weights_run_the_ternary_path(center):
+    """sign(0) = 0 for weights too (reference bnn/ops.py:66,136): tensors with exactly-zero (centred) weights run as two
+    binary launches (zeros packed as -1 / +1) + an exact integer mean.  Integer dots bit-exact, layer output vs the
+    float simulation of the reference."""
     import torch.nn as nn
+    from oracle import floatsim as fs
+    from bnn_b200.ops import BasicInputBinarizer, BasicScaleBinarizer, XNORWeightBinarizer
+    rng = np.random.default_rng(21)
+    x = rng.standard_normal((2, 70, 9, 11)).astype(np.float32)
+    x[rng.random(x.shape) < 0.3] = 0.0
+    w = (rng.standard_normal((40, 70, 3, 3)) * 0.05).astype(np.float32)
+    if center:
+        w[3, :, 1, 1] = 0.25                  # a constant column: centring makes all 70 of them exactly zero
+        w[17, :, 0, 2] = -0.5
+        # the pack kernel's centring: per-tap mean over c_in summed in fp64 and rounded once, fp32 subtraction
+        wc = w - (w.astype(np.float64).sum(1, keepdims=True) / w.shape[1]).astype(np.float32)
+    else:
+        w[rng.random(w.shape) < 0.2] = 0.0    # pruned weights
+        w[5] = 0.0                            # a dead output channel: alpha = 0, every dot = 0
+        wc = w
+    nz_want = int((wc == 0).sum())
+    assert nz_want > 0
+    wts = BF.pack_weights(torch.from_numpy(w).to(DEV), center, True)
+    assert wts.n_zero == nz_want and wts.hi is not None
+    act = BF.pack_activations(torch.from_numpy(x).to(DEV))
+    dot = BF.bconv2d(act, wts, None, None, (2, 1), (1, 1), (1, 1), use_alpha=False).cpu().numpy()
+    assert np.array_equal(dot.astype(np.float64), _sign_dot_f64(x, wc, (2, 1), (1, 1), (1, 1)))
+    # module level: bias + learned post scale, against the torch float simulation of the reference's forward
+    cfg = bnn.BConfig(BasicInputBinarizer, BasicScaleBinarizer, XNORWeightBinarizer.with_args(compute_alpha=True, center_weights=center))
+    m = nn.Conv2d(70, 40, 3, stride=(2, 1), padding=1)
+    m.weight.data.copy_(torch.from_numpy(w))
+    m = bnn.prepare_binary_model(m.to(DEV), cfg).eval()
+    m.activation_post_process.alpha.data.uniform_(0.5, 1.5)
+    with torch.no_grad():
+        y = m(torch.from_numpy(x).to(DEV)).cpu()
+        want = fs.conv2d(torch.from_numpy(x), m.weight.cpu(), m.bias.cpu(), m.activation_post_process.alpha.cpu().reshape(-1),
+                         (2, 1), 1, 1, True, center)
+    assert rel_err(y.numpy(), want.numpy()) <= TOL
+    # Linear and a grouped conv with zeros
+    lin = nn.Linear(100, 24)
+    lin.weight.data[::3, ::7] = 0.0
+    lin = bnn.prepare_binary_model(lin.to(DEV), bnn.BConfig(BasicInputBinarizer, bnn.Identity, XNORWeightBinarizer)).eval()
+    xl = torch.randn(5, 100)
+    with torch.no_grad():
+        assert rel_err(lin(xl.to(DEV)).cpu().numpy(), fs.linear(xl, lin.weight.cpu(), lin.bias.cpu()).numpy()) <= TOL
+    gc = nn.Conv2d(64, 64, 3, padding=1, groups=2, bias=False)
+    gc.weight.data[gc.weight.data.abs() < 0.02] = 0.0
+    gc = bnn.prepare_binary_model(gc.to(DEV), bnn.BConfig(BasicInputBinarizer, bnn.Identity, XNORWeightBinarizer)).eval()
+    xg = torch.randn(2, 64, 7, 7)
+    with torch.no_grad():
+        want = fs.conv2d(xg, gc.weight.cpu(), None, None, 1, 1, 1, True, False, groups=2)
+        assert rel_err(gc(xg.to(DEV)).cpu().numpy(), want.numpy()) <= TOL
+
+
+@pytest.mark.parametrize("kind,cin,cout,k,hw", [("linear", 25088, 96, 1, (1, 3)), ("conv", 6144, 32, 3, (5, 6)),
+                                               ("conv", 16448, 64, 1, (4, 4)), ("linear", 16390, 40, 1, (1, 1))])
+def test_split_k_layers_bit_exact_vs_oracle(kind, cin, cout, k, hw):
+    """Reductions too large for one CTA's shared memory (Linear(25088, .): 392 chunks; 3x3 over 6144 channels; more than
+    16384 channels) are contracted chunk range by chunk range (bnn_conv_split / bnn_bconv2d_partial_fwd /
+    bnn_dot_finish_f32).  Integer dots bit-exact against the oracle, outputs against its float simulation."""
+    rng = np.random.default_rng(31)
+    h, w_ = hw
+    pad = k // 2
+    x = np.maximum(rng.standard_normal((1, cin, h, w_)), -0.3).astype(np.float32)
+    x[rng.random(x.shape) < 0.2] = 0.0
+    wt = (rng.standard_normal((cout, cin, k, k)) * 0.05).astype(np.float32)
+    bias = (rng.standard_normal(cout) * 0.3).astype(np.float32)
+    post = (0.5 + rng.random(cout)).astype(np.float32)
+    g = co.geom(1, cin, h, w_, cout, k, k, (1, 1), (pad, pad), (1, 1))
+    ng = native.ConvGeom(1, cin, h, w_, cout, k, k, 1, 1, pad, pad, 1, 1)
+    assert native.conv_split(ng)[1] > 1
+    wb, alpha, nz = co.pack_weight(wt, True, True)
+    assert nz == 0
+    want_dot = co.bconv2d_dot(co.pack_act(x), wb, g)
+    wts = BF.pack_weights(torch.from_numpy(wt).to(DEV), True, True)
+    assert np.array_equal(wts.bits.cpu().numpy().view(np.uint32), wb)
+    if kind == "linear":
+        rows = x.reshape(cin, w_).T.copy()                        # [rows, features]
+        act = BF.pack_activations(torch.from_numpy(rows).to(DEV), linear_rows=True)
+        dot = BF.blinear(act, wts, None, None, use_alpha=False).cpu().numpy()          # [rows, out]
+        assert np.array_equal(dot.T.reshape(want_dot.shape).astype(np.int32), want_dot)
+        y = BF.blinear(act, wts, torch.from_numpy(bias).to(DEV), torch.from_numpy(post).to(DEV)).cpu().numpy()
+        want = co.floatsim_linear(rows, wt.reshape(cout, cin), bias, post, True, True)
+        assert rel_err(y, want) <= TOL
+    else:
+        act = BF.pack_activations(torch.from_numpy(x).to(DEV))
+        dot = BF.bconv2d(act, wts, None, None, (1, 1), (pad, pad), (1, 1), use_alpha=False).cpu().numpy()
+        assert np.array_equal(dot.astype(np.int32), want_dot)
+        y = BF.bconv2d(act, wts, torch.from_numpy(bias).to(DEV), torch.from_numpy(post).to(DEV), (1, 1), (pad, pad), (1, 1)).cpu().numpy()
+        want = co.floatsim_conv2d(x, wt, bias, post, g, True, True)
+        assert rel_err(y, want) <= TOL
+
+
+def test_large_linear_module_runs():
+    """reference bnn/layers/linear.py:22-27 has no size limit: Linear(25088, 4096) (the VGG classifier shape) through the
+    module API."""
+    import torch.nn as nn
+    from oracle import floatsim as fs
     from bnn_b200.ops import BasicInputBinarizer, XNORWeightBinarizer
-    cfg = bnn.BConfig(BasicInputBinarizer, bnn.Identity, XNORWeightBinarizer)
-    m = bnn.prepare_binary_model(nn.Conv2d(64, 64, 1).to(DEV), cfg).eval()
-    m.weight.data[3, 7] = 0.0
-    with torch.no_grad(), pytest.raises(native.NativeError, match="exactly zero"):
-        m(torch.randn(1, 64, 4, 4, device=DEV))
+    torch.manual_seed(3)
+    lin = nn.Linear(25088, 4096)
+    lin = bnn.prepare_binary_model(lin.to(DEV), bnn.BConfig(BasicInputBinarizer, bnn.Identity, XNORWeightBinarizer)).eval()
+    x = torch.randn(4, 25088)
+    with torch.no_grad():
+        y = lin(x.to(DEV)).cpu()
+        want = fs.linear(x, lin.weight.cpu(), lin.bias.cpu())
+    assert rel_err(y.numpy(), want.numpy()) <= TOL
 
 
 @pytest.mark.parametrize("cin,cout,k,s,pad,h,w", [(1153, 32, 5, 2, 2, 5, 57), (1153, 70, 5, 1, 2, 6, 300)])
