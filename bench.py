@@ -475,6 +475,10 @@ def main():
             rows_per_rank = max(2, -(-8 // world))
             twin, twin_kind, _ = cpu_twin(args.config, args.variant, model_cpu)
             torch.set_num_threads(os.cpu_count() or 1)
+
+            def cpu_reference_rows(rows):                      # the CHECKER: reference CPU forward of a few rows
+                return twin(rows)
+
             got, want = [], []
             for r in range(world):
                 xr = x_host if r == 0 else torch.randn(B, 3, RES, RES, generator=torch.Generator().manual_seed(1000 + r))
@@ -534,6 +538,45 @@ def main():
         e2e_diff = float((last_logits[:B].float() - timed_out[:B].float().cpu()).abs().max())
         assert torch.isfinite(last_logits).all()
         del pipe
+
+        # ---- the same end-to-end loop fed with DECODED IMAGES (uint8 NHWC, a quarter of the bytes): the tcgen05 stem
+        # normalises while it stages the window.  Reported beside `e2e` (fp32 tensors, the reference's input contract).
+        e2e_u8 = None
+        if hasattr(engine, "set_uint8_input") and not args.no_fuse and args.stem in ("auto", "tc"):
+            mean, std = (123.675, 116.28, 103.53), (58.395, 57.12, 57.375)
+            eng8 = fuse.optimize(model, stem="tc").set_uint8_input(mean, std)
+            xu_host = torch.randint(0, 256, (B, RES, RES, 3), dtype=torch.uint8,
+                                    generator=torch.Generator().manual_seed(2000 + rank)).pin_memory()
+            pipe8 = HostPipeline(eng8, xu_host, dev, use_graphs=(graph is not None),
+                                 post=(sharded.gather_logits if world > 1 else None))
+            for _ in range(2):
+                pipe8.submit(xu_host)
+            pipe8.drain()
+            sync_all()
+            u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            u0.record(pipe8.compute_stream)
+            for _ in range(args.steps):
+                pipe8.submit(xu_host)
+            u1.record(pipe8.d2h_stream)
+            logits8 = pipe8.drain()
+            sync_all()
+            ms8_t = torch.tensor([u0.elapsed_time(u1)], device=dev)
+            if world > 1:
+                dist.all_reduce(ms8_t, op=dist.ReduceOp.MAX)
+            ms8 = float(ms8_t.item())
+            e2e_u8 = {"value": B * world / (ms8 / args.steps * 1e-3), "unit": "images/s", "ms_per_step": ms8 / args.steps,
+                      "h2d_bytes_per_step": xu_host.numel() * world, "d2h_bytes_per_step": B * world * 1000 * 4 * world,
+                      "input": "uint8 [n,h,w,3] pinned host batch; (x - mean) * (1/std) folded into bnn_stem_tc_run"}
+            if rank == 0:
+                k = 4
+                istd = torch.tensor([float(torch.tensor(1.0) / torch.tensor(v)) for v in std])
+                xn = ((xu_host[:k].float() - torch.tensor(mean)) * istd).permute(0, 3, 1, 2).contiguous()
+                want8 = cpu_reference_rows(xn)
+                got8 = logits8[:k].float()
+                e2e_u8["parity_max_rel_err"] = float((got8 - want8).abs().max() / want8.abs().max())
+                if not (e2e_u8["parity_max_rel_err"] <= 1e-3):
+                    raise SystemExit(f"bench.py: uint8 end-to-end parity FAILED: {json.dumps(e2e_u8)}")
+            del pipe8, eng8
 
         # ---- the literal drop-in (prepare_binary_model only, no fuse.optimize): per-layer kernels + torch glue
         dropin = None
@@ -693,6 +736,8 @@ def main():
                              "what": f"same launches (+ bit-pack launches) as algorithmic bytes at the drop-in contract: "
                                      f"{total_bytes / 1e9:.3f} GB/step over {path_ms:.3f} ms/step"}},
     }
+    if e2e_u8 is not None:
+        line["e2e_u8"] = e2e_u8
     if dropin is not None:
         line["dropin"] = dropin
     if popc_peak_tbmac:

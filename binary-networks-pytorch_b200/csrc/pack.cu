@@ -195,6 +195,73 @@ static int launch_pack_dense(const float* x, long long pixels, int HW, const flo
     return (int)cudaGetLastError();
 }
 
+// AvgPool2d(2) (kernel = stride = 2, floor mode) of a dense NHWC tensor, fused with the bit-pack of the NEXT binarized
+// layer: one pass reads the fp32 tensor, writes the pooled fp32 tensor (the residual stream the next block adds its
+// convolutions to) and the planes of sign(pooled * pre_scale + pre_shift).  The Hierarchical-Block harness pools a
+// 1 GB NHWC tensor between two blocks (hierarchical_block.py:38-60 stacked as in SURVEY.md A.1.4); as a torch AvgPool2d
+// followed by a pack that was 1.6 + 0.06 ms, this is one HBM pass.  Window sum in row-major order, divided by 4: the pack
+// kernels' (= torch's CPU kernel's) operation order.  A warp owns AP_PPW pooled pixels, lanes <-> channels.
+constexpr int AP_PPW = 2;
+
+template <int NCH>
+__global__ void __launch_bounds__(256)
+avgpool2_pack_cl_kernel(const float* __restrict__ x, long long pooled_pixels, int H, int W, int Ho, int Wo,
+                        const float* __restrict__ pre_scale, const float* __restrict__ pre_shift, int pre_relu,
+                        float* __restrict__ pooled, uint4* __restrict__ abits) {
+    constexpr int C = 64 * NCH, NB = 2 * NCH;
+    const int lane = threadIdx.x & 31;
+    const long long pp0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * AP_PPW;
+    if (pp0 >= pooled_pixels) return;                        // warp-uniform
+    float v[AP_PPW][4][NB];
+    int n_[AP_PPW], ho_[AP_PPW], wo_[AP_PPW];
+#pragma unroll
+    for (int u = 0; u < AP_PPW; ++u) {
+        const long long pp = pp0 + u < pooled_pixels ? pp0 + u : pooled_pixels - 1;
+        wo_[u] = (int)(pp % Wo);
+        const long long t = pp / Wo;
+        ho_[u] = (int)(t % Ho);
+        n_[u] = (int)(t / Ho);
+        const float* px = x + (((size_t)n_[u] * H + 2 * ho_[u]) * W + 2 * wo_[u]) * C + lane;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float* pq = px + ((size_t)(q >> 1) * W + (q & 1)) * C;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) v[u][q][b] = __ldg(pq + b * 32);
+        }
+    }
+    const bool pre = pre_scale != nullptr;
+#pragma unroll
+    for (int u = 0; u < AP_PPW; ++u) {
+        if (pp0 + u >= pooled_pixels) break;                 // warp-uniform
+        const size_t opix = ((size_t)n_[u] * Ho + ho_[u]) * Wo + wo_[u];
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) {
+            uint32_t s_[2], m_[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int b = 2 * ch + h;
+                float t = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(v[u][0][b], v[u][1][b]), v[u][2][b]), v[u][3][b]), 4.0f);
+                if (pooled != nullptr) pooled[opix * C + b * 32 + lane] = t;
+                if (pre) t = __fadd_rn(__fmul_rn(t, __ldg(pre_scale + b * 32 + lane)), __ldg(pre_shift + b * 32 + lane));
+                s_[h] = __ballot_sync(0xffffffffu, t > 0.0f);
+                m_[h] = __ballot_sync(0xffffffffu, t > 0.0f || (t < 0.0f && !pre_relu));
+            }
+            if (lane == 0) abits[((size_t)n_[u] * NCH + ch) * Ho * Wo + (size_t)ho_[u] * Wo + wo_[u]] = make_uint4(s_[0], s_[1], m_[0], m_[1]);
+        }
+    }
+}
+
+template <int NCH>
+static int launch_avgpool2_pack(const float* x, int n, int h, int w, const float* pre_scale, const float* pre_shift,
+                                int pre_relu, float* pooled, void* abits, cudaStream_t stream) {
+    const int ho = h / 2, wo = w / 2;
+    const long long pp = (long long)n * ho * wo, warps = (pp + AP_PPW - 1) / AP_PPW, blocks = (warps + 7) / 8;
+    if (blocks > 0x7fffffffLL) return BNN_E_UNSUPPORTED;
+    avgpool2_pack_cl_kernel<NCH><<<(unsigned)blocks, 256, 0, stream>>>(x, pp, h, w, ho, wo, pre_scale, pre_shift, pre_relu, pooled, (uint4*)abits);
+    count_launch(1);
+    return (int)cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------
 // weights: one CTA per output channel.
 // ---------------------------------------------------------------------------
@@ -342,6 +409,22 @@ extern "C" int bnn_avgpool_pack_f32(const float* x, int64_t sn, int64_t sc, int6
                                     void* stream) {
     if (k < 1) return BNN_E_SHAPE;
     return launch_pack(x, sn, sc, sh, sw, n, c, h, w, k, ceil_mode, pre_scale, pre_shift, pre_relu, abits, stream);
+}
+
+extern "C" int bnn_avgpool2_pack_cl_f32(const float* x, int32_t n, int32_t c, int32_t h, int32_t w, const float* pre_scale,
+                                        const float* pre_shift, int32_t pre_relu, float* pooled_out, void* abits, void* stream_) {
+    if (!x || !abits) return BNN_E_NULL;
+    if ((pre_scale == nullptr) != (pre_shift == nullptr)) return BNN_E_NULL;
+    if (n <= 0 || c <= 0 || h < 2 || w < 2) return BNN_E_SHAPE;
+    if (((uintptr_t)abits & 15) != 0) return BNN_E_ALIGN;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    switch (c) {
+        case 64: return launch_avgpool2_pack<1>(x, n, h, w, pre_scale, pre_shift, pre_relu, pooled_out, abits, stream);
+        case 128: return launch_avgpool2_pack<2>(x, n, h, w, pre_scale, pre_shift, pre_relu, pooled_out, abits, stream);
+        case 256: return launch_avgpool2_pack<4>(x, n, h, w, pre_scale, pre_shift, pre_relu, pooled_out, abits, stream);
+        case 512: return launch_avgpool2_pack<8>(x, n, h, w, pre_scale, pre_shift, pre_relu, pooled_out, abits, stream);
+        default: return BNN_E_UNSUPPORTED;
+    }
 }
 
 extern "C" int bnn_pack_weight_f32(const float* w, int32_t c_out, int32_t c_in, int32_t kh, int32_t kw,

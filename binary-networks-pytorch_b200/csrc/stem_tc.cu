@@ -32,9 +32,9 @@
 
 namespace bnn {
 
-constexpr int TC_NU = 132;                               // 16-byte units per (group, channel, hi/lo) row: m + p <= 130
+constexpr int TC_NU = 128;                               // 16-byte units per (group, channel, hi/lo) row = converter threads
 constexpr int TC_D = 6;                                  // groups in the ring
-constexpr int TC_SLOT = 3 * 2 * TC_NU * 16;              // 12672 bytes per group
+constexpr int TC_SLOT = 3 * 2 * TC_NU * 16;              // 12288 bytes per group
 constexpr int TC_KSTEPS = 12;
 constexpr int TC_BSTEP = 4096;                           // [wh (64 rows) | wl (64 rows)] x 32 bytes per K step
 constexpr int TC_B_BYTES = TC_KSTEPS * TC_BSTEP;         // 49152
@@ -45,36 +45,47 @@ constexpr int TC_CONV_WARPS = 4, TC_EPI_WARPS = 8;
 constexpr int TC_THREADS = (TC_CONV_WARPS + TC_EPI_WARPS + 1) * 32;      // 416
 constexpr int TC_OFF_CONST = 256, TC_OFF_B = 2048, TC_OFF_RING = TC_OFF_B + TC_B_BYTES;
 constexpr int TC_OFF_VBUF = TC_OFF_RING + TC_D * TC_SLOT;
-constexpr int TC_SMEM = TC_OFF_VBUF + 2 * TC_VBUF;                        // 196864
-constexpr int TC_MAX_PT = 63;                            // pooled columns per M tile: 2 * PT + 1 <= 127 conv columns
+constexpr int TC_SMEM = TC_OFF_VBUF + 2 * TC_VBUF;                        // 194560
+constexpr int TC_MAX_PT = 62;                            // pooled columns per M tile: conv columns m <= 124, units m + p <= 127
+constexpr int TC_MAX_CT = 125;                           // conv columns per M tile without pooling
+static_assert(TC_CONV_WARPS * 32 == TC_NU, "one converter thread per unit");
 
 struct StemTcArgs {
-    const float* x;           // [n,3,h,w] contiguous fp32
+    const void* x;            // IN 0: fp32 [n,3,h,w];  IN 1: uint8 [n,h,w,3]
     const void* wops;         // bnn_stem_tc_pack_weight output
-    const float *bn_scale, *bn_shift, *nx_scale, *nx_shift;
+    const float *bn_scale, *bn_shift, *nx_scale, *nx_shift, *nx2_scale, *nx2_shift;
     const float* x_amax;      // device scalar max|x| (NULL: x_log2_scale is used as given)
-    float* out;               // [n,hp,wp,64]
-    uint4* obits;             // [n][1][hp][wp]
-    int x_log2_scale, w_log2_scale;
-    int N, H, W, Hc, Wc, Hp, Wp, tiles_w, PT;
-    long long total_rows;     // N * tiles_w * Hp pooled rows, split evenly over the CTAs
+    float* out;               // pool: [n,hp,wp,64]; no pool: [n,hc,wc,64]
+    uint4 *obits, *obits2;    // [n][1][rows][cols] planes of sign(out*nx + nx_shift) / sign(out*nx2 + nx2_shift)
+    float u8_mean[3], u8_istd[3];
+    int x_log2_scale, w_log2_scale, nx_relu, nx2_relu, vec2;
+    int N, H, W, Hc, Wc, Ho, Wo, tiles_w, TW;   // Ho x Wo: output rows / cols (pooled or conv); TW: output cols per tile
+    long long total_rows;     // N * tiles_w * Ho output rows, split evenly over the CTAs
 };
 
-struct Seg { int n, pc0, ph_a, r_first, nrows; };
+struct Seg { int n, cbase, col0, row_a, r_first, nrows; };
 
-// next run of pooled rows of one (image, column tile) inside [pos, hi)
+// next run of output rows of one (image, column tile) inside [pos, hi)
+template <bool POOL>
 __device__ __forceinline__ bool next_seg(long long& pos, long long hi, const StemTcArgs& a, Seg& s) {
     if (pos >= hi) return false;
-    const long long img = pos / a.Hp;
-    const int ph_a = (int)(pos - img * a.Hp);
-    const long long end = (img + 1) * a.Hp < hi ? (img + 1) * a.Hp : hi;
-    const int ph_b = ph_a + (int)(end - pos);
+    const long long img = pos / a.Ho;
+    const int row_a = (int)(pos - img * a.Ho);
+    const long long end = (img + 1) * a.Ho < hi ? (img + 1) * a.Ho : hi;
+    const int row_b = row_a + (int)(end - pos);
     s.n = (int)(img / a.tiles_w);
-    s.pc0 = (int)(img % a.tiles_w) * a.PT;
-    s.ph_a = ph_a;
-    s.r_first = 2 * ph_a - 1 > 0 ? 2 * ph_a - 1 : 0;
-    const int r_last = 2 * ph_b - 1 < a.Hc - 1 ? 2 * ph_b - 1 : a.Hc - 1;
-    s.nrows = r_last - s.r_first + 1;
+    s.col0 = (int)(img % a.tiles_w) * a.TW;
+    s.row_a = row_a;
+    if (POOL) {
+        s.cbase = 2 * s.col0 - 1;                                  // lane m <-> conv column 2*pc0 - 1 + m
+        s.r_first = 2 * row_a - 1 > 0 ? 2 * row_a - 1 : 0;
+        const int r_last = 2 * row_b - 1 < a.Hc - 1 ? 2 * row_b - 1 : a.Hc - 1;
+        s.nrows = r_last - s.r_first + 1;
+    } else {
+        s.cbase = s.col0;
+        s.r_first = row_a;
+        s.nrows = row_b - row_a;
+    }
     pos = end;
     return true;
 }
@@ -89,21 +100,68 @@ __device__ __forceinline__ int input_log2_scale(const StemTcArgs& a) {
     return sx < -60 ? -60 : (sx > 60 ? 60 : sx);
 }
 
-__device__ __forceinline__ void split8(const float (&v)[8], float xs, uint4& hi, uint4& lo) {
-    uint32_t h[4], l[4];
+// two input rows (y, y + 1) x 3 channels x the unit's column pair, as they come from memory
+template <int IN> struct Raw2 { float2 v[2][3]; };
+template <> struct Raw2<1> { unsigned short v[2][3]; };              // uint8 NHWC: 6 bytes per row = three 16-bit loads
+
+template <int IN>
+__device__ __forceinline__ void load2(const StemTcArgs& a, int n, int y, int colL, Raw2<IN>& r) {
+    const bool cok = (unsigned)colL < (unsigned)a.W;                 // colL is even and (vector path) W is even: pair in or out
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float a = v[2 * i] * xs, b = v[2 * i + 1] * xs;
-        const __half2 hh = __floats2half2_rn(a, b);
-        const float2 hf = __half22float2(hh);
-        const __half2 ll = __floats2half2_rn(a - hf.x, b - hf.y);
-        h[i] = *reinterpret_cast<const uint32_t*>(&hh);
-        l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+    for (int i = 0; i < 2; ++i) {
+        const int yy = y + i;
+        const bool ok = cok && (unsigned)yy < (unsigned)a.H;
+        if constexpr (IN == 0) {
+            const float* x = reinterpret_cast<const float*>(a.x);
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci) {
+                const float* p = x + (((size_t)n * 3 + ci) * a.H + (ok ? yy : 0)) * a.W + (ok ? colL : 0);
+                if (a.vec2) {
+                    r.v[i][ci] = ok ? __ldg(reinterpret_cast<const float2*>(p)) : make_float2(0.0f, 0.0f);
+                } else {                                             // odd W: element-wise, the right column may be outside
+                    const bool ok1 = ok && colL + 1 < a.W;
+                    r.v[i][ci].x = ok ? __ldg(p) : 0.0f;
+                    r.v[i][ci].y = ok1 ? __ldg(p + 1) : 0.0f;
+                }
+            }
+        } else {
+            const unsigned short* p = reinterpret_cast<const unsigned short*>(
+                reinterpret_cast<const unsigned char*>(a.x) + (((size_t)n * a.H + (ok ? yy : 0)) * a.W + (ok ? colL : 0)) * 3);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) r.v[i][k] = ok ? __ldg(p + k) : (unsigned short)0;        // cvt2 zeroes outside positions
+        }
     }
-    hi = make_uint4(h[0], h[1], h[2], h[3]);
-    lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// -> scaled (hi, lo) fp16 pairs: hi[ci][row], lo[ci][row], each the half2 {left column, right column}
+template <int IN>
+__device__ __forceinline__ void cvt2(const StemTcArgs& a, const Raw2<IN>& r, float xs, bool in0, bool in1, uint32_t (&hi)[3][2], uint32_t (&lo)[3][2]) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) {
+            float l, rr;
+            if constexpr (IN == 0) {
+                l = r.v[i][ci].x; rr = r.v[i][ci].y;
+            } else {
+                // bytes of a row: [c0 ch0, c0 ch1, c0 ch2, c1 ch0, c1 ch1, c1 ch2]; normalisation = two rounded fp32 operations
+                const uint32_t w01 = r.v[i][0], w23 = r.v[i][1], w45 = r.v[i][2];
+                const uint32_t b0 = ci == 0 ? (w01 & 0xff) : ci == 1 ? (w01 >> 8) : (w23 & 0xff);
+                const uint32_t b1 = ci == 0 ? (w23 >> 8) : ci == 1 ? (w45 & 0xff) : (w45 >> 8);
+                l = __fmul_rn(__fsub_rn((float)b0, a.u8_mean[ci]), a.u8_istd[ci]);
+                rr = __fmul_rn(__fsub_rn((float)b1, a.u8_mean[ci]), a.u8_istd[ci]);
+                if (!(i ? in1 : in0)) { l = 0.0f; rr = 0.0f; }       // zero padding of the NORMALISED image
+            }
+            const float sa = l * xs, sb = rr * xs;
+            const __half2 hh = __floats2half2_rn(sa, sb);
+            const float2 hf = __half22float2(hh);
+            const __half2 ll = __floats2half2_rn(sa - hf.x, sb - hf.y);
+            hi[ci][i] = *reinterpret_cast<const uint32_t*>(&hh);
+            lo[ci][i] = *reinterpret_cast<const uint32_t*>(&ll);
+        }
+}
+
+template <bool POOL, int IN>
 __global__ void __launch_bounds__(TC_THREADS, 1) stem_tc_kernel(const __grid_constant__ StemTcArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);             // [TC_D]   converters -> MMA
@@ -112,7 +170,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) stem_tc_kernel(const __grid_con
     uint64_t* acc_empty = acc_full + TC_STAGES;                     // [TC_STAGES] epilogue -> MMA
     uint64_t* bbar = acc_empty + TC_STAGES;                         // weights landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bbar + 1);
-    float* consts = reinterpret_cast<float*>(smem + TC_OFF_CONST);  // [4][64]: bn_scale, bn_shift, nx_scale, nx_shift
+    float* consts = reinterpret_cast<float*>(smem + TC_OFF_CONST);  // [6][64]: bn_scale * 2^-(sx+sw), bn_shift, nx, nx2
     unsigned char* b_s = smem + TC_OFF_B;
     unsigned char* ring = smem + TC_OFF_RING;
     float* vbuf = reinterpret_cast<float*>(smem + TC_OFF_VBUF);
@@ -132,56 +190,61 @@ __global__ void __launch_bounds__(TC_THREADS, 1) stem_tc_kernel(const __grid_con
         __syncwarp();
         tc05::tmem_alloc<512>(tmem_slot);
     }
-    for (int i = tid; i < 256; i += TC_THREADS) {
+    const int sx = input_log2_scale(a);
+    for (int i = tid; i < 384; i += TC_THREADS) {
         const int which = i >> 6, c = i & 63;
-        const float* src = which == 0 ? a.bn_scale : which == 1 ? a.bn_shift : which == 2 ? a.nx_scale : a.nx_shift;
-        consts[i] = src ? __ldg(src + c) : (which == 2 ? 1.0f : 0.0f);
+        const float* src = which == 0 ? a.bn_scale : which == 1 ? a.bn_shift : which == 2 ? a.nx_scale
+                         : which == 3 ? a.nx_shift : which == 4 ? a.nx2_scale : a.nx2_shift;
+        float v = src ? __ldg(src + c) : ((which & 1) ? 0.0f : 1.0f);
+        // the accumulators hold conv * 2^(sx+sw): a power of two folds into the BatchNorm scale exactly
+        if (which == 0) v *= pow2f(-(sx + a.w_log2_scale));
+        consts[i] = v;
     }
     tc05::fence_before_sync();
     __syncthreads();
     tc05::fence_after_sync();
     const uint32_t tmem = *tmem_slot;
-    const int sx = input_log2_scale(a);
 
     if (warp < TC_CONV_WARPS) {
-        // =================== converters: fp32 input rows -> (hi, lo) fp16 units of a group ===================
+        // =================== converters: input rows -> (hi, lo) fp16 units; thread u owns unit u of every group ==========
+        // group k = input rows 2(r_first+k)-3 .. +3; consecutive groups share two rows, so per group two NEW rows are
+        // loaded (prefetched one group ahead), converted once and kept for the next group
         const float xs = pow2f(sx);
+        const int u = tid;
         long long pos = lo_row, K = 0;
         Seg s;
-        while (next_seg(pos, hi_row, a, s)) {
-            const float* xn = a.x + (size_t)s.n * 3 * a.H * a.W;
+        while (next_seg<POOL>(pos, hi_row, a, s)) {
+            const int colL = 2 * (s.cbase - 2 + u);                 // unit u <-> input columns (colL, colL + 1)
+            const bool cin = (unsigned)colL < (unsigned)a.W;
             const int ngroups = s.nrows + 2;
+            int y = 2 * s.r_first - 3;
+            Raw2<IN> ra, rb;
+            load2<IN>(a, s.n, y, colL, ra);
+            load2<IN>(a, s.n, y + 2, colL, rb);
+            uint32_t phi[3][2], plo[3][2];
+            cvt2<IN>(a, ra, xs, cin && (unsigned)y < (unsigned)a.H, cin && (unsigned)(y + 1) < (unsigned)a.H, phi, plo);
             for (int k = 0; k < ngroups; ++k, ++K) {
+                // rb holds rows y + 2, y + 3 (the new half of group k); prefetch the new half of group k + 1
+                Raw2<IN> rn;
+                if (k + 1 < ngroups) load2<IN>(a, s.n, y + 4, colL, rn);
+                uint32_t chi[3][2], clo[3][2];
+                cvt2<IN>(a, rb, xs, cin && (unsigned)(y + 2) < (unsigned)a.H, cin && (unsigned)(y + 3) < (unsigned)a.H, chi, clo);
                 const int slot = (int)(K % TC_D);
                 const long long use = K / TC_D;
                 if (use > 0) mbar_wait(empty + slot, (uint32_t)((use - 1) & 1));
-                unsigned char* sb = ring + (size_t)slot * TC_SLOT;
-                const int y0 = 2 * (s.r_first + k) - 3;
-                for (int u = tid; u < TC_NU; u += TC_CONV_WARPS * 32) {
-                    const int c0 = 4 * s.pc0 - 5 + 2 * u;
-                    const bool ok0 = (unsigned)c0 < (unsigned)a.W, ok1 = (unsigned)(c0 + 1) < (unsigned)a.W;
-                    float v[3][8];
+                unsigned char* sb = ring + (size_t)slot * TC_SLOT + (size_t)u * 16;
 #pragma unroll
-                    for (int ci = 0; ci < 3; ++ci)
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int y = y0 + i;
-                            const bool rok = (unsigned)y < (unsigned)a.H;
-                            const float* p = xn + ((size_t)ci * a.H + (rok ? y : 0)) * a.W + c0;
-                            v[ci][2 * i] = (rok && ok0) ? __ldg(p) : 0.0f;
-                            v[ci][2 * i + 1] = (rok && ok1) ? __ldg(p + 1) : 0.0f;
-                        }
-#pragma unroll
-                    for (int ci = 0; ci < 3; ++ci) {
-                        uint4 hi, lo;
-                        split8(v[ci], xs, hi, lo);
-                        *reinterpret_cast<uint4*>(sb + ((size_t)(ci * 2 + 0) * TC_NU + u) * 16) = hi;
-                        *reinterpret_cast<uint4*>(sb + ((size_t)(ci * 2 + 1) * TC_NU + u) * 16) = lo;
-                    }
+                for (int ci = 0; ci < 3; ++ci) {
+                    *reinterpret_cast<uint4*>(sb + (size_t)(ci * 2 + 0) * TC_NU * 16) = make_uint4(phi[ci][0], phi[ci][1], chi[ci][0], chi[ci][1]);
+                    *reinterpret_cast<uint4*>(sb + (size_t)(ci * 2 + 1) * TC_NU * 16) = make_uint4(plo[ci][0], plo[ci][1], clo[ci][0], clo[ci][1]);
                 }
                 fence_proxy_async();                  // generic-proxy stores -> visible to the tensor core's async proxy
                 __syncwarp();
                 if (lane == 0) tc05::mbar_arrive(full + slot);
+#pragma unroll
+                for (int ci = 0; ci < 3; ++ci) { phi[ci][0] = chi[ci][0]; phi[ci][1] = chi[ci][1]; plo[ci][0] = clo[ci][0]; plo[ci][1] = clo[ci][1]; }
+                if (k + 1 < ngroups) rb = rn;
+                y += 2;
             }
         }
     } else if (warp == TC_CONV_WARPS + TC_EPI_WARPS) {
@@ -191,7 +254,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) stem_tc_kernel(const __grid_con
         const uint32_t ring_u = smem_u32(ring), b_u = smem_u32(b_s);
         long long pos = lo_row, K = 0, J = 0;
         Seg s;
-        while (next_seg(pos, hi_row, a, s)) {
+        while (next_seg<POOL>(pos, hi_row, a, s)) {
             for (int j = 0; j < s.nrows; ++j, ++J) {
                 const int stage = (int)(J % TC_STAGES);
                 const long long ause = J / TC_STAGES;
@@ -225,22 +288,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) stem_tc_kernel(const __grid_con
             K += s.nrows + 2;
         }
     } else {
-        // =================== epilogue: TMEM -> BN + ReLU -> vertical max (registers) -> horizontal max -> NHWC + planes
+        // =================== epilogue: TMEM -> BN (+ ReLU) -> [vertical max in registers] -> lanes <-> channels -> NHWC + planes
         const int e = warp - TC_CONV_WARPS;            // 0..7
         const int lq = warp & 3;                       // TMEM lane quarter this warp may read
         const int cb = 32 * (e >> 2);                  // channel half
         const int m = 32 * lq + lane;                  // conv column inside the M tile
-        const float inv_scale = pow2f(-(sx + a.w_log2_scale));
-        const bool has_nx = a.nx_scale != nullptr;
+        const bool has_nx = a.nx_scale != nullptr, has_nx2 = a.nx2_scale != nullptr;
         long long pos = lo_row, J = 0;
         int emits = 0;
         Seg s;
-        while (next_seg(pos, hi_row, a, s)) {
-            const int c = 2 * s.pc0 - 1 + m;
+        while (next_seg<POOL>(pos, hi_row, a, s)) {
+            const int c = s.cbase + m;
             const bool col_ok = (unsigned)c < (unsigned)a.Wc;
             float state[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) state[i] = 0.0f;
+            for (int i = 0; i < 32; ++i) state[i] = 0.0f;            // 0 = max-pool padding after the ReLU (and the ReLU itself)
             for (int j = 0; j < s.nrows; ++j, ++J) {
                 const int r = s.r_first + j;
                 const int stage = (int)(J % TC_STAGES);
@@ -258,47 +320,62 @@ __global__ void __launch_bounds__(TC_THREADS, 1) stem_tc_kernel(const __grid_con
                         const float4 h = *reinterpret_cast<const float4*>(consts + 64 + cb + 16 * hh + i4);
                         const float gg[4] = {g.x, g.y, g.z, g.w}, hv[4] = {h.x, h.y, h.z, h.w};
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float conv = __fadd_rn(p[i4 + i], q[i4 + i]) * inv_scale;
-                            const float v = fmaxf(__fmaf_rn(conv, gg[i], hv[i]), 0.0f);
-                            cur[16 * hh + i4 + i] = col_ok ? v : 0.0f;       // outside the conv output: max-pool padding
-                        }
+                        for (int i = 0; i < 4; ++i) cur[16 * hh + i4 + i] = __fmaf_rn(__fadd_rn(p[i4 + i], q[i4 + i]), gg[i], hv[i]);
                     }
                 }
                 tc05::fence_before_sync();
                 __syncwarp();
                 if (lane == 0) tc05::mbar_arrive(acc_empty + stage);
+                bool emit;
+                int orow;
+                if (POOL) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) state[i] = fmaxf(state[i], cur[i]);
-                const int ph = (r & 1) ? (r - 1) >> 1 : r >> 1;
-                const bool emit = ((r & 1) || r == a.Hc - 1) && ph >= s.ph_a;
+                    for (int i = 0; i < 32; ++i) state[i] = fmaxf(state[i], cur[i]);       // state >= 0: the ReLU is implied
+                    orow = (r & 1) ? (r - 1) >> 1 : r >> 1;
+                    emit = ((r & 1) || r == a.Hc - 1) && orow >= s.row_a;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) state[i] = fmaxf(cur[i], 0.0f);
+                    orow = r;
+                    emit = true;
+                }
                 if (emit) {
                     float* vb = vbuf + (size_t)(emits & 1) * (TC_VBUF / 4);
                     ++emits;
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4)
-                        *reinterpret_cast<float4*>(vb + m * TC_VPITCH + cb + i) = make_float4(state[i], state[i + 1], state[i + 2], state[i + 3]);
+                    for (int i = 0; i < 32; i += 4)                  // columns outside the conv output: max-pool padding (0)
+                        *reinterpret_cast<float4*>(vb + m * TC_VPITCH + cb + i) =
+                            col_ok ? make_float4(state[i], state[i + 1], state[i + 2], state[i + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
                     asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");
-                    // horizontal 3-max, lanes <-> channels: whole 128-byte lines in and out
-                    const size_t prow = ((size_t)s.n * a.Hp + ph) * a.Wp;
-                    for (int jp = e; jp < a.PT; jp += TC_EPI_WARPS) {
-                        const int pc = s.pc0 + jp;
-                        if (pc >= a.Wp) break;
-                        const float* v0 = vb + (2 * jp) * TC_VPITCH + lane;
-                        uint32_t sw[2], mw[2];
+                    // lanes <-> channels: whole 128-byte lines out
+                    const size_t prow = ((size_t)s.n * a.Ho + orow) * a.Wo;
+                    for (int jp = e; jp < a.TW; jp += TC_EPI_WARPS) {
+                        const int oc = s.col0 + jp;
+                        if (oc >= a.Wo) break;
+                        const float* v0 = vb + (POOL ? 2 * jp : jp) * TC_VPITCH + lane;
+                        uint32_t sw[2], mw[2], sw2[2], mw2[2];
 #pragma unroll
                         for (int hb = 0; hb < 2; ++hb) {
-                            const float mx = fmaxf(fmaxf(v0[32 * hb], v0[TC_VPITCH + 32 * hb]), v0[2 * TC_VPITCH + 32 * hb]);
-                            a.out[(prow + pc) * 64 + 32 * hb + lane] = mx;
+                            float mx = v0[32 * hb];
+                            if (POOL) mx = fmaxf(fmaxf(mx, v0[TC_VPITCH + 32 * hb]), v0[2 * TC_VPITCH + 32 * hb]);
+                            a.out[(prow + oc) * 64 + 32 * hb + lane] = mx;
                             const float b = has_nx ? __fmaf_rn(consts[128 + 32 * hb + lane], mx, consts[192 + 32 * hb + lane]) : mx;
                             sw[hb] = __ballot_sync(0xffffffffu, b > 0.0f);
-                            mw[hb] = __ballot_sync(0xffffffffu, b > 0.0f || b < 0.0f);
+                            mw[hb] = a.nx_relu ? sw[hb] : __ballot_sync(0xffffffffu, b > 0.0f || b < 0.0f);
+                            if (has_nx2) {
+                                const float b2 = __fmaf_rn(consts[256 + 32 * hb + lane], mx, consts[320 + 32 * hb + lane]);
+                                sw2[hb] = __ballot_sync(0xffffffffu, b2 > 0.0f);
+                                mw2[hb] = a.nx2_relu ? sw2[hb] : __ballot_sync(0xffffffffu, b2 > 0.0f || b2 < 0.0f);
+                            }
                         }
-                        if (lane == 0 && a.obits) a.obits[prow + pc] = make_uint4(sw[0], sw[1], mw[0], mw[1]);
+                        if (lane == 0) {
+                            if (a.obits) a.obits[prow + oc] = make_uint4(sw[0], sw[1], mw[0], mw[1]);
+                            if (has_nx2 && a.obits2) a.obits2[prow + oc] = make_uint4(sw2[0], sw2[1], mw2[0], mw2[1]);
+                        }
                     }
-                    if (r & 1) {
+                    if (POOL && (r & 1)) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) state[i] = cur[i];      // an odd conv row also opens the next pooled row
+                        for (int i = 0; i < 32; ++i) state[i] = fmaxf(cur[i], 0.0f);       // an odd conv row also opens the next pooled row
                     }
                 }
             }
@@ -311,7 +388,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) stem_tc_kernel(const __grid_con
 
 // conv weight [64,3,7,7] fp32 -> the B operand image: 12 K steps x [wh | wl] rows x 16 K elements, K-major no-swizzle core
 // matrices (8 rows x 16 bytes, the two K chunks 128 bytes apart, 8-row groups 256 bytes apart).
-// K step ks = (grp * 3 + ci) * 2 + pp; K element jj * 8 + i * 2 + b  <->  w[n][ci][kh = 4 grp + i][kw = 4 pp + 2 jj + b].
+// K step ks = (grp * 3 + ci) * 2 + pp; K element jj * 8 + i * 2 + b  <->  w[n][ci][kh = 4 grp + i][kw = 4 pp + 2 jj + b - 1]
+// (units are ALIGNED input column pairs (2q, 2q+1); the conv's left padding of 3 puts the zero tap at kw = -1).
 __global__ void stem_tc_pack_weight_kernel(const float* __restrict__ w, float w_scale, __half* __restrict__ ops) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;       // one fp16 element of the image
     if (idx >= TC_B_BYTES / 2) return;
@@ -319,24 +397,31 @@ __global__ void stem_tc_pack_weight_kernel(const float* __restrict__ w, float w_
     const int n8 = rem / 128, jj = (rem % 128) / 64, nr = (rem % 64) / 8, el = rem % 8;
     const int n = n8 * 8 + nr;                                   // 0..63: wh rows, 64..127: wl rows
     const int grp = ks / 6, ci = (ks >> 1) % 3, pp = ks & 1;
-    const int kh = 4 * grp + (el >> 1), kw = 4 * pp + 2 * jj + (el & 1);
+    const int kh = 4 * grp + (el >> 1), kw = 4 * pp + 2 * jj + (el & 1) - 1;
     float v = 0.0f;
-    if (kh < 7 && kw < 7) v = w[(((n & 63) * 3 + ci) * 7 + kh) * 7 + kw] * w_scale;
+    if (kh < 7 && kw >= 0 && kw < 7) v = w[(((n & 63) * 3 + ci) * 7 + kh) * 7 + kw] * w_scale;
     const __half hi = __float2half_rn(v);
     ops[idx] = n < 64 ? hi : __float2half_rn(v - __half2float(hi));
 }
 
 // max |x| over a tensor (NaN ignored), atomically merged into *amax (which the caller zeroes first)
-__global__ void amax_kernel(const float* __restrict__ x, long long count, float* __restrict__ amax) {
+__global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ x, long long count, float* __restrict__ amax) {
     float m = 0.0f;
-    const long long n4 = count >> 2;
+    const long long n4 = count >> 2, stride = (long long)gridDim.x * blockDim.x;
     const float4* x4 = reinterpret_cast<const float4*>(x);
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n4; i += 4 * stride) {               // four independent 16-byte loads in flight per thread
+        const float4 v0 = __ldg(x4 + i), v1 = __ldg(x4 + i + stride), v2 = __ldg(x4 + i + 2 * stride), v3 = __ldg(x4 + i + 3 * stride);
+        m = fmaxf(m, fmaxf(fmaxf(fmaxf(fabsf(v0.x), fabsf(v0.y)), fmaxf(fabsf(v0.z), fabsf(v0.w))),
+                           fmaxf(fmaxf(fabsf(v1.x), fabsf(v1.y)), fmaxf(fabsf(v1.z), fabsf(v1.w)))));
+        m = fmaxf(m, fmaxf(fmaxf(fmaxf(fabsf(v2.x), fabsf(v2.y)), fmaxf(fabsf(v2.z), fabsf(v2.w))),
+                           fmaxf(fmaxf(fabsf(v3.x), fabsf(v3.y)), fmaxf(fabsf(v3.z), fabsf(v3.w)))));
+    }
+    for (; i < n4; i += stride) {
         const float4 v = __ldg(x4 + i);
         m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
     }
-    for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
-        m = fmaxf(m, fabsf(__ldg(x + i)));
+    for (long long t = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += stride) m = fmaxf(m, fabsf(__ldg(x + t)));
 #pragma unroll
     for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(reinterpret_cast<unsigned int*>(amax), __float_as_uint(m));
@@ -365,9 +450,60 @@ extern "C" int bnn_amax_f32(const float* x, int64_t count, float* amax, void* st
     cudaStream_t stream = (cudaStream_t)stream_;
     cudaError_t ce = cudaMemsetAsync(amax, 0, sizeof(float), stream);
     if (ce != cudaSuccess) return (int)ce;
-    const long long want = (count / 4 + 255) / 256;
+    const long long want = (count / 16 + 255) / 256;
     const int blocks = (int)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
     amax_kernel<<<blocks, 256, 0, stream>>>(x, (long long)count, amax);
+    count_launch(1);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int bnn_stem_tc_run(const bnn_stem_tc_params* p, uint32_t flags, void* stream_) {
+    (void)flags;
+    if (!p) return BNN_E_NULL;
+    if (!p->x || !p->w_ops || !p->bn_scale || !p->bn_shift || !p->out) return BNN_E_NULL;
+    if ((p->nx_scale == nullptr) != (p->nx_shift == nullptr) || (p->nx2_scale == nullptr) != (p->nx2_shift == nullptr)) return BNN_E_NULL;
+    if (p->nx2_scale && !p->out_bits2) return BNN_E_NULL;
+    if (p->n <= 0 || p->h < 7 || p->w < 7) return BNN_E_SHAPE;
+    if (p->x_dtype != 0 && p->x_dtype != 1) return BNN_E_SHAPE;
+    if ((long long)p->h * p->w * 3 >= 0x7fffffffLL) return BNN_E_UNSUPPORTED;
+    if (p->x_log2_scale < -60 || p->x_log2_scale > 60 || p->w_log2_scale < -60 || p->w_log2_scale > 60) return BNN_E_SHAPE;
+    if (((uintptr_t)p->w_ops & 15) || ((uintptr_t)p->out_bits & 15) || ((uintptr_t)p->out_bits2 & 15)) return BNN_E_ALIGN;
+    if (p->x_dtype == 1 && (p->w & 1)) return BNN_E_UNSUPPORTED;            // uint8 rows are read as 16-bit pairs
+    if (p->x_dtype == 1 && ((uintptr_t)p->x & 1)) return BNN_E_ALIGN;
+    StemTcArgs a{};
+    a.x = p->x; a.wops = p->w_ops; a.bn_scale = p->bn_scale; a.bn_shift = p->bn_shift;
+    a.nx_scale = p->nx_scale; a.nx_shift = p->nx_shift; a.nx2_scale = p->nx2_scale; a.nx2_shift = p->nx2_shift;
+    a.nx_relu = p->nx_relu != 0; a.nx2_relu = p->nx2_relu != 0;
+    a.x_amax = p->x_dtype == 0 ? p->x_amax : nullptr; a.out = p->out; a.obits = (uint4*)p->out_bits; a.obits2 = (uint4*)p->out_bits2;
+    for (int i = 0; i < 3; ++i) { a.u8_mean[i] = p->u8_mean[i]; a.u8_istd[i] = p->u8_istd[i]; }
+    a.x_log2_scale = p->x_log2_scale; a.w_log2_scale = p->w_log2_scale;
+    a.vec2 = (p->x_dtype == 0 && (p->w & 1) == 0 && ((uintptr_t)p->x & 7) == 0) ? 1 : 0;
+    a.N = p->n; a.H = p->h; a.W = p->w;
+    a.Hc = (p->h + 6 - 7) / 2 + 1; a.Wc = (p->w + 6 - 7) / 2 + 1;
+    const bool pool = p->pool != 0;
+    a.Ho = pool ? (a.Hc + 2 - 3) / 2 + 1 : a.Hc;
+    a.Wo = pool ? (a.Wc + 2 - 3) / 2 + 1 : a.Wc;
+    const int maxt = pool ? TC_MAX_PT : TC_MAX_CT;
+    a.tiles_w = (a.Wo + maxt - 1) / maxt;
+    a.TW = (a.Wo + a.tiles_w - 1) / a.tiles_w;
+    a.total_rows = (long long)p->n * a.tiles_w * a.Ho;
+    int dev = 0, sms = 148;
+    cudaError_t ce = cudaGetDevice(&dev);
+    if (ce != cudaSuccess) return (int)ce;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const void* fn = pool ? (p->x_dtype ? (const void*)stem_tc_kernel<true, 1> : (const void*)stem_tc_kernel<true, 0>)
+                          : (p->x_dtype ? (const void*)stem_tc_kernel<false, 1> : (const void*)stem_tc_kernel<false, 0>);
+    ce = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM);
+    if (ce != cudaSuccess) return (int)ce;
+    const unsigned ctas = (unsigned)(a.total_rows < sms ? a.total_rows : sms);
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (pool) {
+        if (p->x_dtype) stem_tc_kernel<true, 1><<<ctas, TC_THREADS, TC_SMEM, st>>>(a);
+        else stem_tc_kernel<true, 0><<<ctas, TC_THREADS, TC_SMEM, st>>>(a);
+    } else {
+        if (p->x_dtype) stem_tc_kernel<false, 1><<<ctas, TC_THREADS, TC_SMEM, st>>>(a);
+        else stem_tc_kernel<false, 0><<<ctas, TC_THREADS, TC_SMEM, st>>>(a);
+    }
     count_launch(1);
     return (int)cudaGetLastError();
 }
@@ -376,31 +512,9 @@ extern "C" int bnn_stem_tc_fwd(const float* x, int32_t n, int32_t h, int32_t w, 
                                const float* x_amax, int32_t w_log2_scale, const float* bn_scale, const float* bn_shift,
                                const float* nx_scale, const float* nx_shift, float* out, void* out_bits, uint32_t flags,
                                void* stream_) {
-    (void)flags;
-    if (!x || !w_ops || !bn_scale || !bn_shift || !out) return BNN_E_NULL;
-    if ((nx_scale == nullptr) != (nx_shift == nullptr)) return BNN_E_NULL;
-    if (n <= 0 || h < 7 || w < 7) return BNN_E_SHAPE;
-    if ((long long)h * w * 3 >= 0x7fffffffLL) return BNN_E_UNSUPPORTED;
-    if (x_log2_scale < -60 || x_log2_scale > 60 || w_log2_scale < -60 || w_log2_scale > 60) return BNN_E_SHAPE;
-    if (((uintptr_t)w_ops & 15) || ((uintptr_t)out_bits & 15)) return BNN_E_ALIGN;
-    StemTcArgs a{};
-    a.x = x; a.wops = w_ops; a.bn_scale = bn_scale; a.bn_shift = bn_shift; a.nx_scale = nx_scale; a.nx_shift = nx_shift;
-    a.x_amax = x_amax; a.out = out; a.obits = (uint4*)out_bits;
-    a.x_log2_scale = x_log2_scale; a.w_log2_scale = w_log2_scale;
-    a.N = n; a.H = h; a.W = w;
-    a.Hc = (h + 6 - 7) / 2 + 1; a.Wc = (w + 6 - 7) / 2 + 1;
-    a.Hp = (a.Hc + 2 - 3) / 2 + 1; a.Wp = (a.Wc + 2 - 3) / 2 + 1;
-    a.tiles_w = (a.Wp + TC_MAX_PT - 1) / TC_MAX_PT;
-    a.PT = (a.Wp + a.tiles_w - 1) / a.tiles_w;
-    a.total_rows = (long long)n * a.tiles_w * a.Hp;
-    int dev = 0, sms = 148;
-    cudaError_t ce = cudaGetDevice(&dev);
-    if (ce != cudaSuccess) return (int)ce;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    ce = cudaFuncSetAttribute((const void*)stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM);
-    if (ce != cudaSuccess) return (int)ce;
-    const long long ctas = a.total_rows < sms ? a.total_rows : sms;
-    stem_tc_kernel<<<(unsigned)ctas, TC_THREADS, TC_SMEM, (cudaStream_t)stream_>>>(a);
-    count_launch(1);
-    return (int)cudaGetLastError();
+    bnn_stem_tc_params p{};
+    p.x = x; p.x_dtype = 0; p.n = n; p.h = h; p.w = w; p.w_ops = w_ops; p.w_log2_scale = w_log2_scale;
+    p.x_log2_scale = x_log2_scale; p.x_amax = x_amax; p.bn_scale = bn_scale; p.bn_shift = bn_shift; p.pool = 1;
+    p.nx_scale = nx_scale; p.nx_shift = nx_shift; p.out_bits = out_bits; p.out = out;
+    return bnn_stem_tc_run(&p, flags, stream_);
 }

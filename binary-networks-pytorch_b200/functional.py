@@ -81,6 +81,29 @@ def pack_activations(x: torch.Tensor, linear_rows: bool = False, pre: Optional[T
     return PackedActivations(bits, n, c, ho, wo)
 
 
+def avgpool2_pack(x: torch.Tensor, pre: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, pre_relu: bool = False,
+                  want_pooled: bool = True):
+    """``nn.AvgPool2d(2)`` of a dense channels_last fp32 tensor fused with the bit-pack of the next binarized layer
+    (``bnn_avgpool2_pack_cl_f32``): one pass over ``x``.  Returns (pooled channels_last tensor or None,
+    PackedActivations of ``sign(pooled * pre[0] + pre[1])``)."""
+    _require_cuda_f32(x, "input")
+    if x.dim() != 4 or not x.is_contiguous(memory_format=torch.channels_last):
+        raise native.NativeError("avgpool2_pack expects a dense channels_last [n,c,h,w] tensor")
+    n, c, h, w = x.shape
+    ho, wo = h // 2, w // 2
+    dev = x.device
+    ps, ph = (None, None) if pre is None else (pre[0].data_ptr(), pre[1].data_ptr())
+    with torch.cuda.device(dev):
+        pooled = (torch.empty((n, c, ho, wo), dtype=torch.float32, device=dev, memory_format=torch.channels_last)
+                  if want_pooled else None)
+        bits = torch.empty((n, (c + 63) // 64, ho, wo, 4), dtype=torch.int32, device=dev)
+        rc = native.lib().bnn_avgpool2_pack_cl_f32(x.data_ptr(), n, c, h, w, ps, ph, int(pre_relu),
+                                                   None if pooled is None else pooled.data_ptr(), bits.data_ptr(),
+                                                   _stream_ptr(dev))
+    native.check(rc, "bnn_avgpool2_pack_cl_f32")
+    return pooled, PackedActivations(bits, n, c, ho, wo)
+
+
 def pack_weights(weight: torch.Tensor, center_weights: bool, compute_alpha: bool) -> PackedWeights:
     """``XNORWeightBinarizer`` (reference bnn/ops.py:129-140) as a prepare-time pack.  A tensor with exactly-zero
     (centred) weights -- sign 0 in the reference, bnn/ops.py:66,136 -- comes back with ``hi`` set: a second set of
@@ -471,11 +494,67 @@ def stem_tc_weights(w: torch.Tensor):
     return ops, log2_scale
 
 
+def u8_log2_scale(mean, istd) -> int:
+    """Input scale of the split-fp16 stems for uint8 images normalised as (x - mean) * istd: the largest possible
+    |value| is known, so no measuring pass is needed."""
+    bound = max(max(abs(0.0 - m), abs(255.0 - m)) * abs(s) for m, s in zip(mean, istd))
+    return max(-60, min(60, 15 - math.frexp(float(bound))[1])) if bound > 0 else 0
+
+
 def stem_tc(x: torch.Tensor, wops, bn: Tuple[torch.Tensor, torch.Tensor], nx=None, want_bits: bool = True,
-            x_log2_scale: int = STEM_X_LOG2_SCALE, flags: int = 0, guard=False):
-    """``stem`` on the tcgen05 tensor cores (``bnn_stem_tc_fwd``, csrc/stem_tc.cu): split-fp16 operands, accumulators in
-    tensor memory.  ``wops`` = ``stem_tc_weights(conv.weight)``; ``guard`` as in ``stem_mma``.  Same outputs as ``stem``."""
-    return _stem_split("tc", x, wops, bn, nx, want_bits, x_log2_scale, guard, flags)
+            x_log2_scale: int = STEM_X_LOG2_SCALE, flags: int = 0, guard=False, pool: bool = True, nx_relu: bool = False,
+            nx2=None, nx2_relu: bool = False, u8_norm=None):
+    """The fp32 stem on the tcgen05 tensor cores (``bnn_stem_tc_run``, csrc/stem_tc.cu): split-fp16 operands,
+    accumulators in tensor memory.  ``wops`` = ``stem_tc_weights(conv.weight)``; ``guard`` as in ``stem_mma``.
+    ``pool=False`` drops the max-pool (conv-BN-ReLU, the Hierarchical-Block harness stem); ``nx2`` asks for a second set
+    of planes from the same output; ``nx_relu`` / ``nx2_relu`` put a ReLU in front of the respective sign.
+    ``u8_norm=(mean[3], istd[3])``: ``x`` is a uint8 [n,h,w,3] image batch, normalised in the kernel as
+    ``(x.float() - mean) * istd``.  Returns (out channels_last, planes) or (out, planes, planes2) with ``nx2``."""
+    if u8_norm is None:
+        _require_cuda_f32(x, "input")
+        if x.dim() != 4 or x.shape[1] != 3 or not x.is_contiguous():
+            raise native.NativeError(f"stem expects a contiguous [n,3,h,w] tensor, got {tuple(x.shape)}")
+        n, _, h, w = x.shape
+    else:
+        if not x.is_cuda or x.dtype != torch.uint8 or x.dim() != 4 or x.shape[3] != 3 or not x.is_contiguous():
+            raise native.NativeError(f"uint8 stem input must be a contiguous CUDA uint8 [n,h,w,3] tensor, got {tuple(x.shape)} {x.dtype}")
+        n, h, w, _ = x.shape
+    ops, w_log2_scale = wops
+    dev = x.device
+    lib = native.lib()
+    hc, wc = (h + 6 - 7) // 2 + 1, (w + 6 - 7) // 2 + 1
+    ho, wo = ((hc + 2 - 3) // 2 + 1, (wc + 2 - 3) // 2 + 1) if pool else (hc, wc)
+    p = native.StemTcParams()
+    with torch.cuda.device(dev):
+        x_amax = None
+        if u8_norm is not None:
+            mean, istd = [float(v) for v in u8_norm[0]], [float(v) for v in u8_norm[1]]
+            p.x_dtype = 1
+            p.u8_mean = (ctypes.c_float * 3)(*mean)
+            p.u8_istd = (ctypes.c_float * 3)(*istd)
+            x_log2_scale = u8_log2_scale(mean, istd)
+        elif guard is True:
+            x_amax = amax(x)
+        elif isinstance(guard, torch.Tensor):
+            x_amax = guard
+        out = torch.empty((n, 64, ho, wo), dtype=torch.float32, device=dev, memory_format=torch.channels_last)
+        bits = torch.empty((n, 1, ho, wo, 4), dtype=torch.int32, device=dev) if want_bits else None
+        bits2 = torch.empty((n, 1, ho, wo, 4), dtype=torch.int32, device=dev) if nx2 is not None else None
+        p.x, p.n, p.h, p.w, p.w_ops, p.w_log2_scale = x.data_ptr(), n, h, w, ops.data_ptr(), w_log2_scale
+        p.x_log2_scale, p.x_amax = x_log2_scale, (None if x_amax is None else x_amax.data_ptr())
+        p.bn_scale, p.bn_shift, p.pool = bn[0].data_ptr(), bn[1].data_ptr(), int(pool)
+        if nx is not None:
+            p.nx_scale, p.nx_shift = nx[0].data_ptr(), nx[1].data_ptr()
+        p.nx_relu, p.out_bits = int(nx_relu), (None if bits is None else bits.data_ptr())
+        if nx2 is not None:
+            p.nx2_scale, p.nx2_shift, p.nx2_relu, p.out_bits2 = nx2[0].data_ptr(), nx2[1].data_ptr(), int(nx2_relu), bits2.data_ptr()
+        p.out = out.data_ptr()
+        rc = lib.bnn_stem_tc_run(ctypes.byref(p), flags, _stream_ptr(dev))
+    native.check(rc, "bnn_stem_tc_run")
+    pk = None if bits is None else PackedActivations(bits, n, 64, ho, wo)
+    if nx2 is not None:
+        return out, pk, PackedActivations(bits2, n, 64, ho, wo)
+    return out, pk
 
 
 def ubench(which: int, iters: int = 200) -> float:

@@ -156,18 +156,21 @@ def _conv_args(conv: Conv2d):
 class _StemPlan:
     """conv 7x7/2/3 (3->64, fp32, no bias) + BatchNorm + ReLU + MaxPool 3/2/1 (reference resnet.py:85-92)."""
 
-    def __init__(self, model: nn.Module) -> None:
+    def __init__(self, model: nn.Module, need_pool: bool = True) -> None:
         self.ok = False
         conv, bn, pool = getattr(model, "conv1", None), getattr(model, "bn1", None), getattr(model, "maxpool", None)
-        if type(conv) is not nn.Conv2d or not isinstance(bn, nn.BatchNorm2d) or not isinstance(pool, nn.MaxPool2d):
+        if type(conv) is not nn.Conv2d or not isinstance(bn, nn.BatchNorm2d):
+            return
+        if need_pool and not isinstance(pool, nn.MaxPool2d):
             return
         if not isinstance(getattr(model, "relu", None), nn.ReLU) or getattr(model, "stem_type", "basic") != "basic":
             return
         good = (conv.in_channels == 3 and conv.out_channels == 64 and conv.kernel_size == (7, 7) and conv.stride == (2, 2)
                 and conv.padding == (3, 3) and conv.dilation == (1, 1) and conv.groups == 1 and conv.bias is None
                 and conv.padding_mode == "zeros" and bn.track_running_stats)
-        good = good and (_pair(pool.kernel_size) == (3, 3) and _pair(pool.stride) == (2, 2) and _pair(pool.padding) == (1, 1)
-                         and _pair(pool.dilation) == (1, 1) and not pool.ceil_mode)
+        if need_pool:
+            good = good and (_pair(pool.kernel_size) == (3, 3) and _pair(pool.stride) == (2, 2) and _pair(pool.padding) == (1, 1)
+                             and _pair(pool.dilation) == (1, 1) and not pool.ceil_mode)
         if good:
             self.ok, self.conv, self.bn = True, conv, _FoldedBN(bn)
             self.key, self.w_t = None, None
@@ -302,6 +305,17 @@ class FusedResNet(nn.Module):
                                                channels_last=True, **kw)
         return y, bits
 
+    def set_uint8_input(self, mean, std) -> "FusedResNet":
+        """Accept decoded images as uint8 [n,h,w,3] tensors: the tcgen05 stem normalises them while it stages the input
+        window, ``(x.float() - mean) * (1 / std)`` per channel (mean / std on the 0..255 scale, e.g. ImageNet's
+        (123.675, 116.28, 103.53) / (58.395, 57.12, 57.375)) -- a quarter of the host-to-device bytes of an fp32 batch."""
+        mean = [float(v) for v in mean]
+        istd = [float(torch.tensor(1.0, dtype=torch.float32) / torch.tensor(float(v), dtype=torch.float32)) for v in std]
+        if len(mean) != 3 or len(istd) != 3:
+            raise ValueError("mean and std must have three entries")
+        self.u8_norm = (mean, istd)
+        return self
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         m = self.model
         if m.training or (torch.is_grad_enabled() and any(p.requires_grad for p in m.parameters()) and x.requires_grad):
@@ -309,7 +323,16 @@ class FusedResNet(nn.Module):
         with torch.no_grad():
             bits = None
             first = self.plans[0] if self.plans else None
-            if (self.stem is not None and self.stem.ok and first is not None and first.fused and x.is_cuda
+            if x.dtype == torch.uint8:
+                if getattr(self, "u8_norm", None) is None:
+                    raise native.NativeError("uint8 input: call engine.set_uint8_input(mean, std) first")
+                if not (self.stem is not None and self.stem.ok and first is not None and first.fused and x.is_cuda and x.dim() == 4
+                        and x.shape[3] == 3 and self.stem_kernel == "tc"):
+                    raise native.NativeError("uint8 [n,h,w,3] input needs the tcgen05 stem kernel and a fused first block")
+                self.stem_kernel_used = "bnn_stem_tc_fwd(uint8)"
+                x, bits = BF.stem_tc(x.contiguous(), self.stem.tc_weight(), self.stem.bn.get(), nx=self._entry_affine(first),
+                                     u8_norm=self.u8_norm)
+            elif (self.stem is not None and self.stem.ok and first is not None and first.fused and x.is_cuda
                     and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == 3 and min(x.shape[2:]) >= 7):
                 # fp32 stem in one kernel: NHWC residual stream + the first binarized conv's planes
                 self.stem_kernel_used = {"mma": "bnn_stem_mma_fwd", "fma": "bnn_stem_fwd", "tc": "bnn_stem_tc_fwd"}[self.stem_kernel]
@@ -367,14 +390,17 @@ class _HBlockPlan:
             self.convs, self.bns = convs, [_FoldedBN(b) for b in bns]
 
 
-def run_hblock(plan: _HBlockPlan, x: torch.Tensor, bits=None) -> torch.Tensor:
-    """One fused HBlock on a channels_last fp32 tensor: 3 (+2 with a shortcut conv) launches after the input pack."""
+def run_hblock(plan: _HBlockPlan, x: torch.Tensor, bits=None, shortcut_bits=None) -> torch.Tensor:
+    """One fused HBlock on a channels_last fp32 tensor: 3 (+2 with a shortcut conv) launches after the input pack.
+    ``bits`` / ``shortcut_bits``: the planes of relu(bn1(x)) / relu(bn_shortcut(x)) when the producer already emitted them."""
     if bits is None:
         bits = BF.pack_activations(x, pre=plan.bns[0].get(), pre_relu=True)
     if plan.shortcut is not None:
         bn_d, conv_d = plan.shortcut
         kw, wts = _conv_args(conv_d)
-        res, _ = BF.bconv2d_fused(BF.pack_activations(x, pre=bn_d.get(), pre_relu=True), wts, channels_last=True, **kw)
+        if shortcut_bits is None:
+            shortcut_bits = BF.pack_activations(x, pre=bn_d.get(), pre_relu=True)
+        res, _ = BF.bconv2d_fused(shortcut_bits, wts, channels_last=True, **kw)
     else:
         res = x
     n, _, h, w = x.shape
@@ -396,10 +422,15 @@ class FusedHBlockNet(nn.Module):
     """Engine for the Hierarchical-Block harness of BASELINE configs[3] (``workloads.HBlockNet`` layout:
     conv1/bn1/relu, block0, pool, blocks, avgpool, fc): fp32 stem and pooling stay torch ops, every HBlock is fused."""
 
-    def __init__(self, model: nn.Module) -> None:
+    def __init__(self, model: nn.Module, fuse_stem: bool = True, input_range: float = None) -> None:
         super().__init__()
         self.model = model
         self.plans = [_HBlockPlan(model.block0)] + [_HBlockPlan(b) for b in model.blocks]
+        self.stem = _StemPlan(model, need_pool=False) if fuse_stem else None
+        self.stem_kernel_used = "torch"
+        self.input_range = input_range
+        self._x_log2_scale = (BF.STEM_X_LOG2_SCALE if input_range is None
+                              else max(-60, min(60, 15 - math.frexp(float(input_range))[1])))
 
     @property
     def fused_blocks(self) -> int:
@@ -412,17 +443,42 @@ class FusedHBlockNet(nn.Module):
                     bn.key = None
                 if p.shortcut is not None:
                     p.shortcut[0].key = None
+        if self.stem is not None and self.stem.ok:
+            self.stem.bn.key = self.stem.key = self.stem.mma_key = self.stem.tc_key = None
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         m = self.model
         if m.training:
             raise native.NativeError("FusedHBlockNet is an inference engine: call model.eval()")
         with torch.no_grad():
-            x = m.relu(m.bn1(m.conv1(x))).contiguous(memory_format=torch.channels_last)
-            x = run_hblock(self.plans[0], x) if self.plans[0].ok else m.block0(x)
-            x = m.pool(x)
-            for plan in self.plans[1:]:
-                x = run_hblock(plan, x) if plan.ok else plan.block(x)
+            p0 = self.plans[0]
+            if (self.stem is not None and self.stem.ok and p0.ok and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
+                    and x.shape[1] == 3 and min(x.shape[2:]) >= 7):
+                # conv7x7/2 + BN + ReLU on the tcgen05 stem kernel (no max-pool): NHWC fp32 + the planes of block0's
+                # conv1 (bn1-ReLU-sign) and of its shortcut conv (its own BatchNorm) in one launch
+                self.stem_kernel_used = "bnn_stem_tc_fwd(no pool)"
+                nx2 = p0.shortcut[0].get() if p0.shortcut is not None else None
+                res = BF.stem_tc(x.contiguous(), self.stem.tc_weight(), self.stem.bn.get(), nx=p0.bns[0].get(), nx_relu=True,
+                                 nx2=nx2, nx2_relu=True, pool=False, guard=self.input_range is None,
+                                 x_log2_scale=self._x_log2_scale)
+                x = run_hblock(p0, res[0], res[1], res[2] if nx2 is not None else None)
+            else:
+                x = m.relu(m.bn1(m.conv1(x))).contiguous(memory_format=torch.channels_last)
+                x = run_hblock(p0, x) if p0.ok else m.block0(x)
+            bits = None
+            nxt = self.plans[1] if len(self.plans) > 1 else None
+            pool = m.pool
+            fusable_pool = (isinstance(pool, nn.AvgPool2d) and _pair(pool.kernel_size) == (2, 2) and _pair(pool.stride) == (2, 2)
+                            and _pair(pool.padding) == (0, 0) and not pool.ceil_mode and pool.divisor_override is None
+                            and nxt is not None and nxt.ok and x.shape[1] in (64, 128, 256, 512)
+                            and x.is_contiguous(memory_format=torch.channels_last))
+            if fusable_pool:
+                # pool + the next block's bn1-ReLU-sign in one pass over the 1 GB tensor
+                x, bits = BF.avgpool2_pack(x, pre=nxt.bns[0].get(), pre_relu=True)
+            else:
+                x = pool(x)
+            for i, plan in enumerate(self.plans[1:]):
+                x = run_hblock(plan, x, bits if i == 0 else None) if plan.ok else plan.block(x)
             return m.fc(torch.flatten(m.avgpool(x), 1))
 
 
@@ -439,7 +495,7 @@ def optimize(model: nn.Module, fuse_stem: bool = True, stem: str = "auto", input
         if engine.fused_blocks:
             return engine
     if all(hasattr(model, k) for k in ("conv1", "bn1", "relu", "block0", "pool", "blocks", "avgpool", "fc")):
-        engine = FusedHBlockNet(model)
+        engine = FusedHBlockNet(model, fuse_stem=fuse_stem, input_range=input_range)
         if engine.fused_blocks:
             return engine
     return model

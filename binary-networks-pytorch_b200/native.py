@@ -34,6 +34,16 @@ class Epilogue(ctypes.Structure):
                 ("nx_shift", c_void_p), ("nx_relu", c_int32), ("bits_before_residual", c_int32)]
 
 
+class StemTcParams(ctypes.Structure):
+    """``struct bnn_stem_tc_params`` (include/bnn_b200.h)."""
+    _fields_ = [("x", c_void_p), ("x_dtype", c_int32), ("n", c_int32), ("h", c_int32), ("w", c_int32), ("w_ops", c_void_p),
+                ("w_log2_scale", c_int32), ("x_log2_scale", c_int32), ("x_amax", c_void_p), ("u8_mean", c_float * 3),
+                ("u8_istd", c_float * 3), ("bn_scale", c_void_p), ("bn_shift", c_void_p), ("pool", c_int32),
+                ("nx_scale", c_void_p), ("nx_shift", c_void_p), ("nx_relu", c_int32), ("out_bits", c_void_p),
+                ("nx2_scale", c_void_p), ("nx2_shift", c_void_p), ("nx2_relu", c_int32), ("out_bits2", c_void_p),
+                ("out", c_void_p)]
+
+
 ACT_NONE, ACT_RELU, ACT_PRELU = 0, 1, 2
 
 _SIGNATURES = {
@@ -45,6 +55,8 @@ _SIGNATURES = {
                                  c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
     "bnn_avgpool_pack_f32": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32,
                                      c_int32, c_int32, c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
+    "bnn_avgpool2_pack_cl_f32": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_void_p,
+                                         c_void_p, c_void_p]),
     "bnn_pack_weight_f32": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                                     c_void_p, c_void_p, c_void_p, c_void_p]),
     "bnn_pack_weight_ternary_f32": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
@@ -69,6 +81,7 @@ _SIGNATURES = {
     "bnn_amax_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "bnn_stem_tc_weight_bytes": (c_size_t, []),
     "bnn_stem_tc_pack_weight": (c_int, [c_void_p, c_int32, c_void_p, c_void_p]),
+    "bnn_stem_tc_run": (c_int, [POINTER(StemTcParams), c_uint32, c_void_p]),
     "bnn_stem_tc_fwd": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p]),
     "bnn_shortcut_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,

@@ -103,6 +103,15 @@ int bnn_avgpool_pack_f32(const float *x, int64_t stride_n, int64_t stride_c, int
                          const float *pre_shift, int32_t pre_relu, void *abits, void *stream);
 
 /*
+ * nn.AvgPool2d(2) (kernel = stride = 2, floor mode) of a DENSE channels-last tensor x[n, h, w, c] fused with the bit-pack
+ * above, in one pass over x: pooled_out (may be NULL) receives the pooled fp32 tensor [n, h/2, w/2, c] (channels-last,
+ * the residual stream of the next block), abits the planes of sign(pooled * pre_scale + pre_shift) (pre_relu as above).
+ * Same operation order as bnn_avgpool_pack_f32.  c in {64, 128, 256, 512}, else BNN_E_UNSUPPORTED.
+ */
+int bnn_avgpool2_pack_cl_f32(const float *x, int32_t n, int32_t c, int32_t h, int32_t w, const float *pre_scale,
+                             const float *pre_shift, int32_t pre_relu, float *pooled_out, void *abits, void *stream);
+
+/*
  * XNORWeightBinarizer.forward (bnn/ops.py:129-140) as a prepare-time pack:
  * optional centring over c_in (ops.py:130-132), alpha[co] = mean |w| after
  * centring (ops.py:116-127; 1.0 if !compute_alpha), sign bits -> wbits.
@@ -296,6 +305,39 @@ int bnn_amax_f32(const float *x, int64_t count, float *amax, void *stream);
  */
 size_t bnn_stem_tc_weight_bytes(void);
 int bnn_stem_tc_pack_weight(const float *w, int32_t w_log2_scale, void *w_ops, void *stream);
+
+/*
+ * bnn_stem_tc_run: every form of the tcgen05 stem, described by one struct (bnn_stem_tc_fwd is the fp32 / max-pool form
+ * with positional arguments).
+ *   x_dtype 0: x = fp32 [n,3,h,w] contiguous.
+ *   x_dtype 1: x = uint8 [n,h,w,3] (decoded image bytes, w even); the kernel normalises while it stages the window,
+ *              x' = (float(x) - u8_mean[c]) * u8_istd[c]  (two rounded fp32 operations, i.e. exactly
+ *              `(x.float() - mean) * istd` in torch), then proceeds as for fp32 -- a quarter of the upload bytes.
+ *              x_amax is ignored: choose x_log2_scale from max_c max(|0 - mean|, |255 - mean|) * istd.
+ *   pool 1:    conv7x7/2 -> BatchNorm -> ReLU -> MaxPool 3x3/2/1   (bnn/models/resnet.py:85-92,147-153); out [n,hp,wp,64]
+ *   pool 0:    conv7x7/2 -> BatchNorm -> ReLU                      (the Hierarchical-Block harness stem); out [n,hc,wc,64]
+ *   out_bits  (may be NULL): planes of sign(out * nx_scale + nx_shift), nx_* NULL = identity; nx_relu: a ReLU sits in
+ *              front of the sign (m = s).  out_bits2 / nx2_*: a second set of planes from the same tensor (the HBlock
+ *              harness feeds its first block's conv1 and the shortcut conv from two different BatchNorms).
+ */
+typedef struct bnn_stem_tc_params {
+    const void *x;
+    int32_t x_dtype, n, h, w;
+    const void *w_ops;
+    int32_t w_log2_scale, x_log2_scale;
+    const float *x_amax;
+    float u8_mean[3], u8_istd[3];
+    const float *bn_scale, *bn_shift;
+    int32_t pool;
+    const float *nx_scale, *nx_shift;
+    int32_t nx_relu;
+    void *out_bits;
+    const float *nx2_scale, *nx2_shift;
+    int32_t nx2_relu;
+    void *out_bits2;
+    float *out;
+} bnn_stem_tc_params;
+int bnn_stem_tc_run(const bnn_stem_tc_params *params, uint32_t flags, void *stream);
 int bnn_stem_tc_fwd(const float *x, int32_t n, int32_t h, int32_t w, const void *w_ops, int32_t x_log2_scale,
                     const float *x_amax, int32_t w_log2_scale, const float *bn_scale, const float *bn_shift,
                     const float *nx_scale, const float *nx_shift, float *out, void *out_bits, uint32_t flags,

@@ -214,6 +214,85 @@ def test_stem_tc_matches_mma_stem_on_a_full_batch():
     assert torch.equal(b, b2)
 
 
+@pytest.mark.parametrize("hw", [(64, 64), (256, 256), (37, 52), (9, 520)])
+def test_stem_tc_without_pool_and_two_plane_sets(hw):
+    """pool=False: conv7x7/2 + BN + ReLU (the Hierarchical-Block harness stem) with two sets of ReLU-fed planes from
+    the same output (block0's conv1 and its shortcut conv sit behind different BatchNorms)."""
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal((2, 3) + hw).astype(np.float32)
+    w = (rng.standard_normal((64, 3, 7, 7)) * 0.1).astype(np.float32)
+    g, h = (0.5 + rng.random(64)).astype(np.float32), (rng.standard_normal(64) * 0.3).astype(np.float32)
+    nx = ((0.5 + rng.random(64)).astype(np.float32), (rng.standard_normal(64) * 0.4).astype(np.float32))
+    nx2 = ((0.5 + rng.random(64)).astype(np.float32), (rng.standard_normal(64) * 0.4).astype(np.float32))
+    y = torch.nn.functional.conv2d(torch.from_numpy(x).double(), torch.from_numpy(w).double(), stride=2, padding=3)
+    exact = torch.relu(y * torch.from_numpy(g).double().view(1, -1, 1, 1) + torch.from_numpy(h).double().view(1, -1, 1, 1)).numpy()
+    out, b1, b2 = BF.stem_tc(_d(x), BF.stem_tc_weights(_d(w)), (_d(g), _d(h)), nx=(_d(nx[0]), _d(nx[1])), nx_relu=True,
+                             nx2=(_d(nx2[0]), _d(nx2[1])), nx2_relu=True, pool=False, guard=True)
+    assert out.shape == exact.shape and out.is_contiguous(memory_format=torch.channels_last)
+    got = out.cpu().numpy()
+    assert np.abs(got - exact).max() / np.abs(exact).max() <= 2e-6
+    assert np.array_equal(b1.bits.cpu().numpy().view(np.uint32), co.pack_act(got, pre_scale=nx[0], pre_shift=nx[1], pre_relu=True))
+    assert np.array_equal(b2.bits.cpu().numpy().view(np.uint32), co.pack_act(got, pre_scale=nx2[0], pre_shift=nx2[1], pre_relu=True))
+    # one plane set, no ReLU in front of the sign, identity affine
+    out1, p1 = BF.stem_tc(_d(x), BF.stem_tc_weights(_d(w)), (_d(g), _d(h)), pool=False, guard=True)
+    assert torch.equal(out1, out)
+    assert np.array_equal(p1.bits.cpu().numpy().view(np.uint32), co.pack_act(got))
+
+
+@pytest.mark.parametrize("hw,pool", [((64, 64), True), ((224, 224), True), ((38, 52), True), ((256, 256), False)])
+def test_stem_tc_uint8_input_is_the_fp32_path_on_the_normalised_image(hw, pool):
+    """uint8 [n,h,w,3] input: the kernel normalises while staging, (x.float() - mean) * istd as two rounded fp32
+    operations -- bit-identical to running the fp32 kernel on the tensor torch computes with the same two operations."""
+    torch.manual_seed(11)
+    mean, std = (123.675, 116.28, 103.53), (58.395, 57.12, 57.375)
+    istd = [float(torch.tensor(1.0) / torch.tensor(v)) for v in std]
+    xu = torch.randint(0, 256, (3,) + hw + (3,), dtype=torch.uint8, device=DEV)
+    xf = ((xu.float() - torch.tensor(mean, device=DEV)) * torch.tensor(istd, device=DEV)).permute(0, 3, 1, 2).contiguous()
+    w = torch.randn(64, 3, 7, 7, device=DEV) * 0.1
+    g, h = 0.5 + torch.rand(64, device=DEV), torch.randn(64, device=DEV) * 0.3
+    wops = BF.stem_tc_weights(w)
+    a, abits = BF.stem_tc(xu, wops, (g, h), pool=pool, u8_norm=(mean, istd))
+    b, bbits = BF.stem_tc(xf, wops, (g, h), pool=pool, x_log2_scale=BF.u8_log2_scale(mean, istd))
+    assert torch.equal(a, b) and torch.equal(abits.bits, bbits.bits)
+    with pytest.raises(native.NativeError):
+        BF.stem_tc(xu[:, :, :-1].contiguous(), wops, (g, h), u8_norm=(mean, istd))        # odd width
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 8, 8), (1, 256, 6, 10), (3, 128, 7, 9), (1, 512, 4, 4), (2, 256, 128, 128)])
+def test_avgpool2_pack_fused_kernel_bit_exact(shape):
+    """nn.AvgPool2d(2) + the next block's bn-ReLU-sign in one pass: pooled tensor == torch's, planes == oracle's."""
+    rng = np.random.default_rng(13)
+    x = rng.standard_normal(shape).astype(np.float32)
+    s_, h_ = (0.5 + rng.random(shape[1])).astype(np.float32), (rng.standard_normal(shape[1]) * 0.5).astype(np.float32)
+    xcl = _d(x).contiguous(memory_format=torch.channels_last)
+    pooled, bits = BF.avgpool2_pack(xcl, pre=(_d(s_), _d(h_)), pre_relu=True)
+    want = torch.nn.functional.avg_pool2d(torch.from_numpy(x), 2)
+    assert pooled.is_contiguous(memory_format=torch.channels_last) and torch.equal(pooled.cpu(), want)
+    assert np.array_equal(bits.bits.cpu().numpy().view(np.uint32),
+                          co.pack_act(x, pool=2, ceil_mode=False, pre_scale=s_, pre_shift=h_, pre_relu=True))
+    _, bits2 = BF.avgpool2_pack(xcl, want_pooled=False)
+    assert np.array_equal(bits2.bits.cpu().numpy().view(np.uint32), co.pack_act(x, pool=2, ceil_mode=False))
+    with pytest.raises(native.NativeError):
+        BF.avgpool2_pack(_d(x))                                                        # NCHW
+    with pytest.raises(native.NativeError):
+        BF.avgpool2_pack(torch.zeros(1, 70, 4, 4, device=DEV).contiguous(memory_format=torch.channels_last))
+
+
+def test_fused_resnet_accepts_uint8_images():
+    """engine.set_uint8_input(mean, std): logits equal the engine's own fp32 path on the torch-normalised tensor."""
+    m = build("basic_relu").to(DEV)
+    mean, std = (123.675, 116.28, 103.53), (58.395, 57.12, 57.375)
+    engine = fuse.optimize(m).set_uint8_input(mean, std)
+    xu = torch.randint(0, 256, (4, 96, 96, 3), dtype=torch.uint8, device=DEV)
+    istd = torch.tensor([float(torch.tensor(1.0) / torch.tensor(v)) for v in std], device=DEV)
+    xf = ((xu.float() - torch.tensor(mean, device=DEV)) * istd).permute(0, 3, 1, 2).contiguous()
+    with torch.no_grad():
+        yu = engine(xu)
+        assert engine.stem_kernel_used == "bnn_stem_tc_fwd(uint8)"
+        yf = m(xf)                                                     # per-layer path, torch stem
+    assert rel_err(yu.cpu().numpy(), yf.cpu().numpy()) <= 1e-3
+
+
 def test_amax_kernel():
     torch.manual_seed(1)
     for shape in [(1, 3, 7, 7), (3, 3, 37, 52), (4, 3, 224, 224)]:
