@@ -20,15 +20,17 @@
 //   add.  14 KB of shared-memory operand reads per 96 tensor cycles.
 // * Warp-specialised persistent CTA, one per SM, walking a contiguous range of (image, pooled row):
 //     warps 0-3   convert fp32 input rows to (hi, lo) fp16 units into a 6-deep ring of groups (mbarrier full / empty)
-//     warp 12     one thread issues the MMAs of a conv row into one of 4 TMEM accumulator stages, tcgen05.commit
-//                 releases the stage to the epilogue and the oldest group back to the converters
+//     warp 19     one thread issues the MMAs of a conv row into one of 2 TMEM accumulator stages, tcgen05.commit
+//                 releases the stage to the accumulator warps and the oldest group back to the converters
 //     warps 4-11  tcgen05.ld the accumulators (warp % 4 = TMEM lane quarter, two channel halves), BatchNorm + ReLU, keep
-//                 the running vertical max of the 3 conv rows of a pooled row in REGISTERS (thread = conv column), park
-//                 it in shared memory once per pooled row, then take the horizontal 3-max with lanes <-> channels, store
-//                 NHWC lines and ballot the first binarized layer's planes.
+//                 the running vertical max of the 3 conv rows of a pooled row in REGISTERS (thread = conv column) and
+//                 park it in shared memory once per pooled row (double-buffered, mbarrier full / empty)
+//     warps 12-18 take the horizontal 3-max of a parked row with lanes <-> channels, store NHWC lines and ballot the
+//                 first binarized layer's planes.
 #include "tc05.cuh"
 
 #include <cuda_fp16.h>
+#include <type_traits>
 
 namespace bnn {
 
@@ -40,9 +42,11 @@ constexpr int TC_BSTEP = 4096;                           // [wh (64 rows) | wl (
 constexpr int TC_B_BYTES = TC_KSTEPS * TC_BSTEP;         // 49152
 constexpr int TC_VPITCH = 68;                            // floats per parked conv column (conflict-free STS.128)
 constexpr int TC_VBUF = 128 * TC_VPITCH * 4;             // 34816
-constexpr int TC_STAGES = 4;                             // TMEM accumulator stages of 128 columns
-constexpr int TC_CONV_WARPS = 4, TC_EPI_WARPS = 8;
-constexpr int TC_THREADS = (TC_CONV_WARPS + TC_EPI_WARPS + 1) * 32;      // 416
+constexpr int TC_STAGES = 2;                             // TMEM accumulator stages: [hh0 | sm | hh1] (192 of 256 columns)
+constexpr int TC_STAGE_COLS = 256;
+constexpr int TC_CONV_WARPS = 4, TC_EPI_WARPS = 8, TC_OUT_WARPS = 7;
+constexpr int TC_MMA_WARP = TC_CONV_WARPS + TC_EPI_WARPS + TC_OUT_WARPS;  // 19
+constexpr int TC_THREADS = (TC_MMA_WARP + 1) * 32;                        // 640: 96 registers per thread
 constexpr int TC_OFF_CONST = 256, TC_OFF_B = 2048, TC_OFF_RING = TC_OFF_B + TC_B_BYTES;
 constexpr int TC_OFF_VBUF = TC_OFF_RING + TC_D * TC_SLOT;
 constexpr int TC_SMEM = TC_OFF_VBUF + 2 * TC_VBUF;                        // 194560
@@ -59,6 +63,8 @@ struct StemTcArgs {
     uint4 *obits, *obits2;    // [n][1][rows][cols] planes of sign(out*nx + nx_shift) / sign(out*nx2 + nx2_shift)
     float u8_mean[3], u8_istd[3];
     int x_log2_scale, w_log2_scale, nx_relu, nx2_relu, vec2;
+    int dbg;                  // timing experiments only (flags >> 8 of bnn_stem_tc_run): 1 accumulator warps idle, 2 output warps idle,
+                              // 4 converters idle, 8 no MMAs -- results are then garbage
     int N, H, W, Hc, Wc, Ho, Wo, tiles_w, TW;   // Ho x Wo: output rows / cols (pooled or conv); TW: output cols per tile
     long long total_rows;     // N * tiles_w * Ho output rows, split evenly over the CTAs
 };
@@ -161,6 +167,13 @@ __device__ __forceinline__ void cvt2(const StemTcArgs& a, const Raw2<IN>& r, flo
         }
 }
 
+// timing experiments (dbg & 16): CTA 0 records clock64() stamps of its roles into the buffer passed as out_bits2:
+// tl[role][event index][slot], role 0 converter warp 0, 1 MMA issuer, 2 accumulator warp 4, 3 output warp 12; 4 slots per event
+#define TC_TL(role, idx, slot)                                                                                         \
+    do {                                                                                                               \
+        if (tl != nullptr && lane == 0 && (idx) < 512) tl[((role) * 512 + (idx)) * 4 + (slot)] = clock64();            \
+    } while (0)
+
 template <bool POOL, int IN>
 __global__ void __launch_bounds__(TC_THREADS, 1) stem_tc_kernel(const __grid_constant__ StemTcArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -169,19 +182,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) stem_tc_kernel(const __grid_con
     uint64_t* acc_full = empty + TC_D;                              // [TC_STAGES] MMA (commit) -> epilogue
     uint64_t* acc_empty = acc_full + TC_STAGES;                     // [TC_STAGES] epilogue -> MMA
     uint64_t* bbar = acc_empty + TC_STAGES;                         // weights landed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bbar + 1);
+    uint64_t* vfull = bbar + 1;                                     // [2] accumulator warps -> output warps (parked rows)
+    uint64_t* vempty = vfull + 2;                                   // [2] output warps -> accumulator warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(vempty + 2);
     float* consts = reinterpret_cast<float*>(smem + TC_OFF_CONST);  // [6][64]: bn_scale * 2^-(sx+sw), bn_shift, nx, nx2
     unsigned char* b_s = smem + TC_OFF_B;
     unsigned char* ring = smem + TC_OFF_RING;
     float* vbuf = reinterpret_cast<float*>(smem + TC_OFF_VBUF);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    long long* const tl = ((a.dbg & 16) && blockIdx.x == 0) ? reinterpret_cast<long long*>(a.obits2) : nullptr;
     const long long lo_row = a.total_rows * blockIdx.x / gridDim.x, hi_row = a.total_rows * (blockIdx.x + 1) / gridDim.x;
 
-    if (warp == TC_CONV_WARPS + TC_EPI_WARPS) {
+    if (warp == TC_MMA_WARP) {
         if (lane == 0) {
             for (int i = 0; i < TC_D; ++i) { mbar_init(full + i, TC_CONV_WARPS); mbar_init(empty + i, 1); }
             for (int i = 0; i < TC_STAGES; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, TC_EPI_WARPS); }
+            for (int i = 0; i < 2; ++i) { mbar_init(vfull + i, TC_EPI_WARPS); mbar_init(vempty + i, TC_OUT_WARPS); }
             mbar_init(bbar, 1);
             fence_mbar_init();
             mbar_expect_tx(bbar, (unsigned)TC_B_BYTES);
@@ -226,13 +243,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) stem_tc_kernel(const __grid_con
             for (int k = 0; k < ngroups; ++k, ++K) {
                 // rb holds rows y + 2, y + 3 (the new half of group k); prefetch the new half of group k + 1
                 Raw2<IN> rn;
-                if (k + 1 < ngroups) load2<IN>(a, s.n, y + 4, colL, rn);
+                if (k + 1 < ngroups && !(a.dbg & 4)) load2<IN>(a, s.n, y + 4, colL, rn);
                 uint32_t chi[3][2], clo[3][2];
                 cvt2<IN>(a, rb, xs, cin && (unsigned)(y + 2) < (unsigned)a.H, cin && (unsigned)(y + 3) < (unsigned)a.H, chi, clo);
                 const int slot = (int)(K % TC_D);
                 const long long use = K / TC_D;
+                if (warp == 0) TC_TL(0, (int)K, 0);
                 if (use > 0) mbar_wait(empty + slot, (uint32_t)((use - 1) & 1));
+                if (warp == 0) TC_TL(0, (int)K, 1);
                 unsigned char* sb = ring + (size_t)slot * TC_SLOT + (size_t)u * 16;
+                if (!(a.dbg & 4))
 #pragma unroll
                 for (int ci = 0; ci < 3; ++ci) {
                     *reinterpret_cast<uint4*>(sb + (size_t)(ci * 2 + 0) * TC_NU * 16) = make_uint4(phi[ci][0], phi[ci][1], chi[ci][0], chi[ci][1]);
@@ -241,152 +261,263 @@ __global__ void __launch_bounds__(TC_THREADS, 1) stem_tc_kernel(const __grid_con
                 fence_proxy_async();                  // generic-proxy stores -> visible to the tensor core's async proxy
                 __syncwarp();
                 if (lane == 0) tc05::mbar_arrive(full + slot);
+                if (warp == 0) TC_TL(0, (int)K, 2);
 #pragma unroll
                 for (int ci = 0; ci < 3; ++ci) { phi[ci][0] = chi[ci][0]; phi[ci][1] = chi[ci][1]; plo[ci][0] = clo[ci][0]; plo[ci][1] = clo[ci][1]; }
                 if (k + 1 < ngroups) rb = rn;
                 y += 2;
             }
         }
-    } else if (warp == TC_CONV_WARPS + TC_EPI_WARPS) {
+    } else if (warp == TC_MMA_WARP) {
         // =================== MMA issuer ===================
+        // The tensor core's fp32 accumulate truncates; the error grows with the length of an accumulation chain.  So the
+        // large products xh*wh of the two groups go to two separate accumulators hh0 / hh1 (chains of 6 instead of 12) and
+        // the small terms (xh*wl, xl*wh: 2^-11 of the result) to their own columns sm; the epilogue adds the three with
+        // rounded fp32 adds (max error vs float64: 7e-7 -> 2.3e-7 of max|y|, rms 1.1e-7 -> 3e-8).
         mbar_wait(bbar, 0);
         const uint32_t idesc128 = tc05::idesc_f16_f32(128, 128), idesc64 = tc05::idesc_f16_f32(128, 64);
-        const uint32_t ring_u = smem_u32(ring), b_u = smem_u32(b_s);
-        long long pos = lo_row, K = 0, J = 0;
-        Seg s;
-        while (next_seg<POOL>(pos, hi_row, a, s)) {
-            for (int j = 0; j < s.nrows; ++j, ++J) {
-                const int stage = (int)(J % TC_STAGES);
-                const long long ause = J / TC_STAGES;
-                if (ause > 0) mbar_wait(acc_empty + stage, (uint32_t)((ause - 1) & 1));
-                const long long k0 = K + j, k2 = K + j + 2;
-                const int s0 = (int)(k0 % TC_D), s2 = (int)(k2 % TC_D);
-                mbar_wait(full + s0, (uint32_t)((k0 / TC_D) & 1));
-                mbar_wait(full + s2, (uint32_t)((k2 / TC_D) & 1));
-                tc05::fence_after_sync();
-                if (lane == 0) {
-                    const uint32_t d = tmem + (uint32_t)stage * 128u;
+        // descriptor low words (address in 16-byte units | LBO field); all shared addresses are below 2^14 units, so adding a
+        // unit offset never carries into the LBO field
+        const uint32_t ring_lo = tc05::desc_lo(smem_u32(ring) >> 4, 16), b_lo0 = tc05::desc_lo(smem_u32(b_s) >> 4, 128);
+        constexpr uint32_t A_HI = tc05::desc_hi(128), B_HI = tc05::desc_hi(256);
+        // The issue loop is software-pipelined: the barrier waits of row j + 1 (free accumulator stage, next group landed)
+        // are executed between the two halves of row j's instructions, so their wake-up latency is covered by tensor work
+        // that is already queued instead of leaving the pipe idle between rows.
+        struct RowIt {
+            long long pos, K, J;       // next segment start, first group of the segment, global row counter
+            Seg s;
+            int j;                     // row inside the segment
+            bool valid;
+        } cur, nxt;
+        auto first_row = [&](RowIt& it) {
+            it.pos = lo_row; it.K = 0; it.J = 0; it.j = 0;
+            it.valid = next_seg<POOL>(it.pos, hi_row, a, it.s);
+        };
+        auto next_row = [&](const RowIt& c, RowIt& n) {
+            n = c;
+            ++n.J;
+            if (++n.j == c.s.nrows) {
+                n.K = c.K + c.s.nrows + 2;
+                n.j = 0;
+                n.valid = next_seg<POOL>(n.pos, hi_row, a, n.s);
+            }
+        };
+        auto wait_row = [&](const RowIt& it) {
+            const int stage = (int)(it.J % TC_STAGES);
+            const long long ause = it.J / TC_STAGES;
+            TC_TL(1, (int)it.J, 0);
+            if (ause > 0) mbar_wait(acc_empty + stage, (uint32_t)((ause - 1) & 1));
+            const long long k0 = it.K + it.j, k2 = k0 + 2;
+            if (it.j < 2) mbar_wait(full + (int)(k0 % TC_D), (uint32_t)((k0 / TC_D) & 1));    // later rows saw it as their k2 two rows ago
+            mbar_wait(full + (int)(k2 % TC_D), (uint32_t)((k2 / TC_D) & 1));
+            tc05::fence_after_sync();
+            TC_TL(1, (int)it.J, 1);
+        };
+        first_row(cur);
+        if (cur.valid) wait_row(cur);
+        while (cur.valid) {
+            const int stage = (int)(cur.J % TC_STAGES);
+            const long long k0 = cur.K + cur.j, k2 = k0 + 2;
+            const int s0 = (int)(k0 % TC_D), s2 = (int)(k2 % TC_D);
+            // everything below is warp-uniform; only the tcgen05 instructions themselves are predicated on one lane
+            const bool leader = tc05::elect_one();
+            const uint32_t a0 = ring_lo + (uint32_t)s0 * (TC_SLOT / 16), a2 = ring_lo + (uint32_t)s2 * (TC_SLOT / 16);
+            const uint32_t dst = tmem + (uint32_t)(stage * TC_STAGE_COLS);
+            const bool run_mma = leader && !(a.dbg & 8);
+            TC_TL(1, (int)cur.J, 2);
 #pragma unroll
-                    for (int ks = 0; ks < TC_KSTEPS; ++ks) {
-                        const int grp = ks / 6, ci = (ks >> 1) % 3, pp = ks & 1;
-                        const uint32_t abase = ring_u + (uint32_t)(grp ? s2 : s0) * TC_SLOT + 32u * pp;
-                        const uint64_t a_hi = tc05::smem_desc(abase + (uint32_t)(ci * 2 + 0) * TC_NU * 16, 16, 128);
-                        const uint64_t a_lo = tc05::smem_desc(abase + (uint32_t)(ci * 2 + 1) * TC_NU * 16, 16, 128);
-                        const uint64_t bd = tc05::smem_desc(b_u + (uint32_t)ks * TC_BSTEP, 128, 256);
-                        tc05::mma_f16_ss(d, a_hi, bd, idesc128, ks > 0);       // xh*wh -> cols 0..63, xh*wl -> cols 64..127
-                        tc05::mma_f16_ss(d, a_lo, bd, idesc64, 1);             // xl*wh -> cols 0..63
-                    }
-                    tc05::commit(acc_full + stage);
-                    tc05::commit(empty + s0);                                  // group j is not needed any more
-                    if (j == s.nrows - 1) {
-                        tc05::commit(empty + (int)((K + s.nrows) % TC_D));
-                        tc05::commit(empty + (int)((K + s.nrows + 1) % TC_D));
+            for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                for (int kk = 0; kk < 6; ++kk) {
+                    const int ks = half * 6 + kk;
+                    const int grp = ks / 6, ci = (ks >> 1) % 3, pp = ks & 1;
+                    const uint32_t au = (grp ? a2 : a0) + (uint32_t)(2 * pp);
+                    const uint32_t a_hi = au + (uint32_t)(ci * 2 + 0) * TC_NU, a_lo = au + (uint32_t)(ci * 2 + 1) * TC_NU;
+                    // group 0 blocks are packed [wh | wl], group 1 blocks [wl | wh]: the small-term accumulator sits between
+                    // the two large-term accumulators, so one N = 128 instruction covers (hh0, sm) or (sm, hh1)
+                    const uint32_t b_all = b_lo0 + (uint32_t)ks * (TC_BSTEP / 16), b_wh = b_all + (grp ? 128u : 0u);
+                    if (run_mma) {
+                        if (ks == 6) {
+                            // first instruction into hh1 must overwrite it, but may not reset sm: three N = 64 instructions
+                            tc05::mma_f16_ss_w(dst + 128u, a_hi, A_HI, b_wh, B_HI, idesc64, 0);      // xh*wh -> hh1
+                            tc05::mma_f16_ss_w(dst + 64u, a_hi, A_HI, b_all, B_HI, idesc64, 1);      // xh*wl -> sm
+                        } else {
+                            tc05::mma_f16_ss_w(dst + (grp ? 64u : 0u), a_hi, A_HI, b_all, B_HI, idesc128, ks > 0);   // (hh0, sm) / (sm, hh1)
+                        }
+                        tc05::mma_f16_ss_w(dst + 64u, a_lo, A_HI, b_wh, B_HI, idesc64, 1);           // xl*wh -> sm
                     }
                 }
-                __syncwarp();
+                if (half == 0) {
+                    next_row(cur, nxt);
+                    if (nxt.valid) wait_row(nxt);
+                }
             }
-            K += s.nrows + 2;
+            if (leader) {
+                tc05::commit(acc_full + stage);
+                tc05::commit(empty + s0);                                      // group j is not needed any more
+                if (cur.j == cur.s.nrows - 1) {
+                    tc05::commit(empty + (int)((cur.K + cur.s.nrows) % TC_D));
+                    tc05::commit(empty + (int)((cur.K + cur.s.nrows + 1) % TC_D));
+                }
+            }
+            __syncwarp();
+            TC_TL(1, (int)cur.J, 3);
+            cur = nxt;
         }
-    } else {
-        // =================== epilogue: TMEM -> BN (+ ReLU) -> [vertical max in registers] -> lanes <-> channels -> NHWC + planes
+    } else if (warp < TC_CONV_WARPS + TC_EPI_WARPS) {
+        // =================== accumulator warps: TMEM -> BN (+ ReLU) -> [vertical max in registers] -> parked row in smem
         const int e = warp - TC_CONV_WARPS;            // 0..7
         const int lq = warp & 3;                       // TMEM lane quarter this warp may read
         const int cb = 32 * (e >> 2);                  // channel half
         const int m = 32 * lq + lane;                  // conv column inside the M tile
-        const bool has_nx = a.nx_scale != nullptr, has_nx2 = a.nx2_scale != nullptr;
         long long pos = lo_row, J = 0;
         int emits = 0;
         Seg s;
         while (next_seg<POOL>(pos, hi_row, a, s)) {
             const int c = s.cbase + m;
             const bool col_ok = (unsigned)c < (unsigned)a.Wc;
+            const bool all_ok = __all_sync(0xffffffffu, col_ok);
             float state[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) state[i] = 0.0f;            // 0 = max-pool padding after the ReLU (and the ReLU itself)
             for (int j = 0; j < s.nrows; ++j, ++J) {
                 const int r = s.r_first + j;
                 const int stage = (int)(J % TC_STAGES);
+                bool emit = true;
+                if (POOL) emit = ((r & 1) || r == a.Hc - 1) && ((r & 1) ? (r - 1) >> 1 : r >> 1) >= s.row_a;
+                float* vb = vbuf + (size_t)(emits & 1) * (TC_VBUF / 4) + m * TC_VPITCH + cb;
+                if (e == 0) TC_TL(2, (int)J, 0);
+                if (emit && emits >= 2) mbar_wait(vempty + (emits & 1), (uint32_t)(((emits >> 1) - 1) & 1));
                 mbar_wait(acc_full + stage, (uint32_t)((J / TC_STAGES) & 1));
                 tc05::fence_after_sync();
-                const uint32_t taddr = tmem + ((uint32_t)(32 * lq) << 16) + (uint32_t)(stage * 128 + cb);
-                float cur[32];
+                if (e == 0) TC_TL(2, (int)J, 1);
+                const uint32_t taddr = tmem + ((uint32_t)(32 * lq) << 16) + (uint32_t)(stage * TC_STAGE_COLS + cb);
+                // MODE 0: no emit (state = max(state, v));  1: emit max(state, v), an odd conv row also opens the next pooled
+                // row (state = relu(v));  2: pool-less, emit relu(v).  One instance of the row body per mode: no per-element selects
+                auto row = [&](auto mode_tag) {
+                    constexpr int MODE = decltype(mode_tag)::value;
 #pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    float p[16], q[16];
-                    tc05::tmem_ld16x2_sync(taddr + 16 * hh, taddr + 64 + 16 * hh, p, q);
+                    for (int hh = 0; hh < 4; ++hh) {                 // 8 channels at a time
+                        float p0[8], p1[8], q[8];
+                        tc05::tmem_ld8x3_sync(taddr + 8 * hh, taddr + 128 + 8 * hh, taddr + 64 + 8 * hh, p0, p1, q);   // hh0, hh1, sm
+                        if (hh == 3) {                               // every column of this stage has been read
+                            tc05::fence_before_sync();
+                            __syncwarp();
+                            if (lane == 0) tc05::mbar_arrive(acc_empty + stage);
+                        }
 #pragma unroll
-                    for (int i4 = 0; i4 < 16; i4 += 4) {
-                        const float4 g = *reinterpret_cast<const float4*>(consts + cb + 16 * hh + i4);
-                        const float4 h = *reinterpret_cast<const float4*>(consts + 64 + cb + 16 * hh + i4);
-                        const float gg[4] = {g.x, g.y, g.z, g.w}, hv[4] = {h.x, h.y, h.z, h.w};
+                        for (int i4 = 0; i4 < 8; i4 += 4) {
+                            const float4 g = *reinterpret_cast<const float4*>(consts + cb + 8 * hh + i4);
+                            const float4 h = *reinterpret_cast<const float4*>(consts + 64 + cb + 8 * hh + i4);
+                            const float gg[4] = {g.x, g.y, g.z, g.w}, hv[4] = {h.x, h.y, h.z, h.w};
+                            float o[4];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) cur[16 * hh + i4 + i] = __fmaf_rn(__fadd_rn(p[i4 + i], q[i4 + i]), gg[i], hv[i]);
-                    }
-                }
-                tc05::fence_before_sync();
-                __syncwarp();
-                if (lane == 0) tc05::mbar_arrive(acc_empty + stage);
-                bool emit;
-                int orow;
-                if (POOL) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) state[i] = fmaxf(state[i], cur[i]);       // state >= 0: the ReLU is implied
-                    orow = (r & 1) ? (r - 1) >> 1 : r >> 1;
-                    emit = ((r & 1) || r == a.Hc - 1) && orow >= s.row_a;
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) state[i] = fmaxf(cur[i], 0.0f);
-                    orow = r;
-                    emit = true;
-                }
-                if (emit) {
-                    float* vb = vbuf + (size_t)(emits & 1) * (TC_VBUF / 4);
-                    ++emits;
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4)                  // columns outside the conv output: max-pool padding (0)
-                        *reinterpret_cast<float4*>(vb + m * TC_VPITCH + cb + i) =
-                            col_ok ? make_float4(state[i], state[i + 1], state[i + 2], state[i + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_WARPS * 32) : "memory");
-                    // lanes <-> channels: whole 128-byte lines out
-                    const size_t prow = ((size_t)s.n * a.Ho + orow) * a.Wo;
-                    for (int jp = e; jp < a.TW; jp += TC_EPI_WARPS) {
-                        const int oc = s.col0 + jp;
-                        if (oc >= a.Wo) break;
-                        const float* v0 = vb + (POOL ? 2 * jp : jp) * TC_VPITCH + lane;
-                        uint32_t sw[2], mw[2], sw2[2], mw2[2];
-#pragma unroll
-                        for (int hb = 0; hb < 2; ++hb) {
-                            float mx = v0[32 * hb];
-                            if (POOL) mx = fmaxf(fmaxf(mx, v0[TC_VPITCH + 32 * hb]), v0[2 * TC_VPITCH + 32 * hb]);
-                            a.out[(prow + oc) * 64 + 32 * hb + lane] = mx;
-                            const float b = has_nx ? __fmaf_rn(consts[128 + 32 * hb + lane], mx, consts[192 + 32 * hb + lane]) : mx;
-                            sw[hb] = __ballot_sync(0xffffffffu, b > 0.0f);
-                            mw[hb] = a.nx_relu ? sw[hb] : __ballot_sync(0xffffffffu, b > 0.0f || b < 0.0f);
-                            if (has_nx2) {
-                                const float b2 = __fmaf_rn(consts[256 + 32 * hb + lane], mx, consts[320 + 32 * hb + lane]);
-                                sw2[hb] = __ballot_sync(0xffffffffu, b2 > 0.0f);
-                                mw2[hb] = a.nx2_relu ? sw2[hb] : __ballot_sync(0xffffffffu, b2 > 0.0f || b2 < 0.0f);
+                            for (int i = 0; i < 4; ++i) {
+                                const int k = 8 * hh + i4 + i;
+                                const float conv = __fadd_rn(__fadd_rn(p0[i4 + i], p1[i4 + i]), q[i4 + i]);
+                                const float v = __fmaf_rn(conv, gg[i], hv[i]);
+                                if (MODE == 0) {
+                                    state[k] = fmaxf(state[k], v);       // state >= 0: the ReLU is implied
+                                } else if (MODE == 1) {
+                                    o[i] = fmaxf(state[k], v);
+                                    state[k] = fmaxf(v, 0.0f);
+                                } else {
+                                    o[i] = fmaxf(v, 0.0f);
+                                }
+                            }
+                            if (MODE != 0) {                         // columns outside the conv output: max-pool padding (0)
+                                float4 ov = make_float4(o[0], o[1], o[2], o[3]);
+                                if (!all_ok && !col_ok) ov = make_float4(0.f, 0.f, 0.f, 0.f);
+                                *reinterpret_cast<float4*>(vb + 8 * hh + i4) = ov;
                             }
                         }
-                        if (lane == 0) {
-                            if (a.obits) a.obits[prow + oc] = make_uint4(sw[0], sw[1], mw[0], mw[1]);
-                            if (has_nx2 && a.obits2) a.obits2[prow + oc] = make_uint4(sw2[0], sw2[1], mw2[0], mw2[1]);
-                        }
                     }
-                    if (POOL && (r & 1)) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) state[i] = fmaxf(cur[i], 0.0f);       // an odd conv row also opens the next pooled row
+                };
+                if (a.dbg & 1) {
+                    tc05::fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) tc05::mbar_arrive(acc_empty + stage);
+                } else if (!POOL) row(std::integral_constant<int, 2>{});
+                else if (emit) row(std::integral_constant<int, 1>{});
+                else row(std::integral_constant<int, 0>{});
+                if (emit) {
+                    __syncwarp();
+                    if (lane == 0) tc05::mbar_arrive(vfull + (emits & 1));
+                    ++emits;
+                }
+                if (e == 0) TC_TL(2, (int)J, 2);
+            }
+        }
+    } else {
+        // =================== output warps: parked rows -> [horizontal 3-max] -> NHWC lines + planes, lanes <-> channels
+        const int e = warp - TC_CONV_WARPS - TC_EPI_WARPS;           // 0..6
+        const bool has_nx = a.nx_scale != nullptr, has_nx2 = a.nx2_scale != nullptr && a.obits2 != nullptr;
+        const bool nx_relu = a.nx_relu != 0, nx2_relu = a.nx2_relu != 0;
+        const float k2[2] = {consts[128 + lane], consts[160 + lane]}, k3[2] = {consts[192 + lane], consts[224 + lane]};
+        const float k4[2] = {consts[256 + lane], consts[288 + lane]}, k5[2] = {consts[320 + lane], consts[352 + lane]};
+        float* const outp = a.out;
+        uint4* const ob1 = a.obits;
+        uint4* const ob2 = a.obits2;
+        const int Hc = a.Hc, Ho = a.Ho, Wo = a.Wo, TW = a.TW;
+        long long pos = lo_row;
+        int emits = 0;
+        Seg s;
+        while (next_seg<POOL>(pos, hi_row, a, s)) {
+            const int ncols = Wo - s.col0 < TW ? Wo - s.col0 : TW;  // output columns of this tile
+            for (int j = 0; j < s.nrows; ++j) {
+                const int r = s.r_first + j;
+                int orow = r;
+                if (POOL) {
+                    orow = (r & 1) ? (r - 1) >> 1 : r >> 1;
+                    if (!(((r & 1) || r == Hc - 1) && orow >= s.row_a)) continue;
+                }
+                const float* vb = vbuf + (size_t)(emits & 1) * (TC_VBUF / 4) + lane;
+                if (e == 0) TC_TL(3, emits, 0);
+                mbar_wait(vfull + (emits & 1), (uint32_t)((emits >> 1) & 1));
+                if (e == 0) TC_TL(3, emits, 1);
+                const size_t prow = ((size_t)s.n * Ho + orow) * Wo + s.col0;
+                float* po = outp + (prow + e) * 64 + lane;
+                const float* v0 = vb + (POOL ? 2 * e : e) * TC_VPITCH;
+                for (int jp = (a.dbg & 2) ? ncols : e; jp < ncols; jp += TC_OUT_WARPS, po += TC_OUT_WARPS * 64, v0 += (POOL ? 2 : 1) * TC_OUT_WARPS * TC_VPITCH) {
+                    float mx0 = v0[0], mx1 = v0[32];
+                    if (POOL) {
+                        mx0 = fmaxf(fmaxf(mx0, v0[TC_VPITCH]), v0[2 * TC_VPITCH]);
+                        mx1 = fmaxf(fmaxf(mx1, v0[TC_VPITCH + 32]), v0[2 * TC_VPITCH + 32]);
+                    }
+                    po[0] = mx0;
+                    po[32] = mx1;
+                    const float b0 = has_nx ? __fmaf_rn(k2[0], mx0, k3[0]) : mx0, b1 = has_nx ? __fmaf_rn(k2[1], mx1, k3[1]) : mx1;
+                    const uint32_t s0 = __ballot_sync(0xffffffffu, b0 > 0.0f), s1 = __ballot_sync(0xffffffffu, b1 > 0.0f);
+                    uint32_t m0 = s0, m1 = s1;
+                    if (!nx_relu) {
+                        m0 = __ballot_sync(0xffffffffu, b0 != 0.0f && b0 == b0);          // non-zero and not NaN
+                        m1 = __ballot_sync(0xffffffffu, b1 != 0.0f && b1 == b1);
+                    }
+                    if (lane == 0 && ob1 != nullptr) ob1[prow + jp] = make_uint4(s0, s1, m0, m1);
+                    if (has_nx2) {
+                        const float c0 = __fmaf_rn(k4[0], mx0, k5[0]), c1 = __fmaf_rn(k4[1], mx1, k5[1]);
+                        const uint32_t t0 = __ballot_sync(0xffffffffu, c0 > 0.0f), t1 = __ballot_sync(0xffffffffu, c1 > 0.0f);
+                        uint32_t n0 = t0, n1 = t1;
+                        if (!nx2_relu) {
+                            n0 = __ballot_sync(0xffffffffu, c0 != 0.0f && c0 == c0);
+                            n1 = __ballot_sync(0xffffffffu, c1 != 0.0f && c1 == c1);
+                        }
+                        if (lane == 0) ob2[prow + jp] = make_uint4(t0, t1, n0, n1);
                     }
                 }
+                __syncwarp();
+                if (lane == 0) tc05::mbar_arrive(vempty + (emits & 1));
+                if (e == 0) TC_TL(3, emits, 2);
+                ++emits;
             }
         }
     }
     tc05::fence_before_sync();
     __syncthreads();
-    if (warp == TC_CONV_WARPS + TC_EPI_WARPS) tc05::tmem_dealloc<512>(tmem);
+    if (warp == TC_MMA_WARP) tc05::tmem_dealloc<512>(tmem);
 }
 
-// conv weight [64,3,7,7] fp32 -> the B operand image: 12 K steps x [wh | wl] rows x 16 K elements, K-major no-swizzle core
+// conv weight [64,3,7,7] fp32 -> the B operand image: 12 K steps x ([wh | wl] for group 0, [wl | wh] for group 1) rows x 16 K elements, K-major no-swizzle core
 // matrices (8 rows x 16 bytes, the two K chunks 128 bytes apart, 8-row groups 256 bytes apart).
 // K step ks = (grp * 3 + ci) * 2 + pp; K element jj * 8 + i * 2 + b  <->  w[n][ci][kh = 4 grp + i][kw = 4 pp + 2 jj + b - 1]
 // (units are ALIGNED input column pairs (2q, 2q+1); the conv's left padding of 3 puts the zero tap at kw = -1).
@@ -395,8 +526,9 @@ __global__ void stem_tc_pack_weight_kernel(const float* __restrict__ w, float w_
     if (idx >= TC_B_BYTES / 2) return;
     const int ks = idx / (TC_BSTEP / 2), rem = idx % (TC_BSTEP / 2);
     const int n8 = rem / 128, jj = (rem % 128) / 64, nr = (rem % 64) / 8, el = rem % 8;
-    const int n = n8 * 8 + nr;                                   // 0..63: wh rows, 64..127: wl rows
     const int grp = ks / 6, ci = (ks >> 1) % 3, pp = ks & 1;
+    int n = n8 * 8 + nr;                                         // group 0 blocks: rows 0..63 wh, 64..127 wl
+    if (grp) n ^= 64;                                            // group 1 blocks: rows 0..63 wl, 64..127 wh
     const int kh = 4 * grp + (el >> 1), kw = 4 * pp + 2 * jj + (el & 1) - 1;
     float v = 0.0f;
     if (kh < 7 && kw >= 0 && kw < 7) v = w[(((n & 63) * 3 + ci) * 7 + kh) * 7 + kw] * w_scale;
@@ -458,7 +590,6 @@ extern "C" int bnn_amax_f32(const float* x, int64_t count, float* amax, void* st
 }
 
 extern "C" int bnn_stem_tc_run(const bnn_stem_tc_params* p, uint32_t flags, void* stream_) {
-    (void)flags;
     if (!p) return BNN_E_NULL;
     if (!p->x || !p->w_ops || !p->bn_scale || !p->bn_shift || !p->out) return BNN_E_NULL;
     if ((p->nx_scale == nullptr) != (p->nx_shift == nullptr) || (p->nx2_scale == nullptr) != (p->nx2_shift == nullptr)) return BNN_E_NULL;
@@ -477,6 +608,7 @@ extern "C" int bnn_stem_tc_run(const bnn_stem_tc_params* p, uint32_t flags, void
     a.x_amax = p->x_dtype == 0 ? p->x_amax : nullptr; a.out = p->out; a.obits = (uint4*)p->out_bits; a.obits2 = (uint4*)p->out_bits2;
     for (int i = 0; i < 3; ++i) { a.u8_mean[i] = p->u8_mean[i]; a.u8_istd[i] = p->u8_istd[i]; }
     a.x_log2_scale = p->x_log2_scale; a.w_log2_scale = p->w_log2_scale;
+    a.dbg = (int)((flags >> 8) & 31u);
     a.vec2 = (p->x_dtype == 0 && (p->w & 1) == 0 && ((uintptr_t)p->x & 7) == 0) ? 1 : 0;
     a.N = p->n; a.H = p->h; a.W = p->w;
     a.Hc = (p->h + 6 - 7) / 2 + 1; a.Wc = (p->w + 6 - 7) / 2 + 1;

@@ -338,6 +338,7 @@ typedef struct bnn_stem_tc_params {
     float *out;
 } bnn_stem_tc_params;
 int bnn_stem_tc_run(const bnn_stem_tc_params *params, uint32_t flags, void *stream);
+#define BNN_F_STEM_TC_DBG_SHIFT 8   /* bits 8..11 of flags idle one role of the kernel each (timing experiments; garbage results) */
 int bnn_stem_tc_fwd(const float *x, int32_t n, int32_t h, int32_t w, const void *w_ops, int32_t x_log2_scale,
                     const float *x_amax, int32_t w_log2_scale, const float *bn_scale, const float *bn_shift,
                     const float *nx_scale, const float *nx_shift, float *out, void *out_bits, uint32_t flags,
