@@ -213,6 +213,13 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
                     const int j = lane / P, p = lane - j * P;
                     if ((blk0 + j) * 32 < a.Cout && wo_first + p < a.Wo)
                         prefetch_l1(rb + (blk0 + j) * 32 * e_rc + (wo_first + p) * e_rw);
+                    if constexpr (CL && KWT == 1) {
+                        // 1x1 kernels: the K loop of a group is far shorter than a DRAM round trip, so also request the lines
+                        // of this warp's NEXT group now (g_row / g_col already point at it)
+                        const int ho2 = ho0 + g_row, wo2 = wo0 + g_col * P;
+                        if (g + nwarps < a.G && ho2 < a.Ho && (blk0 + j) * 32 < a.Cout && wo2 + p < a.Wo)
+                            prefetch_l1(res_n + ho2 * e_rh + (blk0 + j) * 32 * e_rc + (wo2 + p) * e_rw);
+                    }
                 }
             }
         }
