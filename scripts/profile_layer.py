@@ -18,6 +18,9 @@ LAYERS = {  # name: (c_in, c_out, h, w, k, stride, pad)
     "l2d": (64, 128, 28, 28, 1, 1, 0), "l3s": (128, 256, 28, 28, 3, 2, 1), "l3": (256, 256, 14, 14, 3, 1, 1),
     "l3d": (128, 256, 14, 14, 1, 1, 0), "l4s": (256, 512, 14, 14, 3, 2, 1), "l4": (512, 512, 7, 7, 3, 1, 1),
     "l4d": (256, 512, 7, 7, 1, 1, 0),
+    # ResNet-50 (use --batch 128): the 1x1 expand convs (conv3: residual + fp32 out + planes) and reduce convs (conv1: planes only)
+    "r50_l1c3": (64, 256, 56, 56, 1, 1, 0), "r50_l2c3": (128, 512, 28, 28, 1, 1, 0), "r50_l3c3": (256, 1024, 14, 14, 1, 1, 0),
+    "r50_l4c3": (512, 2048, 7, 7, 1, 1, 0), "r50_l2c1": (512, 128, 28, 28, 1, 1, 0), "r50_l3c1": (1024, 256, 14, 14, 1, 1, 0),
 }
 
 
