@@ -351,6 +351,7 @@ def main():
     ap.add_argument("--stem", default="auto", choices=["auto", "tc", "mma", "fma"],
                     help="fused engine's stem kernel: tcgen05 (tc), mma.sync split-fp16 (mma) or the fp32 fma chain")
     ap.add_argument("--layers-out", default=None, help="write the per-layer table to this JSON file")
+    ap.add_argument("--shortcut-max-cin", type=int, default=-1, help="experiment knob: bnn_b200.runtime.shortcut_max_cin")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     cfgd = CONFIGS[args.config]
@@ -367,6 +368,9 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 engine has no CPU fallback (use --impl reference)")
+    if args.shortcut_max_cin >= 0:
+        from bnn_b200 import runtime as _rt
+        _rt.shortcut_max_cin(args.shortcut_max_cin)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     numa_node = bind_host_to_gpu_numa(local_rank) if world > 1 else None

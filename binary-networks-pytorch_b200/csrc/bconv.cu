@@ -143,7 +143,9 @@ static int enumerate_plans(const bnn_conv_geom& g, int Ho, int Wo, uint32_t flag
                     if (smem > smem_cap) break;
                     const int G = TH * gpr, rounds = ceil_div(G, NW);
                     if (rounds > 12 && TH > 1) break;
-                    const int occ = smem * 2 <= 226 * 1024 ? 2 : 1;
+                    // resident CTAs: what the instance is compiled for (register budget), capped by shared memory
+                    int occ = bconv_min_ctas(P, C, kwt);
+                    while (occ > 1 && smem * occ > 226 * 1024) --occ;
                     const long long ctas = (long long)g.n * ceil_div(Ho, TH) * tiles_w * cout_tiles;
                     const long long slots = (long long)sms * occ;
                     const double waves = (double)((ctas + slots - 1) / slots);
@@ -317,13 +319,24 @@ extern "C" int bnn_bconv2d_tune(const void* abits, const void* wbits, const bnn_
     std::vector<Cand> cands;
     int rc = enumerate_plans(g, Ho, Wo, flags, sms, cands);
     if (rc) return rc;
-    // keep the model's best few, but make sure different (P, C, warps) families are represented
+    // the model's best candidate of every (P, C) family first (the families differ in registers / resident CTAs, which
+    // the model only approximates), then its best few overall with at most two per (P, C, warps) family
     std::vector<Plan> tries;
     for (const Cand& c : cands) {
+        bool seen = false;
+        for (const Plan& t : tries) seen |= (t.P == c.pl.P && t.C == c.pl.C);
+        if (!seen) tries.push_back(c.pl);
+    }
+    const size_t families = tries.size();
+    for (const Cand& c : cands) {
+        if (tries.size() >= families + (size_t)(top_k > 0 ? top_k : 6)) break;
         int same = 0;
-        for (const Plan& t : tries) same += (t.P == c.pl.P && t.C == c.pl.C && t.NW == c.pl.NW);
-        if (same < 2) tries.push_back(c.pl);
-        if ((int)tries.size() >= (top_k > 0 ? top_k : 8)) break;
+        bool dup = false;
+        for (const Plan& t : tries) {
+            same += (t.P == c.pl.P && t.C == c.pl.C && t.NW == c.pl.NW);
+            dup |= (t.P == c.pl.P && t.C == c.pl.C && t.NW == c.pl.NW && t.TH == c.pl.TH);
+        }
+        if (same < 2 && !dup) tries.push_back(c.pl);
     }
     cudaStream_t stream = (cudaStream_t)stream_;
     cudaEvent_t e0, e1;

@@ -23,6 +23,7 @@
 //     the three taps of a 3-wide kernel row with a 3:2 carry-save adder
 //     (2 more LOP3) so that 3 words cost 2 POPC -- POPC is the slow pipe.
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 
 namespace bnn {
@@ -62,10 +63,32 @@ enum { EP_N = 5 };
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ int word_dis(uint32_t m, uint32_t s, uint32_t t) { return __popc(m & (s ^ t)); }
+// (ms + magic) - 2 * acc as one integer multiply-add
+__device__ __forceinline__ int msm2(int msm, int acc) {
+    int r;
+    asm("mad.lo.s32 %0, %1, -2, %2;" : "=r"(r) : "r"(acc), "r"(msm));
+    return r;
+}
+// acc + ones + 2 * twos.  BNN_ACC_IMAD: the doubling as an integer multiply-add (fma pipe) instead of a second ALU add --
+// LOP3 / IADD3 share the ALU pipe, which runs as loaded as the POPC pipe in the K loop
+__device__ __forceinline__ int acc_csa(int acc, int ones, int twos) {
+#ifdef BNN_ACC_IMAD
+    int r = acc + ones;
+    asm("mad.lo.s32 %0, %1, 2, %0;" : "+r"(r) : "r"(twos));
+    return r;
+#else
+    return acc + ones + 2 * twos;
+#endif
+}
 __device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (c & (a ^ b)); }
 
+// CTAs per SM the instance is compiled for.  1x1 kernels with small tiles keep few values live and their layers are
+// latency-bound (short K loops between a TMA prologue and an HBM-fed epilogue): three resident CTAs (80 registers)
+// overlap those phases better than two; everything else gets the full 128 registers.
+__host__ __device__ constexpr int bconv_min_ctas(int P, int C, int KWT) { return (KWT == 1 && P * C <= 16) ? 3 : 2; }
+
 template <int P, int C, int KWT, int SWT, int MODE, int EPI>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, bconv_min_ctas(P, C, KWT))
 bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ConvArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     // EPI 0: reference epilogue.  EPI 1: fused epilogue, any strides.  EPI 2: fused epilogue with channel-contiguous
@@ -76,6 +99,10 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
     // "positive".  EPI 4, general form: any activation, shortcut before or after it, optional affine in front of the
     // next sign() (its own instance so that the fast form stays small).
     constexpr bool FUSED = EPI >= 1, CL = EPI >= 2, LEAN = EPI >= 3, LEAN_GENERAL = EPI == 4;
+    // int -> float without the conversion pipe (I2F shares the quarter-rate XU pipe with POPC): for |k| < 2^22 the bit
+    // pattern 0x4B400000 + k IS the float 12582912 + k, and subtracting 12582912.0f is exact -- the same value I2F gives
+    constexpr int MAGIC_I = 0x4B400000;
+    constexpr float MAGIC_F = 12582912.0f;
     constexpr int PITCH = P | 1;      // odd pitch: conflict-free transposes
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
     uint4* act = reinterpret_cast<uint4*>(smem + 128);
@@ -171,7 +198,7 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
                     cnt += __popc(v.z) + __popc(v.w);
                 }
             }
-        ms_s[i] = cnt;
+        ms_s[i] = cnt + (LEAN ? MAGIC_I : 0);
     }
     __syncthreads();
 
@@ -186,7 +213,21 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
     float* out_n = a.e.out ? a.e.out + (long long)n * a.e.on : nullptr;
     const int e_rc = CL ? 1 : (int)a.e.rc, e_rh = (int)a.e.rh, e_rw = (int)a.e.rw;
     const int e_oc = CL ? 1 : (int)a.e.oc, e_oh = (int)a.e.oh, e_ow = (int)a.e.ow;
+    const long long rwb = (long long)e_rw * 4, owb = (long long)e_ow * 4;        // byte steps between pixels
     const int a_chstep = a.BH * a.BW, a_khstep = a.DH * a.BW;     // activation rows: per chunk, per kernel row
+    // lean plane store: lane l owns unit (chunk l / P, pixel l % P) of every group -- per-lane part of the unit index
+    size_t obits_base = 0;
+    if constexpr (EPI == 3) {
+        const int lj = lane / P, lp = lane - lj * P;
+        obits_base = ((size_t)n * a.e.ochunks + (blk0 >> 1) + lj) * ((size_t)a.Ho * a.Wo) + lp;
+    }
+    // shortcut prefetch (channels-last): lane -> (32-channel block lane / P, pixel lane % P) of every group
+    int pf_off = -1, pf_p = 0;
+    if (FUSED && lane < P * C) {
+        const int j = lane / P;
+        pf_p = lane - j * P;
+        if ((blk0 + j) * 32 < a.Cout) pf_off = (blk0 + j) * 32 * e_rc + pf_p * e_rw;
+    }
     int g_row = warp / a.gpr, g_col = warp - g_row * a.gpr;      // one division per warp, then incremental
     const int step_row = nwarps / a.gpr, step_col = nwarps - step_row * a.gpr;
     for (int g = warp; g < a.G; g += nwarps) {
@@ -209,16 +250,15 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
                         const int c = (blk0 + j) * 32 + lane;
                         if (c < a.Cout) prefetch_l1(rb + c * e_rc + wo_first);
                     }
-                } else if (lane < P * C) {    // channels-last: one 128-byte line per (pixel, 32-channel block)
-                    const int j = lane / P, p = lane - j * P;
-                    if ((blk0 + j) * 32 < a.Cout && wo_first + p < a.Wo)
-                        prefetch_l1(rb + (blk0 + j) * 32 * e_rc + (wo_first + p) * e_rw);
+                } else if (pf_off >= 0 && (LEAN || wo_first + pf_p < a.Wo)) {
+                    // channels-last: one 128-byte line per (pixel, 32-channel block); the lane's part of the offset is hoisted
+                    prefetch_l1(rb + (wo_first * e_rw + pf_off));
                     if constexpr (CL && KWT == 1) {
                         // 1x1 kernels: the K loop of a group is far shorter than a DRAM round trip, so also request the lines
                         // of this warp's NEXT group now (g_row / g_col already point at it)
                         const int ho2 = ho0 + g_row, wo2 = wo0 + g_col * P;
-                        if (g + nwarps < a.G && ho2 < a.Ho && (blk0 + j) * 32 < a.Cout && wo2 + p < a.Wo)
-                            prefetch_l1(res_n + ho2 * e_rh + (blk0 + j) * 32 * e_rc + (wo2 + p) * e_rw);
+                        if (g + nwarps < a.G && ho2 < a.Ho && wo2 + pf_p < a.Wo)
+                            prefetch_l1(res_n + (ho2 * e_rh + wo2 * e_rw + pf_off));
                     }
                 }
             }
@@ -255,7 +295,7 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
                                        y2 = v2.w & (v2.y ^ t[2][j].y);
                         const int ones = __popc(x0 ^ x1 ^ x2) + __popc(y0 ^ y1 ^ y2);
                         const int twos = __popc(maj3(x0, x1, x2)) + __popc(maj3(y0, y1, y2));
-                        acc[p][j] += ones + 2 * twos;
+                        acc[p][j] = acc_csa(acc[p][j], ones, twos);
                     }
                 }
             }
@@ -307,7 +347,7 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
                                                y2 = v2.w & (v2.y ^ t[2][j].y);
                                 const int ones = __popc(x0 ^ x1 ^ x2) + __popc(y0 ^ y1 ^ y2);
                                 const int twos = __popc(maj3(x0, x1, x2)) + __popc(maj3(y0, y1, y2));
-                                acc[p][j] += ones + 2 * twos;
+                                acc[p][j] = acc_csa(acc[p][j], ones, twos);
                             }
                         }
                     } else {
@@ -346,8 +386,17 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
 
         // ---------------- epilogue ----------------
         int ms[P];
+        if constexpr (P % 4 == 0) {              // tile widths are multiples of P: 16-byte aligned broadcast loads
+            const int4* m4 = reinterpret_cast<const int4*>(ms_s + r * a.TW + wq);
 #pragma unroll
-        for (int p = 0; p < P; ++p) ms[p] = ms_s[r * a.TW + wq + p];      // broadcast loads
+            for (int q = 0; q < P / 4; ++q) {
+                const int4 t = m4[q];
+                ms[4 * q] = t.x; ms[4 * q + 1] = t.y; ms[4 * q + 2] = t.z; ms[4 * q + 3] = t.w;
+            }
+        } else {
+#pragma unroll
+            for (int p = 0; p < P; ++p) ms[p] = ms_s[r * a.TW + wq + p];      // broadcast loads
+        }
         if constexpr (LEAN) {
             const bool has_res = a.e.res != nullptr, has_out = a.e.out != nullptr;
             const int cch = blk0 * 32 + lane;
@@ -355,10 +404,13 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
             float* op = out_n + (ho * e_oh + wo_first * e_ow + cch);            // dereferenced only if has_out
             float res[C][P];
             if (has_res) {                       // every shortcut line of the group in flight before the first use
+                const float* rq = rp;
 #pragma unroll
-                for (int j = 0; j < C; ++j)
+                for (int p = 0; p < P; ++p) {
 #pragma unroll
-                    for (int p = 0; p < P; ++p) res[j][p] = __ldg(rp + p * e_rw + j * 32);
+                    for (int j = 0; j < C; ++j) res[j][p] = __ldg(rq + j * 32);
+                    rq = reinterpret_cast<const float*>(reinterpret_cast<const char*>(rq) + rwb);
+                }
             }
             if constexpr (LEAN_GENERAL) {
                 const bool res_after = a.e.res_after_act != 0, nx = a.e.nx_scale != nullptr;
@@ -378,7 +430,7 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
                         const float k3 = epc[3 * 32 * C + cl], k4 = epc[4 * 32 * C + cl];
 #pragma unroll
                         for (int p = 0; p < P; ++p) {
-                            float v = __fmaf_rn(k0, (float)(ms[p] - 2 * acc[p][j + jj]), k1);
+                            float v = __fmaf_rn(k0, __fadd_rn(__int_as_float(msm2(ms[p], acc[p][j + jj])), -MAGIC_F), k1);
                             if (has_res && !res_after) v = __fadd_rn(v, res[j + jj][p]);
                             if (act == BNN_ACT_RELU) v = fmaxf(v, 0.0f);
                             else if (act == BNN_ACT_PRELU) v = (v > 0.0f) ? v : __fmul_rn(k2, v);
@@ -406,38 +458,50 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
                 }
                 continue;
             }
-            // fast form (EPI 3)
-            uint32_t sw[P][C];                   // ballots are warp-uniform: every lane holds every word
+            // fast form (EPI 3).  Per output: IMAD (ms + magic - 2 acc), FADD (- magic), FFMA, [FADD shortcut], FMNMX,
+            // [STG], FSETP, VOTE -- addresses are running pointers (one 64-bit add per pixel), no conversion instruction
+            // Ballots are warp-uniform, so every lane parks the same finished words {s_lo, s_hi | m_lo, m_hi} (m == s: ReLU
+            // output) in the warp's staging area -- no divergence -- and lane l later stores unit l (chunk-major, P
+            // consecutive units per 64 channels).
+            uint2* sb = reinterpret_cast<uint2*>(stg);
+            const bool want_bits = a.e.obits != nullptr;
+            float k0[C], k1[C];
 #pragma unroll
-            for (int j = 0; j < C; ++j) {
-                const float k0 = epc[j * 32 + lane], k1 = epc[32 * C + j * 32 + lane];
+            for (int j = 0; j < C; ++j) { k0[j] = epc[j * 32 + lane]; k1[j] = epc[32 * C + j * 32 + lane]; }
+            // the four (shortcut, fp32 output) combinations as straight-line code each
+            auto finish = [&](auto HAS_RES, auto HAS_OUT) {
+                float* oq = op;
 #pragma unroll
                 for (int p = 0; p < P; ++p) {
-                    float v = __fmaf_rn(k0, (float)(ms[p] - 2 * acc[p][j]), k1);
-                    if (has_res) v = __fadd_rn(v, res[j][p]);
-                    v = fmaxf(v, 0.0f);
-                    if (has_out) op[p * e_ow + j * 32] = v;
-                    sw[p][j] = __ballot_sync(0xffffffffu, v > 0.0f);
+#pragma unroll
+                    for (int j = 0; j < C; j += 2) {
+                        uint32_t w2[2];
+#pragma unroll
+                        for (int jj = 0; jj < 2; ++jj) {
+                            float v = __fmaf_rn(k0[j + jj], __fadd_rn(__int_as_float(msm2(ms[p], acc[p][j + jj])), -MAGIC_F), k1[j + jj]);
+                            if constexpr (HAS_RES.value) v = __fadd_rn(v, res[j + jj][p]);
+                            if constexpr (HAS_OUT.value) {
+                                v = fmaxf(v, 0.0f);
+                                oq[(j + jj) * 32] = v;
+                            }
+                            w2[jj] = __ballot_sync(0xffffffffu, v > 0.0f);       // max(v, 0) > 0 == v > 0
+                        }
+                        if (!HAS_OUT.value || want_bits) {
+                            sb[((j / 2) * P + p) * 2] = make_uint2(w2[0], w2[1]);
+                            sb[((j / 2) * P + p) * 2 + 1] = make_uint2(w2[0], w2[1]);
+                        }
+                    }
+                    if constexpr (HAS_OUT.value) oq = reinterpret_cast<float*>(reinterpret_cast<char*>(oq) + owb);
                 }
-            }
-            if (a.e.obits != nullptr) {
-                // lane 0 parks finished 16-byte units {s_lo, s_hi, m_lo, m_hi} (m == s: ReLU output) in the warp's
-                // staging area; lane p then stores pixel p's units: consecutive lanes -> consecutive units
-                uint4* sb = reinterpret_cast<uint4*>(stg);
+            };
+            using T_ = std::true_type;
+            using F_ = std::false_type;
+            if (has_res) { if (has_out) finish(T_{}, T_{}); else finish(T_{}, F_{}); }
+            else         { if (has_out) finish(F_{}, T_{}); else finish(F_{}, F_{}); }
+            if (want_bits) {
                 __syncwarp();
-                if (lane == 0) {
-#pragma unroll
-                    for (int p = 0; p < P; ++p)
-#pragma unroll
-                        for (int j = 0; j < C; j += 2) sb[p * (C / 2) + j / 2] = make_uint4(sw[p][j], sw[p][j + 1], sw[p][j], sw[p][j + 1]);
-                }
-                __syncwarp();
-                if (lane < P) {
-                    const size_t unit0 = (((size_t)n * a.e.ochunks + (blk0 >> 1)) * a.Ho + ho) * a.Wo + wo_first + lane;
-                    const size_t ustep = (size_t)a.Ho * a.Wo;
-#pragma unroll
-                    for (int j = 0; j < C; j += 2) a.e.obits[unit0 + (j / 2) * ustep] = sb[lane * (C / 2) + j / 2];
-                }
+                if (lane < P * (C / 2))
+                    a.e.obits[obits_base + (size_t)(ho * a.Wo + wo_first)] = reinterpret_cast<const uint4*>(stg)[lane];
                 __syncwarp();
             }
             continue;

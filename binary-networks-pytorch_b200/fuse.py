@@ -267,7 +267,8 @@ class FusedResNet(nn.Module):
             pool, conv_d, bn_d = plan.shortcut
             kw, wts = _conv_args(conv_d)
             one_kernel = (wts.kh == 1 and wts.kw == 1 and kw["stride"] == (1, 1) and kw["padding"] == (0, 0)
-                          and conv_d.groups == 1 and x.stride(1) == 1 and wts.c_in <= 1024 and wts.c_out <= 4096)
+                          and conv_d.groups == 1 and x.stride(1) == 1 and wts.c_in <= min(1024, runtime.shortcut_max_cin())
+                          and wts.c_out <= 4096)
             if one_kernel:
                 # pool + sign + conv1x1 + BN without the planes ever reaching HBM
                 shortcut = BF.shortcut(x, wts, _pair(pool.kernel_size)[0], pool.ceil_mode, bias=kw["bias"],

@@ -7,7 +7,8 @@ import os
 from ctypes import c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint32, c_void_p, POINTER
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libbnn_b200.so")
+# BNN_B200_LIB: load another build of the same library (kernel A/B experiments, scripts/build_variant.sh)
+LIB_PATH = os.environ.get("BNN_B200_LIB") or os.path.join(_HERE, "csrc", "libbnn_b200.so")
 
 F_STAGE_LDG = 1
 F_NO_CSA = 2

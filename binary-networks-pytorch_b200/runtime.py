@@ -15,7 +15,7 @@ the context managers.
 import contextlib
 import threading
 
-_defaults = {"floatsim": False, "flags": 0, "autotune": True}
+_defaults = {"floatsim": False, "flags": 0, "autotune": True, "shortcut_max_cin": 1024}
 _local = threading.local()
 _UNSET = object()
 
@@ -61,3 +61,11 @@ def autotune(enabled: bool = None) -> bool:
     if enabled is not None:
         _defaults["autotune"] = bool(enabled)
     return _get("autotune")
+
+
+def shortcut_max_cin(value: int = None) -> int:
+    """Largest input-channel count for which the fused engine runs a down-sampling shortcut as ONE kernel
+    (``bnn_shortcut_fwd``: pooled planes stay in shared memory); wider shortcuts take pool+pack and the tiled conv."""
+    if value is not None:
+        _defaults["shortcut_max_cin"] = int(value)
+    return _get("shortcut_max_cin")
