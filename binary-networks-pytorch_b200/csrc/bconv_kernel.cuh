@@ -69,17 +69,6 @@ __device__ __forceinline__ int msm2(int msm, int acc) {
     asm("mad.lo.s32 %0, %1, -2, %2;" : "=r"(r) : "r"(acc), "r"(msm));
     return r;
 }
-// acc + ones + 2 * twos.  BNN_ACC_IMAD: the doubling as an integer multiply-add (fma pipe) instead of a second ALU add --
-// LOP3 / IADD3 share the ALU pipe, which runs as loaded as the POPC pipe in the K loop
-__device__ __forceinline__ int acc_csa(int acc, int ones, int twos) {
-#ifdef BNN_ACC_IMAD
-    int r = acc + ones;
-    asm("mad.lo.s32 %0, %1, 2, %0;" : "+r"(r) : "r"(twos));
-    return r;
-#else
-    return acc + ones + 2 * twos;
-#endif
-}
 __device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (c & (a ^ b)); }
 
 // CTAs per SM the instance is compiled for.  1x1 kernels with small tiles keep few values live and their layers are
@@ -295,7 +284,7 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
                                        y2 = v2.w & (v2.y ^ t[2][j].y);
                         const int ones = __popc(x0 ^ x1 ^ x2) + __popc(y0 ^ y1 ^ y2);
                         const int twos = __popc(maj3(x0, x1, x2)) + __popc(maj3(y0, y1, y2));
-                        acc[p][j] = acc_csa(acc[p][j], ones, twos);
+                        acc[p][j] += ones + 2 * twos;
                     }
                 }
             }
@@ -347,7 +336,7 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
                                                y2 = v2.w & (v2.y ^ t[2][j].y);
                                 const int ones = __popc(x0 ^ x1 ^ x2) + __popc(y0 ^ y1 ^ y2);
                                 const int twos = __popc(maj3(x0, x1, x2)) + __popc(maj3(y0, y1, y2));
-                                acc[p][j] = acc_csa(acc[p][j], ones, twos);
+                                acc[p][j] += ones + 2 * twos;
                             }
                         }
                     } else {

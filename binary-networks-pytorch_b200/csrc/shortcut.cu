@@ -7,8 +7,12 @@
 //     bytes = 4 * C_in * H * W  +  4 * C_out * H_o * W_o   per image.
 // Phase 1 (warp = pooled pixel, lanes <-> input channels): k x k average in the pack kernel's exact operation order,
 // planes by ballot, all loads of two pixels in flight per warp.  Phase 2 (lanes <-> output channels): XNOR/AND +
-// POPC against the packed weights (L1-resident, <= 16 KB for ResNet-18), folded epilogue z = fma(k0, dot, k1) with
-// k0/k1 exactly as bconv_kernel's EPI 1 folds alpha, bias, post-scale and BatchNorm; NHWC store, 128 B per warp.
+// POPC against the packed weights, folded epilogue z = fma(k0, dot, k1) with k0/k1 exactly as bconv_kernel's EPI 1
+// folds alpha, bias, post-scale and BatchNorm; NHWC store, 128 B per warp.  In the compiled-chunk-count instances a
+// warp takes one 32-channel block at a time: the block's weight words for ALL chunks sit in registers (one L2 round
+// trip per block), the CTA's 32 pixels stream past them as broadcast LDS.128, and chunk triples go through the same
+// 3:2 carry-save adder as bconv_kernel (3 words, 2 POPC).  Layers with few pixels and many output channels (ResNet-50
+// layer3/4: 25 k / 6 k pixels, 1024 / 2048 channels) split the channel blocks over gridDim.y so every SM has work.
 // Bit-identical to the two-launch form (tests/test_gpu_fused.py).
 #include "common.cuh"
 
@@ -27,6 +31,8 @@ struct ShortcutArgs {
     float* out;                    // [n, ho, wo, c_out] contiguous
     int N, C, H, W, Ho, Wo, pool, Cout, nch, nblk32;
     int pixels;                    // n * ho * wo
+    int parts;                     // phase 2 (compiled chunk counts): pixel parts per channel block, 1 / 2 / 4 / 8
+    int ysplit;                    // gridDim.y: the 32-channel output blocks are divided among the CTAs of a pixel tile
 };
 
 // k x k average of one channel at one pooled pixel, the pack kernel's operation order (pack.cu)
@@ -151,11 +157,56 @@ shortcut_kernel(const __grid_constant__ ShortcutArgs a) {
     __syncthreads();
 
     // ---------------- phase 2: 1x1 binary conv + folded epilogue ----------------
-    // task = (32-channel output block, group of 8 pixels), round-robin over the warps; lanes <-> output channels.
-    // The block's weight words sit in registers (SC_WREG chunks per pass), the planes are broadcast LDS.128.
-    const int ntask = a.nblk32 * SC_NGRP;
+    const int blk_lo = (int)(((long long)a.nblk32 * blockIdx.y) / gridDim.y);
+    const int blk_hi = (int)(((long long)a.nblk32 * (blockIdx.y + 1)) / gridDim.y);
+    if constexpr (NCH > 0) {
+        // task = (32-channel block, pixel part): the block's weights of all chunks in registers, the part's pixels streamed
+        // past them.  parts > 1 only when there are fewer blocks than warps (host-chosen so that no warp idles).
+        const int nb = blk_hi - blk_lo, ppp = SC_PIX / a.parts;
+        for (int task = warp; task < nb * a.parts; task += SC_WARPS) {
+            const int part = task / nb, blk = blk_lo + (task - part * nb);
+            const int c = blk * 32 + lane;
+            const uint2* wrow = a.wbits + (size_t)blk * NCH * 32 + lane;
+            uint2 t[NCH];
+#pragma unroll
+            for (int u = 0; u < NCH; ++u) t[u] = __ldg(wrow + u * 32);
+            const float k0 = k0s[c], k1 = k1s[c];          // c < nblk32 * 32: the tables are padded
+            const bool c_ok = c < a.Cout;
+            const int p_lo = part * ppp;
+            const int p_hi = min(p_lo + ppp, a.pixels - pix0);           // warp-uniform
+            float* op = a.out + (size_t)pix0 * a.Cout + c;
+            constexpr int NTRI = NCH / 3;
+            // one pixel at a time: the dot of a (pixel, channel) is a scalar per lane, so nothing but the weights stays live
+#pragma unroll 2
+            for (int p = p_lo; p < p_hi; ++p) {
+                const uint4* vp = bits + p * NCH;
+                int dis = 0;
+#pragma unroll
+                for (int q = 0; q < NTRI; ++q) {
+                    const uint4 v0 = vp[3 * q], v1 = vp[3 * q + 1], v2 = vp[3 * q + 2];
+                    const uint32_t x0 = v0.z & (v0.x ^ t[3 * q].x), x1 = v1.z & (v1.x ^ t[3 * q + 1].x),
+                                   x2 = v2.z & (v2.x ^ t[3 * q + 2].x);
+                    const uint32_t y0 = v0.w & (v0.y ^ t[3 * q].y), y1 = v1.w & (v1.y ^ t[3 * q + 1].y),
+                                   y2 = v2.w & (v2.y ^ t[3 * q + 2].y);
+                    const int ones = __popc(x0 ^ x1 ^ x2) + __popc(y0 ^ y1 ^ y2);
+                    const int twos = __popc((x0 & x1) | (x2 & (x0 ^ x1))) + __popc((y0 & y1) | (y2 & (y0 ^ y1)));
+                    dis += ones + 2 * twos;
+                }
+#pragma unroll
+                for (int u = 3 * NTRI; u < NCH; ++u) {
+                    const uint4 v = vp[u];
+                    dis += __popc(v.z & (v.x ^ t[u].x)) + __popc(v.w & (v.y ^ t[u].y));
+                }
+                if (c_ok) op[(size_t)p * a.Cout] = __fmaf_rn(k0, (float)(msum[p] - 2 * dis), k1);
+            }
+        }
+        return;
+    }
+    // any chunk count: task = (32-channel output block, group of 8 pixels), round-robin over the warps; the block's
+    // weight words sit in registers (SC_WREG chunks per pass), the planes are broadcast LDS.128.
+    const int ntask = (blk_hi - blk_lo) * SC_NGRP;
     for (int task = warp; task < ntask; task += SC_WARPS) {
-        const int blk = task / SC_NGRP, i0 = (task - blk * SC_NGRP) * SC_GRP;
+        const int blk = blk_lo + task / SC_NGRP, i0 = (task % SC_NGRP) * SC_GRP;
         const int npix = min(SC_GRP, a.pixels - (pix0 + i0));  // <= 0 beyond the last pixel: warp-uniform
         if (npix <= 0) continue;
         const int c = blk * 32 + lane;
@@ -192,7 +243,7 @@ template <int NCH, int POOL>
 static cudaError_t launch_shortcut(const ShortcutArgs& a, size_t smem, unsigned ctas, cudaStream_t stream) {
     cudaError_t ce = cudaFuncSetAttribute((const void*)shortcut_kernel<NCH, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (ce != cudaSuccess) return ce;
-    shortcut_kernel<NCH, POOL><<<ctas, SC_WARPS * 32, smem, stream>>>(a);
+    shortcut_kernel<NCH, POOL><<<dim3(ctas, (unsigned)a.ysplit, 1), SC_WARPS * 32, smem, stream>>>(a);
     return cudaGetLastError();
 }
 
@@ -227,10 +278,35 @@ extern "C" int bnn_shortcut_fwd(const float* x, int64_t xs_n, int64_t xs_h, int6
     if ((long long)(h - 1) * xs_h + (long long)(w - 1) * xs_w + c_in >= 0x7fffffffLL || xs_h < 0 || xs_w < 0) return BNN_E_UNSUPPORTED;
     if ((long long)SC_PIX * c_out >= 0x7fffffffLL) return BNN_E_UNSUPPORTED;
     const unsigned ctas = (unsigned)((pixels + SC_PIX - 1) / SC_PIX);
+    // few pixel tiles, many channel blocks: divide the blocks over gridDim.y (each CTA repeats the cheap pool + pack) so
+    // that the SMs get equal numbers of CTAs; every CTA keeps at least one block per warp
+    a.ysplit = 1;
+    {
+        int sms = 148, dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (ctas < 4u * (unsigned)sms) {
+            double best = 1e30;
+            for (int ys = 1; ys <= 4 && a.nblk32 / ys >= SC_WARPS; ++ys) {
+                const double per_sm = (double)ctas * ys / sms;
+                const double cost = (double)((long long)(per_sm + 0.999999)) / per_sm * (1.0 + 0.04 * (ys - 1));
+                if (cost < best) { best = cost; a.ysplit = ys; }
+            }
+        }
+    }
     cudaStream_t stream = (cudaStream_t)stream_;
     const bool fast = !(flags & BNN_F_STAGE_LDG) && c_in % 64 == 0 &&
                       ((pool == 2 && h % 2 == 0 && w % 2 == 0) || pool == 1);
     cudaError_t ce;
+    {   // pixel parts per block so that (blocks of a CTA) x parts fills the 8 warps evenly
+        const int nb = a.nblk32 / a.ysplit;               // smallest share of a CTA
+        double best = 1e30;
+        a.parts = 1;
+        for (int parts = 1; parts <= SC_WARPS; parts *= 2) {
+            const double rounds = (double)nb * parts / SC_WARPS;
+            const double cost = (double)((long long)(rounds + 0.999999)) / rounds * (1.0 + 0.02 * (parts - 1));
+            if (cost < best) { best = cost; a.parts = parts; }
+        }
+    }
 #define BNN_SC(nch_, pool_) if (fast && a.nch == nch_ && pool == pool_) ce = launch_shortcut<nch_, pool_>(a, smem, ctas, stream); else
     BNN_SC(1, 2) BNN_SC(2, 2) BNN_SC(4, 2) BNN_SC(8, 2) BNN_SC(16, 2)
     BNN_SC(1, 1) BNN_SC(2, 1) BNN_SC(4, 1) BNN_SC(8, 1) BNN_SC(16, 1)

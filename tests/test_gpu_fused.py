@@ -117,7 +117,9 @@ def test_stem_kernel_bit_exact_vs_oracle(hw, flags):
     ((2, 64, 8, 8), 128, 2, True, "bn"), ((1, 70, 7, 9), 40, 2, True, "bn"), ((1, 64, 7, 9), 96, 2, False, "bn"),
     ((2, 128, 6, 6), 256, 1, True, "bn"), ((1, 64, 9, 7), 64, 3, True, "bn"), ((3, 256, 5, 5), 512, 2, True, "all"),
     ((2, 64, 8, 8), 128, 2, True, "none"), ((67, 64, 4, 4), 32, 2, True, "bn"), ((2, 256, 4, 4), 128, 2, True, "bn"),
-    ((1, 512, 4, 4), 64, 2, True, "all"), ((1, 1024, 2, 2), 96, 1, True, "bn"), ((3, 64, 5, 5), 256, 1, True, "bn")])
+    ((1, 512, 4, 4), 64, 2, True, "all"), ((1, 1024, 2, 2), 96, 1, True, "bn"), ((3, 64, 5, 5), 256, 1, True, "bn"),
+    # few pixels x many channel blocks: the blocks are divided over gridDim.y (ResNet-50 layer3 / layer4 shortcuts)
+    ((2, 1024, 4, 4), 2048, 2, True, "bn"), ((1, 512, 6, 6), 1024, 2, True, "all"), ((5, 256, 9, 9), 520, 2, True, "bn")])
 def test_shortcut_kernel_bit_exact_vs_two_launch_form_and_oracle(shape, c_out, k, ceil, extras):
     """AvgPool -> sign -> conv1x1 -> BN in one kernel == pack(pool) + fused conv (oracle and the two-launch CUDA path)."""
     rng = np.random.default_rng(11)
