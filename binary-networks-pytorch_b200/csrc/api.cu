@@ -3,10 +3,15 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 
 namespace bnn {
 static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("BNN_B200_NO_PDL"); return !(e && e[0] && e[0] != '0'); }();
+    return on;
+}
 }  // namespace bnn
 
 extern "C" int bnn_query(int what, int64_t* value) {

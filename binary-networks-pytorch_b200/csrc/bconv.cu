@@ -289,9 +289,9 @@ static int launch_bconv(const void* abits, const void* wbits, const bnn_conv_geo
     const int cout_tiles = ceil_div(a.nblk32, pl.C);
     if (units > 0x7fffffffLL || cout_tiles > 65535) return BNN_E_UNSUPPORTED;
     dim3 grid((unsigned)units, (unsigned)cout_tiles, 1);
-    fn<<<grid, pl.NW * 32, pl.smem, stream>>>(tmap, a);
+    ce = launch_pdl(fn, grid, dim3(pl.NW * 32), pl.smem, stream, tmap, a);
     count_launch(1);
-    return (int)cudaGetLastError();
+    return (int)(ce != cudaSuccess ? ce : cudaGetLastError());
 }
 
 }  // namespace bnn

@@ -113,6 +113,10 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
     const int nk32 = a.nk * 32;
 
     // ---------------- stage the activation window + weight tile ----------------
+    // Programmatic dependent launch: this CTA may become resident while the previous kernel still drains its last wave.
+    // Up to pdl_wait() it touches no global memory at all (barrier init, tensor-map prefetch from the parameter space,
+    // index arithmetic): weights and per-channel constants may have been written by the kernel just before this one.
+    pdl_launch_dependents();
     if (!a.stage_ldg) {
         if (threadIdx.x == 0) {
             prefetch_tensormap(&tmap);
@@ -120,6 +124,7 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
             fence_mbar_init();
         }
         __syncthreads();
+        pdl_wait();
         if (threadIdx.x == 0) {
             const int nvalid = min(C, a.nblk32 - blk0);
             mbar_expect_tx(bar, a.act_bytes + (unsigned)nvalid * a.w_bytes);
@@ -128,6 +133,7 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
                 bulk_load_1d(wsm + (size_t)j * nk32, a.wbits + (size_t)(blk0 + j) * a.w_blk_stride, a.w_bytes, bar);
         }
     } else {
+        pdl_wait();
         const int units = a.nch * a.BH * a.BW;
         for (int i = threadIdx.x; i < units; i += blockDim.x) {
             const int c = i % a.BW;

@@ -64,6 +64,30 @@ __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------------------------------
+// Every hot-path kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization: its CTAs may become resident
+// while the previous kernel in the stream is still draining its last wave, run the part of their prologue that touches
+// no global memory (barrier init, tensor-map prefetch, TMEM allocation, index arithmetic), and block in pdl_wait() --
+// griddepcontrol.wait: the previous grid has completed and its writes are visible -- before the first global read or
+// write (even weights may have been packed by the kernel just before).  pdl_launch_dependents() at the top of a kernel lets ITS successor
+// do the same.  Works inside CUDA-graph capture (programmatic dependency edges).  BNN_B200_NO_PDL=1 launches plainly.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();      // api.cu: false when BNN_B200_NO_PDL is set
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // process-wide count of kernels this library has launched (bnn_query(BNN_Q_LAUNCH_COUNT))
 void count_launch(int n = 1);
 

@@ -33,6 +33,8 @@ pack_act_kernel(const float* __restrict__ x, long long sn, long long sc, long lo
                 int N, int C, int H, int W, int nch, int pool, int Hin, int Win,
                 const float* __restrict__ pre_scale, const float* __restrict__ pre_shift, int pre_relu,
                 uint4* __restrict__ abits) {
+    pdl_launch_dependents();      // programmatic dependent launch (common.cuh): no global access before pdl_wait()
+    pdl_wait();
     const long long total = (long long)N * nch * H * W;       // H, W: OUTPUT (pooled) plane size
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
@@ -90,6 +92,8 @@ pack_act_cl_kernel(const float* __restrict__ x, long long sn, long long sh, long
                    int N, int C, int H, int W, int nch, int pool, int Hin, int Win,
                    const float* __restrict__ pre_scale, const float* __restrict__ pre_shift, int pre_relu,
                    uint32_t* __restrict__ abits) {
+    pdl_launch_dependents();      // programmatic dependent launch (common.cuh): no global access before pdl_wait()
+    pdl_wait();
     const long long pixels = (long long)N * H * W;
     const long long pix = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (pix >= pixels) return;                               // warp-uniform
@@ -146,6 +150,8 @@ template <int NCH>
 __global__ void __launch_bounds__(256)
 pack_act_cl_dense_kernel(const float* __restrict__ x, int pixels, int HW, const float* __restrict__ pre_scale,
                          const float* __restrict__ pre_shift, int pre_relu, uint4* __restrict__ abits) {
+    pdl_launch_dependents();      // programmatic dependent launch (common.cuh): no global access before pdl_wait()
+    pdl_wait();
     constexpr int C = 64 * NCH, NB = 2 * NCH;
     const int lane = threadIdx.x & 31;
     const int pix0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * PL_PPW;
@@ -190,7 +196,7 @@ static int launch_pack_dense(const float* x, long long pixels, int HW, const flo
                              int pre_relu, void* abits, cudaStream_t stream) {
     const long long warps = (pixels + PL_PPW - 1) / PL_PPW, blocks = (warps + 7) / 8;
     if (blocks > 0x7fffffffLL || pixels > 0x7fffffffLL - PL_PPW) return BNN_E_UNSUPPORTED;
-    pack_act_cl_dense_kernel<NCH><<<(unsigned)blocks, 256, 0, stream>>>(x, (int)pixels, HW, pre_scale, pre_shift, pre_relu, (uint4*)abits);
+    launch_pdl(pack_act_cl_dense_kernel<NCH>, dim3((unsigned)blocks), dim3(256), 0, stream, x, (int)pixels, HW, pre_scale, pre_shift, pre_relu, (uint4*)abits);
     count_launch(1);
     return (int)cudaGetLastError();
 }
@@ -208,6 +214,8 @@ __global__ void __launch_bounds__(256)
 avgpool2_pack_cl_kernel(const float* __restrict__ x, long long pooled_pixels, int H, int W, int Ho, int Wo,
                         const float* __restrict__ pre_scale, const float* __restrict__ pre_shift, int pre_relu,
                         float* __restrict__ pooled, uint4* __restrict__ abits) {
+    pdl_launch_dependents();      // programmatic dependent launch (common.cuh): no global access before pdl_wait()
+    pdl_wait();
     constexpr int C = 64 * NCH, NB = 2 * NCH;
     const int lane = threadIdx.x & 31;
     const long long pp0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * AP_PPW;
@@ -257,7 +265,7 @@ static int launch_avgpool2_pack(const float* x, int n, int h, int w, const float
     const int ho = h / 2, wo = w / 2;
     const long long pp = (long long)n * ho * wo, warps = (pp + AP_PPW - 1) / AP_PPW, blocks = (warps + 7) / 8;
     if (blocks > 0x7fffffffLL) return BNN_E_UNSUPPORTED;
-    avgpool2_pack_cl_kernel<NCH><<<(unsigned)blocks, 256, 0, stream>>>(x, pp, h, w, ho, wo, pre_scale, pre_shift, pre_relu, pooled, (uint4*)abits);
+    launch_pdl(avgpool2_pack_cl_kernel<NCH>, dim3((unsigned)blocks), dim3(256), 0, stream, x, pp, h, w, ho, wo, pre_scale, pre_shift, pre_relu, pooled, (uint4*)abits);
     count_launch(1);
     return (int)cudaGetLastError();
 }
@@ -383,16 +391,16 @@ static int launch_pack(const float* x, int64_t sn, int64_t sc, int64_t sh, int64
         const long long pixels = (long long)n * ho * wo;
         const long long blocks = (pixels + 7) / 8;
         if (blocks > 0x7fffffffLL) return BNN_E_UNSUPPORTED;
-        pack_act_cl_kernel<<<(unsigned)blocks, threads, 0, stream>>>(x, sn, sh, sw, n, c, ho, wo, nch, pool, h, w,
-                                                                    pre_scale, pre_shift, pre_relu, (uint32_t*)abits);
+        launch_pdl(pack_act_cl_kernel, dim3((unsigned)blocks), dim3(threads), 0, stream, x, sn, sh, sw, n, c, ho, wo, nch, pool, h, w,
+                   pre_scale, pre_shift, pre_relu, (uint32_t*)abits);
         count_launch(1);
         return (int)cudaGetLastError();
     }
     const long long total = (long long)n * nch * ho * wo;
     const long long blocks = (total + threads - 1) / threads;
     if (blocks > 0x7fffffffLL) return BNN_E_UNSUPPORTED;
-    pack_act_kernel<<<(unsigned)blocks, threads, 0, stream>>>(x, sn, sc, sh, sw, n, c, ho, wo, nch, pool, h, w,
-                                                            pre_scale, pre_shift, pre_relu, (uint4*)abits);
+    launch_pdl(pack_act_kernel, dim3((unsigned)blocks), dim3(threads), 0, stream, x, sn, sc, sh, sw, n, c, ho, wo, nch, pool, h, w,
+               pre_scale, pre_shift, pre_relu, (uint4*)abits);
     count_launch(1);
     return (int)cudaGetLastError();
 }

@@ -60,6 +60,8 @@ shortcut_kernel(const __grid_constant__ ShortcutArgs a) {
     float* k0s = reinterpret_cast<float*>(msum + SC_PIX);                    // [nblk32 * 32]
     float* k1s = k0s + a.nblk32 * 32;
 
+    pdl_launch_dependents();      // programmatic dependent launch (common.cuh): no global access before pdl_wait()
+    pdl_wait();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int pix0 = blockIdx.x * SC_PIX;
     constexpr bool FAST = POOL > 0;
@@ -243,8 +245,8 @@ template <int NCH, int POOL>
 static cudaError_t launch_shortcut(const ShortcutArgs& a, size_t smem, unsigned ctas, cudaStream_t stream) {
     cudaError_t ce = cudaFuncSetAttribute((const void*)shortcut_kernel<NCH, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (ce != cudaSuccess) return ce;
-    shortcut_kernel<NCH, POOL><<<dim3(ctas, (unsigned)a.ysplit, 1), SC_WARPS * 32, smem, stream>>>(a);
-    return cudaGetLastError();
+    ce = launch_pdl(shortcut_kernel<NCH, POOL>, dim3(ctas, (unsigned)a.ysplit, 1), dim3(SC_WARPS * 32), smem, stream, a);
+    return ce != cudaSuccess ? ce : cudaGetLastError();
 }
 
 }  // namespace bnn

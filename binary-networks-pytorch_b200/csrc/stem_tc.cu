@@ -190,6 +190,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) stem_tc_kernel(const __grid_con
     unsigned char* ring = smem + TC_OFF_RING;
     float* vbuf = reinterpret_cast<float*>(smem + TC_OFF_VBUF);
 
+    pdl_launch_dependents();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     long long* const tl = ((a.dbg & 16) && blockIdx.x == 0) ? reinterpret_cast<long long*>(a.obits2) : nullptr;
     const long long lo_row = a.total_rows * blockIdx.x / gridDim.x, hi_row = a.total_rows * (blockIdx.x + 1) / gridDim.x;
@@ -201,11 +202,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) stem_tc_kernel(const __grid_con
             for (int i = 0; i < 2; ++i) { mbar_init(vfull + i, TC_EPI_WARPS); mbar_init(vempty + i, TC_OUT_WARPS); }
             mbar_init(bbar, 1);
             fence_mbar_init();
-            mbar_expect_tx(bbar, (unsigned)TC_B_BYTES);
-            bulk_load_1d(b_s, a.wops, (unsigned)TC_B_BYTES, bbar);
         }
         __syncwarp();
         tc05::tmem_alloc<512>(tmem_slot);
+    }
+    // programmatic dependent launch (common.cuh): barrier init and the TMEM allocation above overlap the previous kernel's
+    // tail; nothing before this line touches global memory
+    pdl_wait();
+    if (warp == TC_MMA_WARP && lane == 0) {
+        mbar_expect_tx(bbar, (unsigned)TC_B_BYTES);
+        bulk_load_1d(b_s, a.wops, (unsigned)TC_B_BYTES, bbar);
     }
     const int sx = input_log2_scale(a);
     for (int i = tid; i < 384; i += TC_THREADS) {
@@ -538,6 +544,8 @@ __global__ void stem_tc_pack_weight_kernel(const float* __restrict__ w, float w_
 
 // max |x| over a tensor (NaN ignored), atomically merged into *amax (which the caller zeroes first)
 __global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ x, long long count, float* __restrict__ amax) {
+    pdl_launch_dependents();      // programmatic dependent launch (common.cuh): no global access before pdl_wait()
+    pdl_wait();
     float m = 0.0f;
     const long long n4 = count >> 2, stride = (long long)gridDim.x * blockDim.x;
     const float4* x4 = reinterpret_cast<const float4*>(x);
@@ -584,7 +592,7 @@ extern "C" int bnn_amax_f32(const float* x, int64_t count, float* amax, void* st
     if (ce != cudaSuccess) return (int)ce;
     const long long want = (count / 16 + 255) / 256;
     const int blocks = (int)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
-    amax_kernel<<<blocks, 256, 0, stream>>>(x, (long long)count, amax);
+    launch_pdl(amax_kernel, dim3(blocks), dim3(256), 0, stream, x, (long long)count, amax);
     count_launch(1);
     return (int)cudaGetLastError();
 }
@@ -630,11 +638,11 @@ extern "C" int bnn_stem_tc_run(const bnn_stem_tc_params* p, uint32_t flags, void
     const unsigned ctas = (unsigned)(a.total_rows < sms ? a.total_rows : sms);
     cudaStream_t st = (cudaStream_t)stream_;
     if (pool) {
-        if (p->x_dtype) stem_tc_kernel<true, 1><<<ctas, TC_THREADS, TC_SMEM, st>>>(a);
-        else stem_tc_kernel<true, 0><<<ctas, TC_THREADS, TC_SMEM, st>>>(a);
+        if (p->x_dtype) launch_pdl(stem_tc_kernel<true, 1>, dim3(ctas), dim3(TC_THREADS), TC_SMEM, st, a);
+        else launch_pdl(stem_tc_kernel<true, 0>, dim3(ctas), dim3(TC_THREADS), TC_SMEM, st, a);
     } else {
-        if (p->x_dtype) stem_tc_kernel<false, 1><<<ctas, TC_THREADS, TC_SMEM, st>>>(a);
-        else stem_tc_kernel<false, 0><<<ctas, TC_THREADS, TC_SMEM, st>>>(a);
+        if (p->x_dtype) launch_pdl(stem_tc_kernel<false, 1>, dim3(ctas), dim3(TC_THREADS), TC_SMEM, st, a);
+        else launch_pdl(stem_tc_kernel<false, 0>, dim3(ctas), dim3(TC_THREADS), TC_SMEM, st, a);
     }
     count_launch(1);
     return (int)cudaGetLastError();
