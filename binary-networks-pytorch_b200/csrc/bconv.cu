@@ -25,6 +25,8 @@
 //   * inner op per 32 bit-MACs: LOP3 (m & (s ^ t)) + POPC; the CSA mode folds
 //     the three taps of a 3-wide kernel row with a 3:2 carry-save adder
 //     (2 more LOP3) so that 3 words cost 2 POPC -- POPC is the slow pipe.
+#include <cstdio>
+#include <cstdlib>
 #include "bconv_kernel.cuh"
 
 #include <algorithm>
@@ -341,6 +343,8 @@ extern "C" int bnn_bconv2d_tune(const void* abits, const void* wbits, const bnn_
     cudaStream_t stream = (cudaStream_t)stream_;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
+    // BNN_B200_TUNE_LOG=1: one stderr line per timed candidate (which plans exist for a layer and how far apart they are)
+    static const bool tune_log = [] { const char* e = getenv("BNN_B200_TUNE_LOG"); return e && e[0] && e[0] != '0'; }();
     float best = 1e30f;
     Plan best_pl = tries[0];
     for (const Plan& pl : tries) {
@@ -356,6 +360,10 @@ extern "C" int bnn_bconv2d_tune(const void* abits, const void* wbits, const bnn_
             cudaEventElapsedTime(&ms, e0, e1);
             ms_min = ms < ms_min ? ms : ms_min;
         }
+        if (tune_log)
+            fprintf(stderr, "[bnn tune] n%d c%d->%d %dx%d k%d s%d epi%d | P%d C%d TH%d NW%d ctas %lld smem %zu | %.4f ms\n", g.n,
+                    g.c_in, g.c_out, g.h, g.w, g.kh, g.stride_h, epi, pl.P, pl.C, pl.TH, pl.NW,
+                    (long long)g.n * pl.tiles_h * pl.tiles_w * ceil_div(ceil_div(g.c_out, 32), pl.C), pl.smem, ms_min);
         if (ms_min < best) { best = ms_min; best_pl = pl; }
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);

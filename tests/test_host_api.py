@@ -158,6 +158,11 @@ def test_runtime_switches_are_process_wide_with_thread_local_override():
     finally:
         runtime.floatsim(False)
     assert runtime.floatsim() is False
+    assert runtime.shortcut_max_cin() == 1024          # engine tuning knob: one-kernel shortcuts up to 1024 input channels
+    try:
+        assert runtime.shortcut_max_cin(128) == 128
+    finally:
+        runtime.shortcut_max_cin(1024)
 
 
 def test_floatsim_matches_reference_known_answers(golden_units):
