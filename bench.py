@@ -352,6 +352,7 @@ def main():
                     help="fused engine's stem kernel: tcgen05 (tc), mma.sync split-fp16 (mma) or the fp32 fma chain")
     ap.add_argument("--layers-out", default=None, help="write the per-layer table to this JSON file")
     ap.add_argument("--shortcut-max-cin", type=int, default=-1, help="experiment knob: bnn_b200.runtime.shortcut_max_cin")
+    ap.add_argument("--no-overlap", action="store_true", help="A/B: shortcuts on the main stream instead of a second one")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     cfgd = CONFIGS[args.config]
@@ -391,7 +392,7 @@ def main():
     import copy
     model = copy.deepcopy(model_cpu).to(dev)
     from bnn_b200 import fuse
-    engine = model if args.no_fuse else fuse.optimize(model, stem=args.stem)   # public API: bnn_b200.fuse.optimize
+    engine = model if args.no_fuse else fuse.optimize(model, stem=args.stem, overlap_shortcuts=not args.no_overlap)   # public API: bnn_b200.fuse.optimize
     B = args.batch
     # every rank gets its own images (seed 1000 + rank): rank 0 can regenerate any rank's rows for the parity check
     x_host = torch.randn(B, 3, RES, RES, generator=torch.Generator().manual_seed(1000 + rank)).pin_memory()
@@ -561,7 +562,7 @@ def main():
         e2e_u8 = None
         if hasattr(engine, "set_uint8_input") and not args.no_fuse and args.stem in ("auto", "tc"):
             mean, std = (123.675, 116.28, 103.53), (58.395, 57.12, 57.375)
-            eng8 = fuse.optimize(model, stem="tc").set_uint8_input(mean, std)
+            eng8 = fuse.optimize(model, stem="tc", overlap_shortcuts=not args.no_overlap).set_uint8_input(mean, std)
             xu_host = torch.randint(0, 256, (B, RES, RES, 3), dtype=torch.uint8,
                                     generator=torch.Generator().manual_seed(2000 + rank)).pin_memory()
             pipe8 = HostPipeline(eng8, xu_host, dev, use_graphs=(graph is not None),
@@ -644,9 +645,16 @@ def main():
             hooks = [m.register_forward_hook(lambda mod, i, o, n=n: order.append(n))
                      for n, m in model.named_modules() if isinstance(m, bnn.layers.Conv2d)]
             reps = max(3, min(args.steps, 10))
+            # launches are timed one by one on one stream here: the engine's second stream (shortcuts concurrent with the
+            # first convs of their block) is switched off for this pass -- the step time above includes the overlap
+            overlap = getattr(engine, "overlap_shortcuts", None)
+            if overlap is not None:
+                engine.overlap_shortcuts = False
             for _ in range(reps):
                 engine(x_dev)                      # rank-local: no collective in this pass
             torch.cuda.synchronize()
+            if overlap is not None:
+                engine.overlap_shortcuts = overlap
             BF.pack_activations, BF.bconv2d, BF.bconv2d_fused, BF.shortcut = orig_pack, orig_conv, orig_fused, orig_short
             for h in hooks:
                 h.remove()

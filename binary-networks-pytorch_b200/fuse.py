@@ -208,9 +208,18 @@ class _StemPlan:
 class FusedResNet(nn.Module):
     """Inference engine over a prepared ResNet; same call signature as the wrapped model."""
 
-    def __init__(self, model: nn.Module, fuse_stem: bool = True, stem: str = "auto", input_range: float = None) -> None:
+    def __init__(self, model: nn.Module, fuse_stem: bool = True, stem: str = "auto", input_range: float = None,
+                 overlap_shortcuts: bool = True) -> None:
         super().__init__()
         self.stem_kernel_used = "torch"
+        # the down-sampling shortcut of a block depends only on the block input: it is launched on a second stream and
+        # joined before the conv that adds it, so its (HBM / latency bound) CTAs fill the SM slots that the (POPC bound)
+        # conv1 / conv2 launches of the same block leave idle in their ramps and tails.  Inside a CUDA-graph capture the
+        # fork / join become graph edges.
+        self.overlap_shortcuts = bool(overlap_shortcuts)
+        self._side_streams = {}
+        self._shapes_seen = set()       # the first forward of an input shape autotunes tile plans: no concurrency then
+        self._overlap_now = False
         if stem not in ("auto", "tc", "mma", "fma"):
             raise ValueError("stem must be 'auto', 'tc' (tcgen05, split fp16), 'mma' (mma.sync, split fp16) or 'fma' "
                              f"(fp32 fma chain), got {stem!r}")
@@ -262,6 +271,7 @@ class FusedResNet(nn.Module):
             return y, bits
         if xbits is None:
             xbits = BF.pack_activations(x, pre=self._entry_affine(plan))
+        join = None
         # shortcut branch
         if plan.shortcut is not None:
             pool, conv_d, bn_d = plan.shortcut
@@ -271,8 +281,23 @@ class FusedResNet(nn.Module):
                           and wts.c_out <= 4096)
             if one_kernel:
                 # pool + sign + conv1x1 + BN without the planes ever reaching HBM
-                shortcut = BF.shortcut(x, wts, _pair(pool.kernel_size)[0], pool.ceil_mode, bias=kw["bias"],
-                                       post=kw["post"], bn=bn_d.get(), use_alpha=kw["use_alpha"])
+                bn_pair = bn_d.get()
+                if self.overlap_shortcuts and self._overlap_now and x.is_cuda:
+                    main = torch.cuda.current_stream(x.device)
+                    side = self._side_streams.get(x.device)
+                    if side is None:
+                        side = self._side_streams[x.device] = torch.cuda.Stream(x.device)
+                    k = _pair(pool.kernel_size)[0]
+                    out = torch.empty(BF.shortcut_out_shape(x, wts, k, pool.ceil_mode), dtype=torch.float32, device=x.device,
+                                      memory_format=torch.channels_last)         # allocated on the main stream
+                    side.wait_stream(main)                                         # fork: the block input is complete
+                    with torch.cuda.stream(side):
+                        shortcut = BF.shortcut(x, wts, k, pool.ceil_mode, bias=kw["bias"], post=kw["post"], bn=bn_pair,
+                                               use_alpha=kw["use_alpha"], out=out)
+                    join = (main, side)
+                else:
+                    shortcut = BF.shortcut(x, wts, _pair(pool.kernel_size)[0], pool.ceil_mode, bias=kw["bias"],
+                                           post=kw["post"], bn=bn_pair, use_alpha=kw["use_alpha"])
             else:
                 pooled = BF.pack_activations(x, pool=_pair(pool.kernel_size)[0], ceil_mode=pool.ceil_mode)
                 shortcut, _ = BF.bconv2d_fused(pooled, wts, bn=bn_d.get(), channels_last=True, **kw)
@@ -285,6 +310,8 @@ class FusedResNet(nn.Module):
             code, prelu = _activation_spec(act_mod)
             kw, wts = _conv_args(conv)
             slope = _slope(prelu, conv.out_channels, dev)
+            if i == last and join is not None:
+                join[0].wait_stream(join[1])            # join: the launch below adds the shortcut
             if plan.kind == "basic":
                 # conv -> bn -> act -> [sign of the next conv]; the last conv adds the shortcut before its activation
                 if i < last:
@@ -324,6 +351,9 @@ class FusedResNet(nn.Module):
         with torch.no_grad():
             bits = None
             first = self.plans[0] if self.plans else None
+            shape_key = (tuple(x.shape), x.dtype)
+            self._overlap_now = shape_key in self._shapes_seen
+            self._shapes_seen.add(shape_key)
             if x.dtype == torch.uint8:
                 if getattr(self, "u8_norm", None) is None:
                     raise native.NativeError("uint8 input: call engine.set_uint8_input(mean, std) first")
@@ -483,16 +513,19 @@ class FusedHBlockNet(nn.Module):
             return m.fc(torch.flatten(m.avgpool(x), 1))
 
 
-def optimize(model: nn.Module, fuse_stem: bool = True, stem: str = "auto", input_range: float = None) -> nn.Module:
+def optimize(model: nn.Module, fuse_stem: bool = True, stem: str = "auto", input_range: float = None,
+             overlap_shortcuts: bool = True) -> nn.Module:
     """Return the fused inference engine for ``model`` if its layout is recognised, else ``model``.
     ``stem``: "tc" (= "auto") the stem kernel on the tcgen05 tensor cores, "mma" the same arithmetic on mma.sync (both:
     split-fp16 operands, fp32-level accuracy), "fma" the fp32 fma-chain stem kernel (bit-identical to the oracle's
     summation order).  ``input_range``: a bound on |x| the caller guarantees (e.g. 3.0 for normalised images) -- the
     split-fp16 stems then use a fixed input scale; by default (None) they measure max|x| on the device every forward
-    (one extra pass over the input, graph-capturable), so inputs of any magnitude are handled."""
+    (one extra pass over the input, graph-capturable), so inputs of any magnitude are handled.  ``overlap_shortcuts``:
+    launch each down-sampling shortcut on a second stream, concurrently with the first convs of its block."""
     needed = ("conv1", "layer1", "layer2", "layer3", "layer4", "avgpool", "fc")
     if all(hasattr(model, k) for k in needed):
-        engine = FusedResNet(model, fuse_stem=fuse_stem, stem=stem, input_range=input_range)
+        engine = FusedResNet(model, fuse_stem=fuse_stem, stem=stem, input_range=input_range,
+                             overlap_shortcuts=overlap_shortcuts)
         if engine.fused_blocks:
             return engine
     if all(hasattr(model, k) for k in ("conv1", "bn1", "relu", "block0", "pool", "blocks", "avgpool", "fc")):

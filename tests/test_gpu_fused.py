@@ -402,6 +402,39 @@ def test_fused_engine_tracks_batchnorm_updates_and_graph_capture():
     assert torch.equal(out, y1)
 
 
+@pytest.mark.parametrize("arch", ["resnet18", "resnet50"])
+def test_shortcuts_on_a_second_stream_change_nothing(arch):
+    """The engine launches every down-sampling shortcut on a second stream, concurrently with the first convs of its
+    block (fork after the block input, join before the conv that adds it): same bits as the single-stream order, in
+    eager mode and inside a captured graph, over repeated runs (a missing join would show up as a race)."""
+    torch.manual_seed(3)
+    if arch == "resnet18":
+        m = build("basic_relu")
+    else:
+        m = bnn.prepare_binary_model(workloads.resnet50(), xnor_cfg(BasicScaleBinarizer), ignore_layers_name=["_first_", "_last_"])
+        workloads.randomize_batchnorm(m)
+    m = m.eval().to(DEV)
+    serial, overlapped = fuse.optimize(m, overlap_shortcuts=False), fuse.optimize(m, overlap_shortcuts=True)
+    x = torch.randn(8, 3, 128, 128, device=DEV)
+    with torch.no_grad():
+        want = serial(x)
+        overlapped(x)                                      # first forward of a shape tunes tile plans: single stream
+        assert overlapped._overlap_now is False
+        for _ in range(5):
+            got = overlapped(x)
+            assert overlapped._overlap_now is True
+            assert torch.equal(got, want)
+        g, s_ = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+        with torch.cuda.stream(s_):
+            torch.cuda.current_stream().synchronize()
+            with torch.cuda.graph(g, stream=s_):
+                out = overlapped(x)
+        for _ in range(5):
+            g.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(out, want)
+
+
 @pytest.mark.parametrize("pre", [False, True], ids=["bottleneck", "prebottleneck"])
 def test_fused_engine_resnet50_blocks(pre):
     """BASELINE configs[2] through the fused engine: 16 (Pre)Bottleneck blocks, 52 binarized convs, learned XNOR-Net++
