@@ -60,6 +60,7 @@ struct ConvArgs {
 //                                                k2 = PReLU slope, k3/k4 = next layer's pre-sign affine
 enum { EP_N = 5 };
 
+// (a dropped read-only load instead of the prefetch instruction was measured slower: the register it names is waited on)
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ int word_dis(uint32_t m, uint32_t s, uint32_t t) { return __popc(m & (s ^ t)); }
