@@ -101,5 +101,11 @@ def test_sass_contains_tma_and_popc():
     sass = subprocess.run([cuobjdump, "-sass", native.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in sass
     for mnemonic in ("UTMALDG", "UBLKCP", "POPC", "LOP3", "HMMA.16816.F32", "FFMA2",      # + the mma.sync / fma stems
-                     "UTCHMMA", "LDTM", "UTCBAR"):                                        # tcgen05 stem: MMA, TMEM load, commit
+                     "UTCHMMA", "LDTM", "UTCBAR",                                         # tcgen05 stem: MMA, TMEM load, commit
+                     "ACQBULK", "PREEXIT"):                                               # programmatic dependent launch
         assert mnemonic in sass, mnemonic
+    # the lean fused epilogue (EPI 3 instances) converts its integer dots without the conversion pipe, which POPC saturates
+    blocks = sass.split("Function : ")[1:]
+    lean = [b for b in blocks if b.startswith("_ZN3bnn12bconv_kernel") and b.split("\n", 1)[0].rstrip().endswith("ELi3EEEv14CUtensorMap_stNS_8ConvArgsE")]
+    assert len(lean) >= 20
+    assert not any("I2FP.F32.S32" in b for b in lean)
