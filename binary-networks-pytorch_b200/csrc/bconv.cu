@@ -258,6 +258,7 @@ static int launch_bconv(const void* abits, const void* wbits, const bnn_conv_geo
     a.SH = g.stride_h; a.SW = g.stride_w; a.PH = g.pad_h; a.PW = g.pad_w; a.DH = g.dil_h; a.DW = g.dil_w;
     a.Ho = Ho; a.Wo = Wo;
     a.nch = ceil_div(g.c_in, 64); a.nk = a.nch * g.kh * g.kw; a.nblk32 = ceil_div(g.c_out, 32);
+    if ((long long)a.nk * 64 >= (1LL << 22)) return BNN_E_UNSUPPORTED;     // epilogues convert |dot| < 2^22 by bit pattern
     a.TH = pl.TH; a.TW = pl.TW; a.BH = pl.BH; a.BW = pl.BW; a.gpr = pl.gpr; a.G = pl.G;
     a.tiles_h = pl.tiles_h; a.tiles_w = pl.tiles_w;
     a.act_bytes = (unsigned)((size_t)a.nch * pl.BH * pl.BW * 16);

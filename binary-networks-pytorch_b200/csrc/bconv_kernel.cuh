@@ -194,7 +194,7 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
                     cnt += __popc(v.z) + __popc(v.w);
                 }
             }
-        ms_s[i] = cnt + (LEAN ? MAGIC_I : 0);
+        ms_s[i] = cnt + MAGIC_I;               // every epilogue converts (ms + magic) - 2 acc by bit pattern, see MAGIC_I
     }
     __syncthreads();
 
@@ -525,7 +525,7 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
                 // reference order (conv.py:92-97, ops.py:136,202): (alpha*dot + bias) * alpha_post
 #pragma unroll
                 for (int p = 0; p < P; ++p)
-                    v[p] = __fmul_rn(__fadd_rn(__fmul_rn(k0, (float)(ms[p] - 2 * acc[p][j])), k1), k2);
+                    v[p] = __fmul_rn(__fadd_rn(__fmul_rn(k0, __fadd_rn(__int_as_float(msm2(ms[p], acc[p][j])), -MAGIC_F)), k1), k2);
             } else {
                 // ---- fused epilogue.  `full` groups (all P pixels and all 32 channels valid) take the
                 //      predicate-free path; strides are 32-bit here (the host checked the tensors fit)
@@ -558,7 +558,7 @@ bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ C
                     }
                 }
 #pragma unroll
-                for (int p = 0; p < P; ++p) v[p] = __fmaf_rn(k0, (float)(ms[p] - 2 * acc[p][j]), k1);
+                for (int p = 0; p < P; ++p) v[p] = __fmaf_rn(k0, __fadd_rn(__int_as_float(msm2(ms[p], acc[p][j])), -MAGIC_F), k1);
                 if (has_res && !a.e.res_after_act) {
 #pragma unroll
                     for (int p = 0; p < P; ++p) v[p] = __fadd_rn(v[p], res[p]);
