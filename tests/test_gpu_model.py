@@ -175,3 +175,41 @@ def test_config34_logits_match_the_real_reference(which, golden_cfg34):
     print(which, "per-layer vs reference", rel_err(per_layer, ref), "fused vs reference", rel_err(fused, ref))
     assert rel_err(per_layer, ref) <= 1e-3 and rel_err(fused, ref) <= 1e-3
     assert (np.argmax(per_layer, 1) == np.argmax(ref, 1)).all() and (np.argmax(fused, 1) == np.argmax(ref, 1)).all()
+
+
+def test_reference_resnet_with_dabnn_stem_through_the_reference_entry_point():
+    """the reference's own ResNet with ``stem_type='dabnn'`` (bnn/models/resnet.py:10-47), built from the
+    byte-compiled reference (oracle/_ref), converted by the REFERENCE's prepare_binary_model with our module mapping.
+    The fused engine keeps the DaBNN stem as torch ops and fuses the eight residual blocks; its logits match the same
+    model with the reference's own float-simulated layers on the CPU."""
+    from oracle import build as oracle_build
+    ref = oracle_build.load_ref()
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    import importlib
+    from bnn_b200 import fuse
+    rops = importlib.import_module("bnn_ref.ops")
+    rres = importlib.import_module("bnn_ref.models.resnet")
+    rcfg = ref.BConfig(activation_pre_process=rops.BasicInputBinarizer, activation_post_process=ref.Identity,
+                       weight_pre_process=rops.XNORWeightBinarizer.with_args(compute_alpha=True, center_weights=True))
+    torch.manual_seed(7)
+    plain = rres.resnet18(stem_type="dabnn")
+    workloads.randomize_batchnorm(plain, seed=2)
+    state = {k: v.clone() for k, v in plain.state_dict().items()}
+    ours = ref.prepare_binary_model(plain, rcfg, modules_mapping=bnn.mapping_for_reference(ref),
+                                    ignore_layers_name=["_first_", "_last_"]).eval().to(DEV)
+    theirs = rres.resnet18(stem_type="dabnn")
+    theirs.load_state_dict(state)
+    theirs = ref.prepare_binary_model(theirs, rcfg, ignore_layers_name=["_first_", "_last_"]).eval()
+    engine = fuse.optimize(ours)
+    assert isinstance(engine, fuse.FusedResNet) and engine.fused_blocks == 8 and not engine.stem.ok
+    x = torch.randn(2, 3, 96, 96, generator=torch.Generator().manual_seed(11))
+    with torch.no_grad():
+        want = theirs(x).numpy()
+        got = engine(x.to(DEV)).cpu().numpy()
+        again = engine(x.to(DEV)).cpu().numpy()            # second forward: shortcuts on the second stream
+        per_layer = ours(x.to(DEV)).cpu().numpy()
+    assert engine.stem_kernel_used == "torch"
+    assert np.array_equal(got, again)
+    assert rel_err(per_layer, want) <= 1e-3
+    assert rel_err(got, want) <= 1e-3
