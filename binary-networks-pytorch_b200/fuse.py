@@ -477,13 +477,32 @@ class FusedHBlockNet(nn.Module):
         if self.stem is not None and self.stem.ok:
             self.stem.bn.key = self.stem.key = self.stem.mma_key = self.stem.tc_key = None
 
+    def set_uint8_input(self, mean, std) -> "FusedHBlockNet":
+        """Accept decoded images as uint8 [n,h,w,3] tensors (see ``FusedResNet.set_uint8_input``)."""
+        mean = [float(v) for v in mean]
+        istd = [float(torch.tensor(1.0, dtype=torch.float32) / torch.tensor(float(v), dtype=torch.float32)) for v in std]
+        if len(mean) != 3 or len(istd) != 3:
+            raise ValueError("mean and std must have three entries")
+        self.u8_norm = (mean, istd)
+        return self
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         m = self.model
         if m.training:
             raise native.NativeError("FusedHBlockNet is an inference engine: call model.eval()")
         with torch.no_grad():
             p0 = self.plans[0]
-            if (self.stem is not None and self.stem.ok and p0.ok and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
+            if x.dtype == torch.uint8:
+                if getattr(self, "u8_norm", None) is None:
+                    raise native.NativeError("uint8 input: call engine.set_uint8_input(mean, std) first")
+                if not (self.stem is not None and self.stem.ok and p0.ok and x.is_cuda and x.dim() == 4 and x.shape[3] == 3):
+                    raise native.NativeError("uint8 [n,h,w,3] input needs the tcgen05 stem kernel and a fused first block")
+                self.stem_kernel_used = "bnn_stem_tc_fwd(no pool, uint8)"
+                nx2 = p0.shortcut[0].get() if p0.shortcut is not None else None
+                res = BF.stem_tc(x.contiguous(), self.stem.tc_weight(), self.stem.bn.get(), nx=p0.bns[0].get(), nx_relu=True,
+                                 nx2=nx2, nx2_relu=True, pool=False, u8_norm=self.u8_norm)
+                x = run_hblock(p0, res[0], res[1], res[2] if nx2 is not None else None)
+            elif (self.stem is not None and self.stem.ok and p0.ok and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
                     and x.shape[1] == 3 and min(x.shape[2:]) >= 7):
                 # conv7x7/2 + BN + ReLU on the tcgen05 stem kernel (no max-pool): NHWC fp32 + the planes of block0's
                 # conv1 (bn1-ReLU-sign) and of its shortcut conv (its own BatchNorm) in one launch

@@ -477,6 +477,27 @@ def test_fused_hblock_net_matches_twin_and_unfused():
     assert rel_err(got, want) <= 1e-3 and rel_err(eager, want) <= 1e-3
 
 
+def test_fused_hblock_net_accepts_uint8_images():
+    """The Hierarchical-Block engine on decoded uint8 images: bit-identical to its own fp32 path on the torch-normalised
+    tensor with the same (range-derived) input scale."""
+    torch.manual_seed(0)
+    m = bnn.prepare_binary_model(workloads.HBlockNet(depth=2), xnor_cfg(), ignore_layers_name=["_first_", "_last_"])
+    workloads.randomize_batchnorm(m, seed=1)
+    m = m.eval().to(DEV)
+    mean, std = (123.675, 116.28, 103.53), (58.395, 57.12, 57.375)
+    engine = fuse.optimize(m).set_uint8_input(mean, std)
+    assert isinstance(engine, fuse.FusedHBlockNet)
+    xu = torch.randint(0, 256, (2, 64, 64, 3), dtype=torch.uint8, device=DEV)
+    istd = torch.tensor([float(torch.tensor(1.0) / torch.tensor(v)) for v in std], device=DEV)
+    xf = ((xu.float() - torch.tensor(mean, device=DEV)) * istd).permute(0, 3, 1, 2).contiguous()
+    bound = max(max(abs(0.0 - mu), abs(255.0 - mu)) / sd for mu, sd in zip(mean, std))
+    with torch.no_grad():
+        yu = engine(xu)
+        assert engine.stem_kernel_used == "bnn_stem_tc_fwd(no pool, uint8)"
+        yf = fuse.optimize(m, input_range=bound)(xf)
+    assert torch.equal(yu, yf)
+
+
 def test_unrecognised_models_are_returned_unchanged():
     m = nn.Sequential(nn.Conv2d(3, 64, 3), nn.ReLU(), nn.Conv2d(64, 64, 3))
     m = bnn.prepare_binary_model(m, xnor_cfg(), ignore_layers_name=["_first_"]).eval().to(DEV)
