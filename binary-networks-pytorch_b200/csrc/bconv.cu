@@ -137,7 +137,12 @@ static int enumerate_plans(const bnn_conv_geom& g, int Ho, int Wo, uint32_t flag
             // cycles per 32-bit word per warp: fewer channels per lane -> more shared-memory loads per word
             double cpw = (C == 4 ? 1.0 : C == 2 ? 1.25 : 1.5) * (window ? 1.0 : 1.12) * (P == 4 ? 1.06 : 1.0);
             const double round_work = (double)P * C * nk * 2.0 * cpw + 60.0 * P * C;   // main loop + epilogue
-            for (int NW = 8; NW >= 7; --NW) {
+            // warps per CTA: 8 / 7 (two or three resident CTAs), or fewer -- smaller CTAs, more of them resident: about the
+            // same number of warps per SM, but the prologues, epilogue stalls and tails of four to eight CTAs interleave
+            // instead of two (registers per thread are those of the instance; shared memory decides whether they all fit)
+            const int nws[4] = {8, 7, 4, 2};        // (5 and 3 warps were measured too: never the best, r02al tuner log)
+            for (int nwi = 0; nwi < 4; ++nwi) {
+                const int NW = nws[nwi];
                 for (int TH = 1; TH <= Ho; ++TH) {
                     const int BH = (TH - 1) * g.stride_h + (g.kh - 1) * g.dil_h + 1;
                     if (BH > 256) break;
@@ -146,8 +151,11 @@ static int enumerate_plans(const bnn_conv_geom& g, int Ho, int Wo, uint32_t flag
                     const int G = TH * gpr, rounds = ceil_div(G, NW);
                     if (rounds > 12 && TH > 1) break;
                     // resident CTAs: what the instance is compiled for (register budget), capped by shared memory
-                    int occ = bconv_min_ctas(P, C, kwt);
+                    // resident CTAs by registers (the instance is compiled for bconv_min_ctas CTAs of 256 threads)
+                    const int by_regs = NW >= 7 ? bconv_min_ctas(P, C, kwt) : (bconv_min_ctas(P, C, kwt) * 8) / NW;
+                    int occ = by_regs < 32 ? by_regs : 32;
                     while (occ > 1 && smem * occ > 226 * 1024) --occ;
+                    if (NW < 7 && occ < by_regs) continue;       // small CTAs only pay when all of them fit
                     const long long ctas = (long long)g.n * ceil_div(Ho, TH) * tiles_w * cout_tiles;
                     const long long slots = (long long)sms * occ;
                     const double waves = (double)((ctas + slots - 1) / slots);
@@ -327,7 +335,7 @@ extern "C" int bnn_bconv2d_tune(const void* abits, const void* wbits, const bnn_
     std::vector<Plan> tries;
     for (const Cand& c : cands) {
         bool seen = false;
-        for (const Plan& t : tries) seen |= (t.P == c.pl.P && t.C == c.pl.C);
+        for (const Plan& t : tries) seen |= (t.P == c.pl.P && t.C == c.pl.C && (t.NW >= 7 ? 8 : t.NW) == (c.pl.NW >= 7 ? 8 : c.pl.NW));
         if (!seen) tries.push_back(c.pl);
     }
     const size_t families = tries.size();

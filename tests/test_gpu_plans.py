@@ -171,7 +171,7 @@ def test_every_tile_family_bit_exact_vs_oracle(gm, ename):
         if inst["epi"] != EXPECT_EPI[ename]:
             # e.g. lean epilogues with C == 1 do not exist; those families run EPI 2 -- still compared below
             assert ename.startswith("lean") and inst["epi"] == 2, (ename, P, C, inst)
-        for warps in (0, 7):
+        for warps in (0, 7, 4):                     # best / 7-warp / 4-warp (half-size CTA) candidate of the family
             try:
                 out, bits = BF.bconv2d_fused(act, wts, bias=_d(d["bias"]), post=_d(d["post"]), bn=pair(d["bn"]),
                                              residual=res, residual_after_act=d["res_after"], activation=d["act"],
@@ -179,7 +179,7 @@ def test_every_tile_family_bit_exact_vs_oracle(gm, ename):
                                              nx=pair(d["nx"]), stride=stride, padding=pad, flags=flags, channels_last=fused and cl,
                                              nx_relu=d["nx_relu"], bits_before_residual=d["bits_pre"], plan=(P, C, 0, warps))
             except native.NativeError:
-                assert warps == 7                          # a 7-warp variant of this family may not exist
+                assert warps != 0                          # a 7- or 4-warp variant of this family may not exist
                 continue
             ran += 1
             assert np.array_equal(out.cpu().numpy(), want_out), (gm["name"], ename, P, C, warps)
