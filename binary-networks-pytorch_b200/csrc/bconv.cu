@@ -152,7 +152,7 @@ static int enumerate_plans(const bnn_conv_geom& g, int Ho, int Wo, uint32_t flag
                     if (rounds > 12 && TH > 1) break;
                     // resident CTAs: what the instance is compiled for (register budget), capped by shared memory
                     // resident CTAs by registers (the instance is compiled for bconv_min_ctas CTAs of 256 threads)
-                    const int by_regs = NW >= 7 ? bconv_min_ctas(P, C, kwt) : (bconv_min_ctas(P, C, kwt) * 8) / NW;
+                    const int by_regs = NW >= 7 ? bconv_min_ctas(P, C, kwt) : bconv_warps_per_sm(P, C, kwt) / NW;
                     int occ = by_regs < 32 ? by_regs : 32;
                     while (occ > 1 && smem * occ > 226 * 1024) --occ;
                     if (NW < 7 && occ < by_regs) continue;       // small CTAs only pay when all of them fit

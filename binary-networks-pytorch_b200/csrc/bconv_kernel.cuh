@@ -75,10 +75,24 @@ __device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) { r
 // CTAs per SM the instance is compiled for.  1x1 kernels with small tiles keep few values live and their layers are
 // latency-bound (short K loops between a TMA prologue and an HBM-fed epilogue): three resident CTAs (80 registers)
 // overlap those phases better than two; everything else gets the full 128 registers.
+#ifndef BNN_CONV_REGS_C2
+#define BNN_CONV_REGS_C2 96        // registers per thread of the C <= 2 instances: 5 resident 4-warp CTAs = 20 warps per SM (128: 16)
+#endif
 __host__ __device__ constexpr int bconv_min_ctas(int P, int C, int KWT) { return (KWT == 1 && P * C <= 16) ? 3 : 2; }
+// registers per thread an instance is compiled for, and the warps per SM the register file then holds
+__host__ __device__ constexpr int bconv_regs(int P, int C, int KWT) {
+    return (KWT == 1 && P * C <= 16) ? 80 : (C <= 2 ? BNN_CONV_REGS_C2 : 128);
+}
+__host__ __device__ constexpr int bconv_warps_per_sm(int P, int C, int KWT) {
+    return (KWT == 1 && P * C <= 16) ? 24 : 2048 / bconv_regs(P, C, KWT);
+}
 
 template <int P, int C, int KWT, int SWT, int MODE, int EPI>
+#if BNN_CONV_REGS_C2 == 128
 __global__ void __launch_bounds__(256, bconv_min_ctas(P, C, KWT))
+#else
+__global__ void __maxnreg__(bconv_regs(P, C, KWT))
+#endif
 bconv_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ ConvArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     // EPI 0: reference epilogue.  EPI 1: fused epilogue, any strides.  EPI 2: fused epilogue with channel-contiguous
