@@ -177,3 +177,27 @@ def test_tile_planner_invariants(gm):
     assert tiles_per_image * pl["TH"] * pl["TW"] >= ho * wo                       # every output pixel is in some tile
     assert pl["channel_tiles"] * 32 * pl["C"] >= gm["c_out"]                        # every output channel in some block
     assert (pl["channel_tiles"] - 1) * 32 * pl["C"] < gm["c_out"]                   # ... and no empty channel tile
+
+
+def test_small_cta_plans_are_listed_only_when_all_of_them_fit():
+    """Host only (bnn_conv_plan_list): 4- and 2-warp CTAs are candidates with proportionally more CTAs resident -- the same
+    warps per SM as the 8-warp form of the instance -- and only when shared memory holds all of them."""
+    from bnn_b200 import native
+
+    def plans(n, ci, h, w, co, k, s, p):
+        return native.conv_plan_list(native.ConvGeom(n, ci, h, w, co, k, k, s, s, p, p, 1, 1), 0)
+
+    for geom in ((256, 64, 56, 56, 64, 3, 1, 1), (256, 512, 7, 7, 512, 3, 1, 1), (128, 256, 14, 14, 1024, 1, 1, 0)):
+        for p in plans(*geom):
+            assert p["warps"] in (8, 7, 4, 2)
+            if p["warps"] < 7:
+                one_by_one = p["kw_inst"] == 1 and p["P"] * p["C"] <= 16
+                regs = 80 if one_by_one else (96 if p["C"] <= 2 else 128)       # bconv_regs() of bconv_kernel.cuh
+                warps_per_sm = 24 if one_by_one else 2048 // regs
+                resident = min(32, warps_per_sm // p["warps"])
+                assert resident * p["smem"] <= 226 * 1024, p
+    # layer1 (4.6 KB of weights per CTA): every (P, C) family has 4- and 2-warp forms; layer4 with C = 4 (73 KB): none
+    l1 = {(p["P"], p["C"], p["warps"]) for p in plans(256, 64, 56, 56, 64, 3, 1, 1)}
+    assert {(8, 2, 4), (8, 2, 2), (7, 2, 4)} <= l1
+    l4 = {(p["P"], p["C"], p["warps"]) for p in plans(256, 512, 7, 7, 512, 3, 1, 1)}
+    assert not any(c == 4 and w < 7 for (_, c, w) in l4) and (7, 2, 4) in l4
